@@ -1,0 +1,1153 @@
+// engine.cu -- CUDA engine behind include/ppm.h (sm_100a, f64, no FMA).
+//
+// Kernels (one per hot-path computation of SURVEY.md section 8a):
+//   k_intersect        calc_intersection probe                  tracer.rs:306-350
+//   k_emit             Light::generate_photon probe             light.rs:67-91
+//   k_trace_photons    emit + bounce loop + record compaction   tracer.rs:31-125
+//   k_bbox/k_cell_key/k_scatter/k_hist  photon map = uniform grid, radix sorted
+//                      (replaces the kd-tree of photonmap.rs:23-29)
+//   k_gather           estimate_radiance                        tracer.rs:179-216
+//   k_within           kdtree.within probe                      tracer.rs:180
+//   k_gen_rays         Camera::generate_ray                     camera.rs:58-75
+//   k_eye_expand       trace_ray recursion -> gather-node list  tracer.rs:129-177
+//   k_direct_light     get_radiance_from_light / illuminated    tracer.rs:263-290
+//   k_combine          bsdf combination + pass accumulation     surface.rs:135-206, averager2.rb:49-62
+#include "dev_core.cuh"
+
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+// ===========================================================================
+// kernels
+// ===========================================================================
+
+__global__ void k_intersect(const __grid_constant__ DevScene sc, const double* __restrict__ rays6, int64_t n,
+                            int32_t* __restrict__ hit, double* __restrict__ t, double* __restrict__ pos3,
+                            double* __restrict__ nrm3, int32_t* __restrict__ io) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  D3 p = ld3(rays6 + i * 6), d = ld3(rays6 + i * 6 + 3);
+  Isect is;
+  bool ok = nearest_hit(sc, p, d, is);
+  hit[i] = ok ? is.obj : -1;
+  if (t) t[i] = ok ? is.t : 0.0;
+  if (pos3) st3(pos3 + i * 3, ok ? is.pos : mk3(0, 0, 0));
+  if (nrm3) st3(nrm3 + i * 3, ok ? is.nvec : mk3(0, 0, 0));
+  if (io) io[i] = ok ? is.io : 0;
+}
+
+struct LightSplit {
+  int64_t first[PPM_MAX_LIGHTS + 1];   // first[l] = global index of light l's first photon
+};
+__device__ __forceinline__ int light_of(const LightSplit& ls, int nlights, int64_t i) {
+  int l = 0;
+  while (l + 1 < nlights && i >= ls.first[l + 1]) ++l;
+  return l;
+}
+
+__global__ void k_emit(const __grid_constant__ DevScene sc, const __grid_constant__ LightSplit ls, uint64_t seed,
+                       uint32_t pass, int64_t n, ppm_photon* __restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Philox rng(seed, pass, PPM_DOMAIN_PHOTON, (uint64_t)i, 0);
+  int wl; D3 pos, dir;
+  generate_photon(sc.lights[light_of(ls, sc.nlights, i)], rng, wl, pos, dir);
+  st3(out[i].pos, pos); st3(out[i].dir, dir);
+  out[i].wl = wl; out[i]._pad = 0;
+}
+
+// Unsorted photon records as produced by tracing / import.
+struct RecBuf {
+  double* pos3;     // [cap][3]
+  double* dir3;     // [cap][3]
+  uint8_t* wl;      // [cap]
+  uint64_t* tag;    // [cap]  (photon index << 4) | depth
+};
+
+// One thread = one photon path (its own Philox stream).  Records are appended
+// with one atomic per warp (warp-aggregated).
+__global__ void __launch_bounds__(256)
+k_trace_photons(const __grid_constant__ DevScene sc, const __grid_constant__ LightSplit ls, uint64_t seed, uint32_t pass,
+                int uc, int64_t n, RecBuf rec, unsigned long long* __restrict__ counter, unsigned long long cap) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool alive = i < n;
+  Philox rng(seed, pass, PPM_DOMAIN_PHOTON, (uint64_t)(alive ? i : 0), 0);
+  int wl = 0, medium = -1;
+  D3 pos = mk3(0, 0, 0), dir = mk3(1, 0, 0);
+  if (alive) generate_photon(sc.lights[light_of(ls, sc.nlights, i)], rng, wl, pos, dir);
+  const unsigned lane = threadIdx.x & 31u;
+  for (int l = 0; l < PPM_MAX_TRACE; ++l) {
+    if (!__any_sync(0xffffffffu, alive)) break;
+    Isect is;
+    bool store = false;
+    D3 in_dir = dir;
+    if (alive) {
+      if (!nearest_hit(sc, pos, dir, is)) {
+        alive = false;
+      } else {
+        store = (uc == 0 || l > 0) && surf_store_photon(sc.mats[is.mat]);
+        D3 nd;
+        bool go = photon_bounce(sc, is, wl, dir, rng, medium, nd);
+        pos = is.pos;
+        if (go) dir = nd; else alive = false;
+      }
+    }
+    unsigned m = __ballot_sync(0xffffffffu, store);
+    if (m) {
+      unsigned long long base = 0;
+      if (lane == (unsigned)(__ffs(m) - 1)) base = atomicAdd(counter, (unsigned long long)__popc(m));
+      base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+      if (store) {
+        unsigned long long slot = base + __popc(m & ((1u << lane) - 1u));
+        if (slot < cap) {
+          st3(rec.pos3 + slot * 3, is.pos);
+          st3(rec.dir3 + slot * 3, in_dir);
+          rec.wl[slot] = (uint8_t)wl;
+          rec.tag[slot] = ((uint64_t)i << 4) | (uint64_t)l;
+        }
+      }
+    }
+  }
+}
+
+__global__ void k_import(const ppm_photon* __restrict__ in, uint64_t n, RecBuf rec) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  for (int k = 0; k < 3; ++k) { rec.pos3[i * 3 + k] = in[i].pos[k]; rec.dir3[i * 3 + k] = in[i].dir[k]; }
+  rec.wl[i] = (uint8_t)in[i].wl;
+  rec.tag[i] = i << 4;
+}
+__global__ void k_export(RecBuf rec, uint64_t n, ppm_photon* __restrict__ out) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  for (int k = 0; k < 3; ++k) { out[i].pos[k] = rec.pos3[i * 3 + k]; out[i].dir[k] = rec.dir3[i * 3 + k]; }
+  out[i].wl = rec.wl[i]; out[i]._pad = 0;
+}
+
+// ---- photon map: uniform grid, cell edge >= r, cells linearised x-fastest ----
+struct Grid {
+  double org[3];
+  double inv_cell;
+  int32_t nx, ny, nz;
+  uint32_t ncells;
+};
+__device__ __forceinline__ unsigned long long enc_ord(double v) {
+  unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+static inline double dec_ord(unsigned long long e) {
+  unsigned long long b = (e & 0x8000000000000000ull) ? (e & 0x7fffffffffffffffull) : ~e;
+  double v;
+  std::memcpy(&v, &b, 8);
+  return v;
+}
+// mm[0..2] = min xyz, mm[3..5] = max xyz (order-preserving encoding)
+__global__ void k_bbox(const double* __restrict__ pos3, uint64_t n, unsigned long long* __restrict__ mm) {
+  unsigned long long lo[3] = {~0ull, ~0ull, ~0ull}, hi[3] = {0ull, 0ull, 0ull};
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+    for (int k = 0; k < 3; ++k) {
+      unsigned long long e = enc_ord(pos3[i * 3 + k]);
+      lo[k] = e < lo[k] ? e : lo[k];
+      hi[k] = e > hi[k] ? e : hi[k];
+    }
+  for (int k = 0; k < 3; ++k) {
+    for (int o = 16; o > 0; o >>= 1) {
+      unsigned long long a = __shfl_xor_sync(0xffffffffu, lo[k], o), b = __shfl_xor_sync(0xffffffffu, hi[k], o);
+      lo[k] = a < lo[k] ? a : lo[k];
+      hi[k] = b > hi[k] ? b : hi[k];
+    }
+    if ((threadIdx.x & 31) == 0) { atomicMin(&mm[k], lo[k]); atomicMax(&mm[3 + k], hi[k]); }
+  }
+}
+__device__ __forceinline__ int cell_coord(const Grid& g, double p, int ax) {
+  return (int)floor((p - g.org[ax]) * g.inv_cell);
+}
+// sort key = (cell << 38) | (tag & (2^38-1)): photons ordered by cell, then by
+// (photon index, depth) -> the map is bit-reproducible whatever order the
+// tracing atomics produced.
+__global__ void k_cell_key(Grid g, const double* __restrict__ pos3, const uint64_t* __restrict__ tag, uint64_t n,
+                           uint64_t* __restrict__ keys, uint32_t* __restrict__ vals, uint32_t* __restrict__ hist) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int cx = cell_coord(g, pos3[i * 3], 0), cy = cell_coord(g, pos3[i * 3 + 1], 1), cz = cell_coord(g, pos3[i * 3 + 2], 2);
+  cx = min(max(cx, 0), g.nx - 1); cy = min(max(cy, 0), g.ny - 1); cz = min(max(cz, 0), g.nz - 1);
+  uint32_t c = ((uint32_t)cz * (uint32_t)g.ny + (uint32_t)cy) * (uint32_t)g.nx + (uint32_t)cx;
+  keys[i] = ((uint64_t)c << 38) | (tag[i] & ((1ull << 38) - 1ull));
+  vals[i] = (uint32_t)i;
+  atomicAdd(&hist[c], 1u);
+}
+// Sorted structure-of-arrays photon map.
+struct MapSoA {
+  double *px, *py, *pz, *dx, *dy, *dz;
+  uint8_t* wl;
+  uint32_t* orig;   // index in the unsorted (import/export) order
+};
+__global__ void k_scatter(RecBuf rec, const uint32_t* __restrict__ vals, uint64_t n, MapSoA m) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t s = vals[i];
+  m.px[i] = rec.pos3[(uint64_t)s * 3]; m.py[i] = rec.pos3[(uint64_t)s * 3 + 1]; m.pz[i] = rec.pos3[(uint64_t)s * 3 + 2];
+  m.dx[i] = rec.dir3[(uint64_t)s * 3]; m.dy[i] = rec.dir3[(uint64_t)s * 3 + 1]; m.dz[i] = rec.dir3[(uint64_t)s * 3 + 2];
+  m.wl[i] = rec.wl[s];
+  m.orig[i] = s;
+}
+
+// ---- gather -------------------------------------------------------------------
+// tracer.rs:198-216
+__device__ __forceinline__ double filter_cone(double d, double rmax) {
+  const double K_CONE = 1.1;
+  const double FAC_K = 1.0 - 2.0 / (3.0 * K_CONE);
+  double d2 = sqrt(d / rmax) / K_CONE;
+  return d2 > 1.0 ? 0.0 : (1.0 - d2) / FAC_K;
+}
+__device__ __forceinline__ double filter_gauss(double d, double rmax) {
+  const double ALPHA = 0.918, BETA = 1.953, E_BETA = 1.0 - 0.14184788965323, CORR = 0.5;
+  double e_r = 1.0 - exp(-BETA * d / (rmax * 2.0));
+  return e_r > E_BETA ? 0.0 : ALPHA * (1.0 - e_r / E_BETA) + CORR;
+}
+
+// v1: one thread per query, photons read straight from the sorted SoA (L1/L2).
+template <int FILTER>
+__global__ void __launch_bounds__(128)
+k_gather(Grid g, const uint32_t* __restrict__ cell_start, MapSoA m, const double* __restrict__ qpos3,
+         const double* __restrict__ qnrm3, int64_t n, double power, double r2, double* __restrict__ rgb3,
+         uint32_t* __restrict__ counts, unsigned long long* __restrict__ sum_k) {
+  int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t cnt = 0;
+  if (q < n) {
+    const double qx = qpos3[q * 3], qy = qpos3[q * 3 + 1], qz = qpos3[q * 3 + 2];
+    const D3 nv = ld3(qnrm3 + q * 3);
+    double rr = 0.0, rg = 0.0, rb = 0.0;
+    int cx = cell_coord(g, qx, 0), cy = cell_coord(g, qy, 1), cz = cell_coord(g, qz, 2);
+    int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.nx - 1);
+    if (x0 <= x1) {
+      for (int z = max(cz - 1, 0); z <= min(cz + 1, g.nz - 1); ++z)
+        for (int y = max(cy - 1, 0); y <= min(cy + 1, g.ny - 1); ++y) {
+          uint32_t row = ((uint32_t)z * (uint32_t)g.ny + (uint32_t)y) * (uint32_t)g.nx;
+          uint32_t b = cell_start[row + x0], e = cell_start[row + x1 + 1];
+          for (uint32_t j = b; j < e; ++j) {
+            // squared_euclidean: ((qx-px)^2 + (qy-py)^2) + (qz-pz)^2, member iff d2 <= r2
+            double ax = qx - m.px[j], ay = qy - m.py[j], az = qz - m.pz[j];
+            double d2 = (ax * ax + ay * ay) + az * az;
+            if (d2 <= r2) {
+              ++cnt;
+              double wt = FILTER == PPM_FILTER_NONE ? 1.0 : (FILTER == PPM_FILTER_CONE ? filter_cone(d2, r2) : filter_gauss(d2, r2));
+              // photon_to_radiance, optics.rs:224-233
+              double cos0 = (nv.x * m.dx[j] + nv.y * m.dy[j]) + nv.z * m.dz[j];
+              double pw2 = cos0 < 0.0 ? (wt * power) * -cos0 : 0.0;
+              int w = m.wl[j];
+              if (w == 0) rr = rr + pw2; else if (w == 1) rg = rg + pw2; else rb = rb + pw2;
+            }
+          }
+        }
+    }
+    const double s = (1.0 / PPM_PI) / r2;     // rad * (ONE_PI / radius), tracer.rs:193
+    rgb3[q * 3] = rr * s; rgb3[q * 3 + 1] = rg * s; rgb3[q * 3 + 2] = rb * s;
+    if (counts) counts[q] = cnt;
+  }
+  if (sum_k) {
+    unsigned long long c = cnt;
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(sum_k, c);
+  }
+}
+
+__global__ void k_within(Grid g, const uint32_t* __restrict__ cell_start, MapSoA m, const double* __restrict__ qpos3,
+                         int64_t n, double r2, uint32_t* __restrict__ idx, uint32_t* __restrict__ counts, uint32_t cap) {
+  int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n) return;
+  const double qx = qpos3[q * 3], qy = qpos3[q * 3 + 1], qz = qpos3[q * 3 + 2];
+  uint32_t cnt = 0;
+  int cx = cell_coord(g, qx, 0), cy = cell_coord(g, qy, 1), cz = cell_coord(g, qz, 2);
+  int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.nx - 1);
+  if (x0 <= x1)
+    for (int z = max(cz - 1, 0); z <= min(cz + 1, g.nz - 1); ++z)
+      for (int y = max(cy - 1, 0); y <= min(cy + 1, g.ny - 1); ++y) {
+        uint32_t row = ((uint32_t)z * (uint32_t)g.ny + (uint32_t)y) * (uint32_t)g.nx;
+        uint32_t b = cell_start[row + x0], e = cell_start[row + x1 + 1];
+        for (uint32_t j = b; j < e; ++j) {
+          double ax = qx - m.px[j], ay = qy - m.py[j], az = qz - m.pz[j];
+          double d2 = (ax * ax + ay * ay) + az * az;
+          if (d2 <= r2) {
+            if (cnt < cap) idx[(uint64_t)q * cap + cnt] = m.orig[j];
+            ++cnt;
+          }
+        }
+      }
+  counts[q] = cnt;
+}
+
+// ---- camera ---------------------------------------------------------------------
+__device__ __forceinline__ void camera_ray(const ppm_camera& cam, int64_t pix, uint64_t seed, uint32_t pass, D3& pos, D3& dir) {
+  Philox rng(seed, pass, PPM_DOMAIN_EYE, (uint64_t)pix, 0);
+  double y = (double)(pix / cam.xreso), x = (double)(pix % cam.xreso);
+  D3 blur = mk3(0.0, 0.0, 0.0);
+  if (cam.blur) {
+    double r1 = rng.range(-0.5, 0.5);
+    double r2 = rng.range(-0.5, 0.5);
+    blur = r1 * ld3(cam.eex) + r2 * ld3(cam.eey);
+  }
+  double r3 = 0.0, r4 = 0.0;
+  if (cam.progressive && cam.antialias) { r3 = rng.range(-0.5, 0.5); r4 = rng.range(-0.5, 0.5); }
+  pos = ld3(cam.eye_pos) + blur;
+  D3 ed = ((ld3(cam.origin) + (x + r3) * ld3(cam.esx)) + (y + r4) * ld3(cam.esy)) - blur;
+  dir = mk3(1.0, 0.0, 0.0);
+  normalize(ed, dir);
+}
+__global__ void k_gen_rays(const __grid_constant__ ppm_camera cam, uint64_t seed, uint32_t pass, int64_t n,
+                           double* __restrict__ rays6) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  D3 p, d;
+  camera_ray(cam, i, seed, pass, p, d);
+  st3(rays6 + i * 6, p); st3(rays6 + i * 6 + 3, d);
+}
+
+// ---- eye path expansion ------------------------------------------------------------
+// The binary recursion of trace_ray becomes a per-pixel depth-first walk with an
+// explicit stack and a top-down RGB throughput W.  Each visited node that has a
+// non-zero diffuse coefficient becomes one "gather node" (hit point, normal,
+// W (.) kd).  WRITE=false counts nodes per pixel, WRITE=true (after an exclusive
+// scan) writes them at deterministic offsets in reference recursion order.
+struct EyeNodes {
+  double* pos3;     // [N][3] hit position     (gather / direct-light query)
+  double* nrm3;     // [N][3] facing normal
+  double* w3;       // [N][3] W (.) kd
+};
+struct EyeStack {
+  D3 pos, dir, W;
+  int medium, depth;
+  uint32_t node;
+};
+template <bool WRITE>
+__global__ void __launch_bounds__(128)
+k_eye_expand(const __grid_constant__ DevScene sc, const __grid_constant__ ppm_camera cam, const double* __restrict__ rays6,
+             int64_t n, int64_t first_pixel, uint64_t seed, uint32_t pass, uint32_t* __restrict__ node_count,
+             const uint32_t* __restrict__ node_off, EyeNodes nodes, double* __restrict__ emit3,
+             unsigned long long* __restrict__ n_visited) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t pix = first_pixel + i;
+  EyeStack st[PPM_MAX_TRACE + 2];
+  int sp = 0;
+  if (rays6) { st[0].pos = ld3(rays6 + i * 6); st[0].dir = ld3(rays6 + i * 6 + 3); }
+  else camera_ray(cam, pix, seed, pass, st[0].pos, st[0].dir);
+  st[0].W = mk3(1.0, 1.0, 1.0); st[0].medium = -1; st[0].depth = 0; st[0].node = 1;
+  sp = 1;
+  D3 emit = mk3(0.0, 0.0, 0.0);
+  uint32_t cnt = 0, visited = 0;
+  const uint32_t off = WRITE ? node_off[i] : 0;
+  const double SR_HALF = 1.0 / (2.0 * PPM_PI);
+  while (sp > 0) {
+    EyeStack e = st[--sp];
+    if (e.depth >= PPM_MAX_TRACE) continue;
+    Isect is;
+    if (!nearest_hit(sc, e.pos, e.dir, is)) continue;
+    ++visited;
+    Philox rng(seed, pass, PPM_DOMAIN_EYE, (uint64_t)pix, e.node);
+    EyeNode nd;
+    eye_node(sc, is, e.dir, e.medium, rng, nd);
+    const ppm_material& m = sc.mats[is.mat];
+    emit = emit + cmul(e.W, ld3(m.emittance) * SR_HALF);
+    D3 wd = cmul(e.W, nd.kd);
+    if (any_nz(wd)) {
+      if (WRITE) {
+        uint64_t s = (uint64_t)off + cnt;
+        st3(nodes.pos3 + s * 3, is.pos); st3(nodes.nrm3 + s * 3, is.nvec); st3(nodes.w3 + s * 3, wd);
+      }
+      ++cnt;
+    }
+    // push the refract child first so that the reflect subtree is walked first
+    // (reference order: si is evaluated before ti, tracer.rs:152-171)
+    if (nd.refract) {
+      D3 wt = cmul(e.W, nd.kt);
+      if (any_nz(wt) && sp < PPM_MAX_TRACE + 2) {
+        EyeStack& c = st[sp++];
+        c.pos = is.pos; c.dir = nd.tdir; c.W = wt; c.medium = nd.t_medium; c.depth = e.depth + 1; c.node = e.node * 2 + 1;
+      }
+    }
+    if (nd.reflect) {
+      D3 ws = cmul(e.W, nd.ks);
+      if (any_nz(ws) && sp < PPM_MAX_TRACE + 2) {
+        EyeStack& c = st[sp++];
+        c.pos = is.pos; c.dir = nd.rdir; c.W = ws; c.medium = e.medium; c.depth = e.depth + 1; c.node = e.node * 2;
+      }
+    }
+  }
+  if (WRITE) {
+    st3(emit3 + i * 3, emit);
+  } else {
+    node_count[i] = cnt;
+    if (n_visited) {
+      unsigned long long v = visited;
+      atomicAdd(n_visited, v);
+    }
+  }
+}
+
+// ---- direct light: one warp per gather node, one lane per light sample -------------
+// get_radiance_from_light (tracer.rs:263-270) pairs [0, L(d0), L(d1), ...] with
+// [c0, c1, c2, ...] (the RADIANCE0 seed of light.rs:132): the i-th surviving
+// sample is weighted with the radiance of the (i-1)-th.  Point and sun lights
+// have one sample, which is paired with the zero -> they contribute nothing.
+__device__ __forceinline__ double ts5(unsigned i) {   // the literals 0.1, 0.3, 0.5, 0.7, 0.9
+  return i == 0 ? 0.1 : (i == 1 ? 0.3 : (i == 2 ? 0.5 : (i == 3 ? 0.7 : 0.9)));
+}
+__global__ void __launch_bounds__(256)
+k_direct_light(const __grid_constant__ DevScene sc, const double* __restrict__ pos3, const double* __restrict__ nrm3,
+               int64_t n, double* __restrict__ out3) {
+  const int64_t node = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned lane = threadIdx.x & 31u;
+  if (node >= n) return;
+  const D3 p = ld3(pos3 + node * 3), nv = ld3(nrm3 + node * 3);
+  D3 total = mk3(0.0, 0.0, 0.0);
+  for (int li = 0; li < sc.nlights; ++li) {
+    const ppm_light& l = sc.lights[li];
+    if (l.type != PPM_LIGHT_PARALLELOGRAM) continue;
+    bool valid = lane < 25;
+    double sq_ldist = 0.0, cc = 0.0;
+    if (valid) {
+      // TSS[lane] = (TS[lane/5], TS[lane%5]), light.rs:164-170
+      D3 gp = (ld3(l.pos) + ts5(lane / 5) * ld3(l.dir1)) + ts5(lane % 5) * ld3(l.dir2);   // gen_pos, light.rs:152-154
+      D3 d = gp - p;
+      valid = dot(ld3(l.nvec), d) < 0.0;
+      D3 ld;
+      if (valid) valid = normalize(d, ld);
+      if (valid) {
+        double cos0 = dot(nv, ld);
+        if (cos0 < 0.0) valid = false;
+        else {
+          Isect is;
+          if (!nearest_hit(sc, p, ld, is)) valid = false;     // no hit counts as occluded, tracer.rs:282
+          else {
+            sq_ldist = dot(d, d);
+            D3 po = is.pos - p;
+            double sq_odist = dot(po, po);
+            if (sq_ldist - sq_odist > 0.002) valid = false;
+            cc = cos0 * cos0;
+          }
+        }
+      }
+    }
+    unsigned mask = __ballot_sync(0xffffffffu, valid);
+    unsigned lower = mask & ((1u << lane) - 1u);
+    int src = lower ? 31 - __clz(lower) : (int)lane;
+    double dprev = __shfl_sync(0xffffffffu, sq_ldist, src);
+    D3 term = mk3(0.0, 0.0, 0.0);
+    if (valid && lower) {
+      const double PI4 = PPM_PI * 4.0;
+      double l0 = (2.0 * l.flux * 0.2 * 0.2) / (PI4 * dprev);    // light.rs:142
+      term = mk3((l.color[0] * l0) * cc, (l.color[1] * l0) * cc, (l.color[2] * l0) * cc);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      term.x += __shfl_xor_sync(0xffffffffu, term.x, o);
+      term.y += __shfl_xor_sync(0xffffffffu, term.y, o);
+      term.z += __shfl_xor_sync(0xffffffffu, term.z, o);
+    }
+    total = total + term;
+  }
+  if (lane == 0) st3(out3 + node * 3, total);
+}
+
+// ---- combine + accumulate ------------------------------------------------------------
+// pixel = sum_nodes W(.)kd (.) (direct + photon estimate) + sum emittance terms;
+// then the pass image is added to the running sum (util/averager2.rb:49-62).
+__global__ void k_combine(const uint32_t* __restrict__ node_off, const double* __restrict__ w3,
+                          const double* __restrict__ direct3, const double* __restrict__ photon3,
+                          const double* __restrict__ emit3, int64_t n, double* __restrict__ out3,
+                          double* __restrict__ accum3, int64_t accum_first) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  D3 rad = ld3(emit3 + i * 3);
+  for (uint32_t s = node_off[i]; s < node_off[i + 1]; ++s) {
+    D3 di = ld3(photon3 + (uint64_t)s * 3);
+    if (direct3) di = ld3(direct3 + (uint64_t)s * 3) + di;     // di = direct + estimate, tracer.rs:136-145
+    rad = rad + cmul(ld3(w3 + (uint64_t)s * 3), di);
+  }
+  st3(out3 + i * 3, rad);
+  if (accum3) {
+    double* a = accum3 + (accum_first + i) * 3;
+    a[0] += rad.x; a[1] += rad.y; a[2] += rad.z;
+  }
+}
+__global__ void k_bump(double* npass) { npass[0] += 1.0; }
+__global__ void k_scale(const double* __restrict__ in, const double* __restrict__ npass, int64_t n, double* __restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[i] / npass[0];
+}
+
+// ===========================================================================
+// context
+// ===========================================================================
+struct DBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <typename T> T* as() const { return (T*)p; }
+};
+
+struct ppm_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  bool have_scene = false, have_camera = false, have_map = false;
+  DevScene scene;
+  ppm_camera cam;
+  // unsorted records
+  DBuf r_pos, r_dir, r_wl, r_tag, counter;
+  uint64_t n_rec = 0;
+  double power = 0.0;
+  // map
+  DBuf keys, keys2, vals, vals2, cub_tmp, cell_start, hist, bbox;
+  DBuf m_px, m_py, m_pz, m_dx, m_dy, m_dz, m_wl, m_orig;
+  Grid grid;
+  double r2 = 0.0;
+  // staging for h_or_d arguments
+  DBuf st_in0, st_in1, st_out0, st_out1, st_out2, st_out3, st_out4;
+  // eye path
+  DBuf e_cnt, e_off, e_pos, e_nrm, e_w, e_emit, e_direct, e_photon, e_rays;
+  DBuf pass_img, accum, npass, stats;
+  uint64_t accum_pixels = 0;
+  // last pass stats
+  double ms[8] = {0};
+  uint64_t counters[8] = {0};
+  cudaEvent_t ev[8] = {nullptr};
+  uint64_t launches = 0;
+};
+
+namespace {
+
+#define CK(ctx, call)                                                                      \
+  do {                                                                                     \
+    cudaError_t e__ = (call);                                                              \
+    if (e__ != cudaSuccess) {                                                              \
+      (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e__);                    \
+      return PPM_ERR_CUDA;                                                                 \
+    }                                                                                      \
+  } while (0)
+#define KCHECK(ctx)                                                                        \
+  do {                                                                                     \
+    (ctx)->launches++;                                                                     \
+    cudaError_t e__ = cudaGetLastError();                                                  \
+    if (e__ != cudaSuccess) {                                                              \
+      (ctx)->err = std::string("kernel launch: ") + cudaGetErrorString(e__);               \
+      return PPM_ERR_CUDA;                                                                 \
+    }                                                                                      \
+  } while (0)
+
+int fail(ppm_ctx* c, int code, const std::string& m) { if (c) c->err = m; return code; }
+
+bool is_device_ptr(const void* p) {
+  if (!p) return false;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+// input: returns a device pointer holding `bytes` of user data
+int stage_in(ppm_ctx* c, const void* user, size_t bytes, DBuf& scratch, const void** dev) {
+  if (is_device_ptr(user)) { *dev = user; return PPM_OK; }
+  CK(c, scratch.ensure(bytes));
+  CK(c, cudaMemcpyAsync(scratch.p, user, bytes, cudaMemcpyHostToDevice, c->stream));
+  *dev = scratch.p;
+  return PPM_OK;
+}
+// output: returns a device pointer to write; finish_out copies back if user is host memory
+int stage_out(ppm_ctx* c, void* user, size_t bytes, DBuf& scratch, void** dev) {
+  if (!user) { *dev = nullptr; return PPM_OK; }
+  if (is_device_ptr(user)) { *dev = user; return PPM_OK; }
+  CK(c, scratch.ensure(bytes));
+  *dev = scratch.p;
+  return PPM_OK;
+}
+int finish_out(ppm_ctx* c, void* user, size_t bytes, void* dev) {
+  if (!user || user == dev) return PPM_OK;
+  CK(c, cudaMemcpyAsync(user, dev, bytes, cudaMemcpyDeviceToHost, c->stream));
+  return PPM_OK;
+}
+inline unsigned nblk(int64_t n, int b) { return (unsigned)((n + b - 1) / b); }
+
+RecBuf recbuf(ppm_ctx* c) {
+  RecBuf r;
+  r.pos3 = c->r_pos.as<double>(); r.dir3 = c->r_dir.as<double>(); r.wl = c->r_wl.as<uint8_t>(); r.tag = c->r_tag.as<uint64_t>();
+  return r;
+}
+int ensure_records(ppm_ctx* c, uint64_t cap) {
+  CK(c, c->r_pos.ensure(cap * 24)); CK(c, c->r_dir.ensure(cap * 24));
+  CK(c, c->r_wl.ensure(cap)); CK(c, c->r_tag.ensure(cap * 8));
+  CK(c, c->counter.ensure(64));
+  return PPM_OK;
+}
+MapSoA mapsoa(ppm_ctx* c) {
+  MapSoA m;
+  m.px = c->m_px.as<double>(); m.py = c->m_py.as<double>(); m.pz = c->m_pz.as<double>();
+  m.dx = c->m_dx.as<double>(); m.dy = c->m_dy.as<double>(); m.dz = c->m_dz.as<double>();
+  m.wl = c->m_wl.as<uint8_t>(); m.orig = c->m_orig.as<uint32_t>();
+  return m;
+}
+int light_split(ppm_ctx* c, const int64_t* n_per_light, LightSplit* ls, int64_t* total) {
+  int64_t acc = 0;
+  for (int i = 0; i < c->scene.nlights; ++i) {
+    if (n_per_light[i] < 0) return fail(c, PPM_ERR_ARG, "negative photon count");
+    ls->first[i] = acc; acc += n_per_light[i];
+  }
+  for (int i = c->scene.nlights; i <= PPM_MAX_LIGHTS; ++i) ls->first[i] = acc;
+  *total = acc;
+  return PPM_OK;
+}
+
+// -- internal (device-resident) building blocks shared by the probes and render_pass --
+int do_trace_photons(ppm_ctx* c, uint64_t seed, uint32_t pass, int uc, const int64_t* n_per_light, double power) {
+  LightSplit ls;
+  int64_t total = 0;
+  int rc = light_split(c, n_per_light, &ls, &total);
+  if (rc) return rc;
+  uint64_t cap = (uint64_t)total * PPM_MAX_TRACE;
+  if (cap == 0) cap = 1;
+  rc = ensure_records(c, cap);
+  if (rc) return rc;
+  CK(c, cudaMemsetAsync(c->counter.p, 0, 8, c->stream));
+  if (total > 0) {
+    k_trace_photons<<<nblk(total, 256), 256, 0, c->stream>>>(c->scene, ls, seed, pass, uc, total, recbuf(c),
+                                                             c->counter.as<unsigned long long>(), cap);
+    KCHECK(c);
+  }
+  unsigned long long n = 0;
+  CK(c, cudaMemcpyAsync(&n, c->counter.p, 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(c, cudaStreamSynchronize(c->stream));
+  if (n > cap) return fail(c, PPM_ERR_CAPACITY, "photon record capacity exceeded");
+  c->n_rec = n; c->power = power; c->have_map = false;
+  return PPM_OK;
+}
+
+int do_map_build(ppm_ctx* c, double radius2) {
+  if (!(radius2 > 0.0)) return fail(c, PPM_ERR_ARG, "radius2 must be > 0");
+  const uint64_t n = c->n_rec;
+  c->r2 = radius2;
+  Grid g;
+  std::memset(&g, 0, sizeof g);
+  double cell = std::sqrt(radius2) * (1.0 + 1.0 / 1024.0);   // edge slightly > r: the 27-cell walk can never miss
+  g.nx = g.ny = g.nz = 1; g.inv_cell = 1.0 / cell; g.ncells = 1;
+  if (n > 0) {
+    CK(c, c->bbox.ensure(48));
+    unsigned long long init[6] = {~0ull, ~0ull, ~0ull, 0ull, 0ull, 0ull};
+    CK(c, cudaMemcpyAsync(c->bbox.p, init, 48, cudaMemcpyHostToDevice, c->stream));
+    k_bbox<<<std::min<unsigned>(nblk((int64_t)n, 256), 148 * 8), 256, 0, c->stream>>>(c->r_pos.as<double>(), n,
+                                                                                     c->bbox.as<unsigned long long>());
+    KCHECK(c);
+    unsigned long long mm[6];
+    CK(c, cudaMemcpyAsync(mm, c->bbox.p, 48, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    double lo[3], hi[3];
+    for (int k = 0; k < 3; ++k) { lo[k] = dec_ord(mm[k]); hi[k] = dec_ord(mm[3 + k]); }
+    for (int k = 0; k < 3; ++k)
+      if (!(lo[k] == lo[k]) || !(hi[k] == hi[k]) || std::isinf(lo[k]) || std::isinf(hi[k]))
+        return fail(c, PPM_ERR_ARG, "photon positions are not finite");
+    const double CELL_CAP = 67108864.0;   // 2^26 cells
+    for (;;) {
+      double dims[3];
+      for (int k = 0; k < 3; ++k) dims[k] = std::floor((hi[k] - lo[k]) / cell) + 2.0;
+      if (dims[0] * dims[1] * dims[2] <= CELL_CAP && dims[0] < 2e9 && dims[1] < 2e9 && dims[2] < 2e9) {
+        g.nx = (int32_t)dims[0]; g.ny = (int32_t)dims[1]; g.nz = (int32_t)dims[2];
+        break;
+      }
+      cell *= 2.0;
+    }
+    for (int k = 0; k < 3; ++k) g.org[k] = lo[k];
+    g.inv_cell = 1.0 / cell;
+    g.ncells = (uint32_t)g.nx * (uint32_t)g.ny * (uint32_t)g.nz;
+  }
+  c->grid = g;
+  CK(c, c->hist.ensure(((size_t)g.ncells + 1) * 4));
+  CK(c, c->cell_start.ensure(((size_t)g.ncells + 1) * 4));
+  CK(c, cudaMemsetAsync(c->hist.p, 0, ((size_t)g.ncells + 1) * 4, c->stream));
+  size_t nn = n ? n : 1;
+  CK(c, c->keys.ensure(nn * 8)); CK(c, c->keys2.ensure(nn * 8));
+  CK(c, c->vals.ensure(nn * 4)); CK(c, c->vals2.ensure(nn * 4));
+  CK(c, c->m_px.ensure(nn * 8)); CK(c, c->m_py.ensure(nn * 8)); CK(c, c->m_pz.ensure(nn * 8));
+  CK(c, c->m_dx.ensure(nn * 8)); CK(c, c->m_dy.ensure(nn * 8)); CK(c, c->m_dz.ensure(nn * 8));
+  CK(c, c->m_wl.ensure(nn)); CK(c, c->m_orig.ensure(nn * 4));
+  if (n > 0) {
+    k_cell_key<<<nblk((int64_t)n, 256), 256, 0, c->stream>>>(g, c->r_pos.as<double>(), c->r_tag.as<uint64_t>(), n,
+                                                            c->keys.as<uint64_t>(), c->vals.as<uint32_t>(), c->hist.as<uint32_t>());
+    KCHECK(c);
+    int cell_bits = 1;
+    while ((1ull << cell_bits) < (unsigned long long)g.ncells) ++cell_bits;
+    int end_bit = std::min(64, 38 + cell_bits);
+    size_t tmp = 0;
+    CK(c, cub::DeviceRadixSort::SortPairs(nullptr, tmp, c->keys.as<uint64_t>(), c->keys2.as<uint64_t>(), c->vals.as<uint32_t>(),
+                                          c->vals2.as<uint32_t>(), (int64_t)n, 0, end_bit, c->stream));
+    CK(c, c->cub_tmp.ensure(tmp));
+    CK(c, cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp, c->keys.as<uint64_t>(), c->keys2.as<uint64_t>(), c->vals.as<uint32_t>(),
+                                          c->vals2.as<uint32_t>(), (int64_t)n, 0, end_bit, c->stream));
+    c->launches += 8;
+    k_scatter<<<nblk((int64_t)n, 256), 256, 0, c->stream>>>(recbuf(c), c->vals2.as<uint32_t>(), n, mapsoa(c));
+    KCHECK(c);
+  }
+  {
+    size_t tmp = 0;
+    CK(c, cub::DeviceScan::ExclusiveSum(nullptr, tmp, c->hist.as<uint32_t>(), c->cell_start.as<uint32_t>(), (int64_t)g.ncells + 1, c->stream));
+    CK(c, c->cub_tmp.ensure(tmp));
+    CK(c, cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tmp, c->hist.as<uint32_t>(), c->cell_start.as<uint32_t>(), (int64_t)g.ncells + 1, c->stream));
+    c->launches += 2;
+  }
+  c->have_map = true;
+  return PPM_OK;
+}
+
+int launch_gather(ppm_ctx* c, const double* dpos, const double* dnrm, int64_t n, int filter, double* drgb, uint32_t* dcounts,
+                  unsigned long long* dsumk) {
+  if (n <= 0) return PPM_OK;
+  const int B = 128;
+  const uint32_t* cs = c->cell_start.as<uint32_t>();
+  switch (filter) {
+    case PPM_FILTER_NONE:
+      k_gather<PPM_FILTER_NONE><<<nblk(n, B), B, 0, c->stream>>>(c->grid, cs, mapsoa(c), dpos, dnrm, n, c->power, c->r2, drgb, dcounts, dsumk);
+      break;
+    case PPM_FILTER_CONE:
+      k_gather<PPM_FILTER_CONE><<<nblk(n, B), B, 0, c->stream>>>(c->grid, cs, mapsoa(c), dpos, dnrm, n, c->power, c->r2, drgb, dcounts, dsumk);
+      break;
+    case PPM_FILTER_GAUSS:
+      k_gather<PPM_FILTER_GAUSS><<<nblk(n, B), B, 0, c->stream>>>(c->grid, cs, mapsoa(c), dpos, dnrm, n, c->power, c->r2, drgb, dcounts, dsumk);
+      break;
+    default: return fail(c, PPM_ERR_ARG, "bad filter");
+  }
+  KCHECK(c);
+  return PPM_OK;
+}
+
+// eye rays (device, or NULL = generate from the camera) -> radiance image (device) [+ accumulate]
+int do_trace_rays(ppm_ctx* c, const double* drays, int64_t n, int64_t first_pixel, uint64_t seed, uint32_t pass, int uc,
+                  double* dout, double* daccum, bool timed) {
+  if (n <= 0) return PPM_OK;
+  CK(c, c->e_cnt.ensure((size_t)(n + 1) * 4)); CK(c, c->e_off.ensure((size_t)(n + 1) * 4));
+  CK(c, c->e_emit.ensure((size_t)n * 24)); CK(c, c->stats.ensure(64));
+  CK(c, cudaMemsetAsync(c->stats.p, 0, 64, c->stream));
+  CK(c, cudaMemsetAsync(c->e_cnt.p, 0, (size_t)(n + 1) * 4, c->stream));
+  unsigned long long* dstats = c->stats.as<unsigned long long>();
+  EyeNodes none = {nullptr, nullptr, nullptr};
+  if (timed) cudaEventRecord(c->ev[2], c->stream);
+  k_eye_expand<false><<<nblk(n, 128), 128, 0, c->stream>>>(c->scene, c->cam, drays, n, first_pixel, seed, pass,
+                                                          c->e_cnt.as<uint32_t>(), nullptr, none, nullptr, dstats);
+  KCHECK(c);
+  size_t tmp = 0;
+  CK(c, cub::DeviceScan::ExclusiveSum(nullptr, tmp, c->e_cnt.as<uint32_t>(), c->e_off.as<uint32_t>(), n + 1, c->stream));
+  CK(c, c->cub_tmp.ensure(tmp));
+  CK(c, cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tmp, c->e_cnt.as<uint32_t>(), c->e_off.as<uint32_t>(), n + 1, c->stream));
+  c->launches += 2;
+  uint32_t nn = 0;
+  CK(c, cudaMemcpyAsync(&nn, c->e_off.as<uint32_t>() + n, 4, cudaMemcpyDeviceToHost, c->stream));
+  CK(c, cudaStreamSynchronize(c->stream));
+  size_t cap = nn ? nn : 1;
+  CK(c, c->e_pos.ensure(cap * 24)); CK(c, c->e_nrm.ensure(cap * 24)); CK(c, c->e_w.ensure(cap * 24));
+  CK(c, c->e_direct.ensure(cap * 24)); CK(c, c->e_photon.ensure(cap * 24));
+  EyeNodes nodes = {c->e_pos.as<double>(), c->e_nrm.as<double>(), c->e_w.as<double>()};
+  k_eye_expand<true><<<nblk(n, 128), 128, 0, c->stream>>>(c->scene, c->cam, drays, n, first_pixel, seed, pass, nullptr,
+                                                         c->e_off.as<uint32_t>(), nodes, c->e_emit.as<double>(), nullptr);
+  KCHECK(c);
+  if (timed) cudaEventRecord(c->ev[3], c->stream);
+  if (uc && nn) {
+    k_direct_light<<<nblk((int64_t)nn * 32, 256), 256, 0, c->stream>>>(c->scene, nodes.pos3, nodes.nrm3, nn, c->e_direct.as<double>());
+    KCHECK(c);
+  }
+  if (timed) cudaEventRecord(c->ev[4], c->stream);
+  int rc = launch_gather(c, nodes.pos3, nodes.nrm3, nn, c->cam.pfilter, c->e_photon.as<double>(), nullptr, dstats + 1);
+  if (rc) return rc;
+  if (timed) cudaEventRecord(c->ev[5], c->stream);
+  k_combine<<<nblk(n, 256), 256, 0, c->stream>>>(c->e_off.as<uint32_t>(), nodes.w3, uc ? c->e_direct.as<double>() : nullptr,
+                                                c->e_photon.as<double>(), c->e_emit.as<double>(), n, dout, daccum, first_pixel);
+  KCHECK(c);
+  c->counters[3] = nn;
+  return PPM_OK;
+}
+
+}  // namespace
+
+// ===========================================================================
+// C ABI
+// ===========================================================================
+extern "C" {
+
+int ppm_create(int device, ppm_ctx** out) {
+  if (!out) return PPM_ERR_ARG;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { cudaGetLastError(); return PPM_ERR_NODEVICE; }
+  if (device < 0 || device >= ndev) return PPM_ERR_ARG;
+  if (cudaSetDevice(device) != cudaSuccess) return PPM_ERR_CUDA;
+  ppm_ctx* c = new ppm_ctx();
+  c->device = device;
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return PPM_ERR_CUDA; }
+  for (int i = 0; i < 8; ++i) cudaEventCreate(&c->ev[i]);
+  std::memset(&c->scene, 0, sizeof c->scene);
+  ppm_camera_default(&c->cam);
+  *out = c;
+  return PPM_OK;
+}
+
+void ppm_destroy(ppm_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  DBuf* all[] = {&c->r_pos, &c->r_dir, &c->r_wl, &c->r_tag, &c->counter, &c->keys, &c->keys2, &c->vals, &c->vals2, &c->cub_tmp,
+                 &c->cell_start, &c->hist, &c->bbox, &c->m_px, &c->m_py, &c->m_pz, &c->m_dx, &c->m_dy, &c->m_dz, &c->m_wl, &c->m_orig,
+                 &c->st_in0, &c->st_in1, &c->st_out0, &c->st_out1, &c->st_out2, &c->st_out3, &c->st_out4,
+                 &c->e_cnt, &c->e_off, &c->e_pos, &c->e_nrm, &c->e_w, &c->e_emit, &c->e_direct, &c->e_photon, &c->e_rays,
+                 &c->pass_img, &c->accum, &c->npass, &c->stats};
+  for (DBuf* b : all) b->release();
+  for (int i = 0; i < 8; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+  cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+const char* ppm_last_error(const ppm_ctx* c) { return c ? c->err.c_str() : "null context"; }
+void* ppm_stream(ppm_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+int ppm_scene_set(ppm_ctx* c, const ppm_prim* prims, int32_t nprims, const ppm_material* mats, int32_t nmats,
+                  const ppm_light* lights, int32_t nlights) {
+  if (!c) return PPM_ERR_ARG;
+  if (!prims || !mats || nprims <= 0 || nmats <= 0 || nlights < 0 || (nlights > 0 && !lights)) return fail(c, PPM_ERR_ARG, "null/empty scene arrays");
+  if (nprims > PPM_MAX_PRIMS || nmats > PPM_MAX_MATS || nlights > PPM_MAX_LIGHTS) return fail(c, PPM_ERR_CAPACITY, "scene exceeds 64 prims / 48 materials / 8 lights");
+  for (int i = 0; i < nprims; ++i) {
+    if (prims[i].material < 0 || prims[i].material >= nmats) return fail(c, PPM_ERR_ARG, "primitive material index out of range");
+    if (prims[i].type < PPM_SHAPE_POINT || prims[i].type > PPM_SHAPE_PARALLELOGRAM) return fail(c, PPM_ERR_ARG, "bad shape type");
+  }
+  for (int i = 0; i < nlights; ++i)
+    if (lights[i].type < PPM_LIGHT_POINT || lights[i].type > PPM_LIGHT_SUN) return fail(c, PPM_ERR_ARG, "bad light type");
+  std::memset(&c->scene, 0, sizeof c->scene);
+  c->scene.nprims = nprims; c->scene.nmats = nmats; c->scene.nlights = nlights;
+  std::memcpy(c->scene.prims, prims, sizeof(ppm_prim) * nprims);
+  std::memcpy(c->scene.mats, mats, sizeof(ppm_material) * nmats);
+  if (nlights) std::memcpy(c->scene.lights, lights, sizeof(ppm_light) * nlights);
+  c->have_scene = true;
+  return PPM_OK;
+}
+
+int ppm_camera_set(ppm_ctx* c, const ppm_camera* cam) {
+  if (!c || !cam) return PPM_ERR_ARG;
+  if (cam->xreso <= 0 || cam->yreso <= 0) return fail(c, PPM_ERR_ARG, "bad resolution");
+  if (cam->pfilter < PPM_FILTER_NONE || cam->pfilter > PPM_FILTER_GAUSS) return fail(c, PPM_ERR_ARG, "bad photon filter");
+  c->cam = *cam;
+  c->have_camera = true;
+  return PPM_OK;
+}
+
+int ppm_intersect(ppm_ctx* c, const double* rays6, int64_t n, int32_t* hit_idx, double* t, double* pos3, double* nrm3, int32_t* io) {
+  if (!c) return PPM_ERR_ARG;
+  if (!c->have_scene) return fail(c, PPM_ERR_STATE, "scene not set");
+  if (n < 0 || (n > 0 && (!rays6 || !hit_idx))) return fail(c, PPM_ERR_ARG, "null rays / hit_idx");
+  if (n == 0) return PPM_OK;
+  CK(c, cudaSetDevice(c->device));
+  const void* drays; void *dh, *dt, *dp, *dn, *di;
+  int rc;
+  if ((rc = stage_in(c, rays6, (size_t)n * 48, c->st_in0, &drays))) return rc;
+  if ((rc = stage_out(c, hit_idx, (size_t)n * 4, c->st_out0, &dh))) return rc;
+  if ((rc = stage_out(c, t, (size_t)n * 8, c->st_out1, &dt))) return rc;
+  if ((rc = stage_out(c, pos3, (size_t)n * 24, c->st_out2, &dp))) return rc;
+  if ((rc = stage_out(c, nrm3, (size_t)n * 24, c->st_out3, &dn))) return rc;
+  if ((rc = stage_out(c, io, (size_t)n * 4, c->st_out4, &di))) return rc;
+  k_intersect<<<nblk(n, 128), 128, 0, c->stream>>>(c->scene, (const double*)drays, n, (int32_t*)dh, (double*)dt, (double*)dp,
+                                                  (double*)dn, (int32_t*)di);
+  KCHECK(c);
+  if ((rc = finish_out(c, hit_idx, (size_t)n * 4, dh))) return rc;
+  if ((rc = finish_out(c, t, (size_t)n * 8, dt))) return rc;
+  if ((rc = finish_out(c, pos3, (size_t)n * 24, dp))) return rc;
+  if ((rc = finish_out(c, nrm3, (size_t)n * 24, dn))) return rc;
+  if ((rc = finish_out(c, io, (size_t)n * 4, di))) return rc;
+  CK(c, cudaStreamSynchronize(c->stream));
+  return PPM_OK;
+}
+
+int ppm_emit_photons(ppm_ctx* c, uint64_t seed, uint32_t pass, const int64_t* n_per_light, ppm_photon* out) {
+  if (!c) return PPM_ERR_ARG;
+  if (!c->have_scene || c->scene.nlights == 0) return fail(c, PPM_ERR_STATE, "scene with lights not set");
+  if (!n_per_light || !out) return fail(c, PPM_ERR_ARG, "null argument");
+  CK(c, cudaSetDevice(c->device));
+  LightSplit ls; int64_t total;
+  int rc = light_split(c, n_per_light, &ls, &total);
+  if (rc) return rc;
+  if (total == 0) return PPM_OK;
+  void* d;
+  if ((rc = stage_out(c, out, (size_t)total * sizeof(ppm_photon), c->st_out0, &d))) return rc;
+  k_emit<<<nblk(total, 128), 128, 0, c->stream>>>(c->scene, ls, seed, pass, total, (ppm_photon*)d);
+  KCHECK(c);
+  if ((rc = finish_out(c, out, (size_t)total * sizeof(ppm_photon), d))) return rc;
+  CK(c, cudaStreamSynchronize(c->stream));
+  return PPM_OK;
+}
+
+int ppm_trace_photons(ppm_ctx* c, uint64_t seed, uint32_t pass, int uc, const int64_t* n_per_light, double power, uint64_t* n_stored) {
+  if (!c) return PPM_ERR_ARG;
+  if (!c->have_scene || c->scene.nlights == 0) return fail(c, PPM_ERR_STATE, "scene with lights not set");
+  if (!n_per_light) return fail(c, PPM_ERR_ARG, "null n_per_light");
+  CK(c, cudaSetDevice(c->device));
+  int rc = do_trace_photons(c, seed, pass, uc, n_per_light, power);
+  if (rc) return rc;
+  if (n_stored) *n_stored = c->n_rec;
+  return PPM_OK;
+}
+
+int ppm_photons_count(ppm_ctx* c, uint64_t* n, double* power) {
+  if (!c) return PPM_ERR_ARG;
+  if (n) *n = c->n_rec;
+  if (power) *power = c->power;
+  return PPM_OK;
+}
+
+int ppm_photons_export(ppm_ctx* c, ppm_photon* out, uint64_t cap, uint64_t* tags) {
+  if (!c) return PPM_ERR_ARG;
+  if (c->n_rec == 0) return PPM_OK;
+  if (!out) return fail(c, PPM_ERR_ARG, "null output");
+  if (cap < c->n_rec) return fail(c, PPM_ERR_CAPACITY, "export buffer too small");
+  CK(c, cudaSetDevice(c->device));
+  void* d; int rc;
+  size_t bytes = (size_t)c->n_rec * sizeof(ppm_photon);
+  if ((rc = stage_out(c, out, bytes, c->st_out0, &d))) return rc;
+  k_export<<<nblk((int64_t)c->n_rec, 256), 256, 0, c->stream>>>(recbuf(c), c->n_rec, (ppm_photon*)d);
+  KCHECK(c);
+  if ((rc = finish_out(c, out, bytes, d))) return rc;
+  if (tags) CK(c, cudaMemcpyAsync(tags, c->r_tag.p, (size_t)c->n_rec * 8, is_device_ptr(tags) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->stream));
+  CK(c, cudaStreamSynchronize(c->stream));
+  return PPM_OK;
+}
+
+int ppm_photons_import(ppm_ctx* c, const ppm_photon* in, uint64_t n, double power) {
+  if (!c) return PPM_ERR_ARG;
+  if (n > 0 && !in) return fail(c, PPM_ERR_ARG, "null input");
+  if (n >= (1ull << 32)) return fail(c, PPM_ERR_CAPACITY, "at most 2^32-1 photon records");
+  CK(c, cudaSetDevice(c->device));
+  int rc = ensure_records(c, n ? n : 1);
+  if (rc) return rc;
+  if (n) {
+    const void* d;
+    if ((rc = stage_in(c, in, (size_t)n * sizeof(ppm_photon), c->st_in0, &d))) return rc;
+    k_import<<<nblk((int64_t)n, 256), 256, 0, c->stream>>>((const ppm_photon*)d, n, recbuf(c));
+    KCHECK(c);
+    CK(c, cudaStreamSynchronize(c->stream));
+  }
+  c->n_rec = n; c->power = power; c->have_map = false;
+  return PPM_OK;
+}
+
+int ppm_map_build(ppm_ctx* c, double radius2) {
+  if (!c) return PPM_ERR_ARG;
+  CK(c, cudaSetDevice(c->device));
+  int rc = do_map_build(c, radius2);
+  if (rc) return rc;
+  CK(c, cudaStreamSynchronize(c->stream));
+  return PPM_OK;
+}
+
+int ppm_within(ppm_ctx* c, const double* q3, int64_t nq, uint32_t* idx, uint32_t* count, uint32_t cap) {
+  if (!c) return PPM_ERR_ARG;
+  if (!c->have_map) return fail(c, PPM_ERR_STATE, "photon map not built");
+  if (nq < 0 || (nq > 0 && (!q3 || !count || (cap > 0 && !idx)))) return fail(c, PPM_ERR_ARG, "null argument");
+  if (nq == 0) return PPM_OK;
+  CK(c, cudaSetDevice(c->device));
+  const void* dq; void *di, *dc; int rc;
+  size_t ib = (size_t)nq * (cap ? cap : 1) * 4;
+  if ((rc = stage_in(c, q3, (size_t)nq * 24, c->st_in0, &dq))) return rc;
+  CK(c, c->st_out0.ensure(ib));
+  di = c->st_out0.p;
+  if ((rc = stage_out(c, count, (size_t)nq * 4, c->st_out1, &dc))) return rc;
+  k_within<<<nblk(nq, 128), 128, 0, c->stream>>>(c->grid, c->cell_start.as<uint32_t>(), mapsoa(c), (const double*)dq, nq, c->r2,
+                                                (uint32_t*)di, (uint32_t*)dc, cap);
+  KCHECK(c);
+  if ((rc = finish_out(c, count, (size_t)nq * 4, dc))) return rc;
+  if (cap) {
+    // sort each neighbour list ascending by photon index on the host (probe only)
+    std::vector<uint32_t> h((size_t)nq * cap), hc((size_t)nq);
+    CK(c, cudaMemcpyAsync(h.data(), di, ib, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaMemcpyAsync(hc.data(), dc, (size_t)nq * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    for (int64_t q = 0; q < nq; ++q) {
+      uint32_t k = std::min(hc[(size_t)q], cap);
+      std::sort(h.begin() + (size_t)q * cap, h.begin() + (size_t)q * cap + k);
+    }
+    if (is_device_ptr(idx)) CK(c, cudaMemcpy(idx, h.data(), ib, cudaMemcpyHostToDevice));
+    else std::memcpy(idx, h.data(), ib);
+  }
+  CK(c, cudaStreamSynchronize(c->stream));
+  return PPM_OK;
+}
+
+int ppm_gather(ppm_ctx* c, const double* pos3, const double* nrm3, int64_t n, int filter, double* rgb3, uint32_t* counts) {
+  if (!c) return PPM_ERR_ARG;
+  if (!c->have_map) return fail(c, PPM_ERR_STATE, "photon map not built");
+  if (n < 0 || (n > 0 && (!pos3 || !nrm3 || !rgb3))) return fail(c, PPM_ERR_ARG, "null argument");
+  if (filter < PPM_FILTER_NONE || filter > PPM_FILTER_GAUSS) return fail(c, PPM_ERR_ARG, "bad filter");
+  if (n == 0) return PPM_OK;
+  CK(c, cudaSetDevice(c->device));
+  const void *dp, *dn; void *dr, *dc; int rc;
+  if ((rc = stage_in(c, pos3, (size_t)n * 24, c->st_in0, &dp))) return rc;
+  if ((rc = stage_in(c, nrm3, (size_t)n * 24, c->st_in1, &dn))) return rc;
+  if ((rc = stage_out(c, rgb3, (size_t)n * 24, c->st_out0, &dr))) return rc;
+  if ((rc = stage_out(c, counts, (size_t)n * 4, c->st_out1, &dc))) return rc;
+  if ((rc = launch_gather(c, (const double*)dp, (const double*)dn, n, filter, (double*)dr, (uint32_t*)dc, nullptr))) return rc;
+  if ((rc = finish_out(c, rgb3, (size_t)n * 24, dr))) return rc;
+  if ((rc = finish_out(c, counts, (size_t)n * 4, dc))) return rc;
+  CK(c, cudaStreamSynchronize(c->stream));
+  return PPM_OK;
+}
+
+int ppm_generate_rays(ppm_ctx* c, uint64_t seed, uint32_t pass, double* rays6) {
+  if (!c) return PPM_ERR_ARG;
+  if (!c->have_camera) return fail(c, PPM_ERR_STATE, "camera not set");
+  if (!rays6) return fail(c, PPM_ERR_ARG, "null output");
+  CK(c, cudaSetDevice(c->device));
+  int64_t n = (int64_t)c->cam.xreso * c->cam.yreso;
+  void* d; int rc;
+  if ((rc = stage_out(c, rays6, (size_t)n * 48, c->st_out0, &d))) return rc;
+  k_gen_rays<<<nblk(n, 128), 128, 0, c->stream>>>(c->cam, seed, pass, n, (double*)d);
+  KCHECK(c);
+  if ((rc = finish_out(c, rays6, (size_t)n * 48, d))) return rc;
+  CK(c, cudaStreamSynchronize(c->stream));
+  return PPM_OK;
+}
+
+int ppm_trace_rays(ppm_ctx* c, const double* rays6, int64_t n, int64_t first_pixel, uint64_t seed, uint32_t pass, int uc, double* rgb3) {
+  if (!c) return PPM_ERR_ARG;
+  if (!c->have_scene) return fail(c, PPM_ERR_STATE, "scene not set");
+  if (!c->have_map) return fail(c, PPM_ERR_STATE, "photon map not built");
+  if (n < 0 || first_pixel < 0 || (n > 0 && (!rays6 || !rgb3))) return fail(c, PPM_ERR_ARG, "null argument");
+  if (n == 0) return PPM_OK;
+  CK(c, cudaSetDevice(c->device));
+  const void* dr; void* dout; int rc;
+  if ((rc = stage_in(c, rays6, (size_t)n * 48, c->st_in0, &dr))) return rc;
+  if ((rc = stage_out(c, rgb3, (size_t)n * 24, c->st_out0, &dout))) return rc;
+  if ((rc = do_trace_rays(c, (const double*)dr, n, first_pixel, seed, pass, uc, (double*)dout, nullptr, false))) return rc;
+  if ((rc = finish_out(c, rgb3, (size_t)n * 24, dout))) return rc;
+  CK(c, cudaStreamSynchronize(c->stream));
+  return PPM_OK;
+}
+
+static int ensure_accum(ppm_ctx* c) {
+  uint64_t npix = (uint64_t)c->cam.xreso * (uint64_t)c->cam.yreso;
+  if (c->accum_pixels == npix && c->accum.p) return PPM_OK;
+  // sum image and pass counter live in ONE allocation so a single reduce covers both
+  CK(c, c->accum.ensure((size_t)(npix * 3 + 1) * 8));
+  CK(c, cudaMemsetAsync(c->accum.p, 0, (size_t)(npix * 3 + 1) * 8, c->stream));
+  c->accum_pixels = npix;
+  return PPM_OK;
+}
+
+int ppm_render_pass(ppm_ctx* c, uint64_t seed, uint32_t pass, int64_t nphoton, double radius2, int uc) {
+  if (!c) return PPM_ERR_ARG;
+  if (!c->have_scene || c->scene.nlights == 0) return fail(c, PPM_ERR_STATE, "scene with lights not set");
+  if (!c->have_camera) return fail(c, PPM_ERR_STATE, "camera not set");
+  if (nphoton <= 0 || !(radius2 > 0.0)) return fail(c, PPM_ERR_ARG, "nphoton and radius2 must be positive");
+  CK(c, cudaSetDevice(c->device));
+  int rc;
+  double power;
+  int64_t ns[PPM_MAX_LIGHTS];
+  if ((rc = ppm_photon_budget(c->scene.lights, c->scene.nlights, nphoton, &power, ns))) return fail(c, rc, "photon budget");
+  if ((rc = ensure_accum(c))) return rc;
+  const int64_t npix = (int64_t)c->cam.xreso * c->cam.yreso;
+  CK(c, c->pass_img.ensure((size_t)npix * 24));
+  const uint64_t l0 = c->launches;
+  cudaEventRecord(c->ev[0], c->stream);
+  if ((rc = do_trace_photons(c, seed, pass, uc, ns, power))) return rc;
+  cudaEventRecord(c->ev[1], c->stream);
+  if ((rc = do_map_build(c, radius2))) return rc;
+  if ((rc = do_trace_rays(c, nullptr, npix, 0, seed, pass, uc, c->pass_img.as<double>(), c->accum.as<double>(), true))) return rc;
+  k_bump<<<1, 1, 0, c->stream>>>(c->accum.as<double>() + (size_t)npix * 3);
+  KCHECK(c);
+  cudaEventRecord(c->ev[6], c->stream);
+  unsigned long long st[2];
+  CK(c, cudaMemcpyAsync(st, c->stats.p, 16, cudaMemcpyDeviceToHost, c->stream));
+  CK(c, cudaStreamSynchronize(c->stream));
+  float f;
+  for (int i = 0; i < 6; ++i) { cudaEventElapsedTime(&f, c->ev[i], c->ev[i + 1]); c->ms[i] = f; }
+  cudaEventElapsedTime(&f, c->ev[0], c->ev[6]); c->ms[6] = f; c->ms[7] = 0.0;
+  int64_t emitted = 0;
+  for (int i = 0; i < c->scene.nlights; ++i) emitted += ns[i];
+  c->counters[0] = (uint64_t)emitted; c->counters[1] = c->n_rec; c->counters[2] = st[0];
+  c->counters[4] = st[1]; c->counters[5] = c->launches - l0;
+  return PPM_OK;
+}
+
+int ppm_last_pass_stats(ppm_ctx* c, double ms[8], uint64_t counters[8]) {
+  if (!c) return PPM_ERR_ARG;
+  if (ms) std::memcpy(ms, c->ms, sizeof c->ms);
+  if (counters) std::memcpy(counters, c->counters, sizeof c->counters);
+  return PPM_OK;
+}
+
+static int copy_out(ppm_ctx* c, void* user, const void* dev, size_t bytes) {
+  CK(c, cudaMemcpyAsync(user, dev, bytes, is_device_ptr(user) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->stream));
+  CK(c, cudaStreamSynchronize(c->stream));
+  return PPM_OK;
+}
+
+int ppm_pass_image_read(ppm_ctx* c, double* rgb3) {
+  if (!c || !rgb3) return PPM_ERR_ARG;
+  if (!c->pass_img.p) return fail(c, PPM_ERR_STATE, "no pass rendered yet");
+  CK(c, cudaSetDevice(c->device));
+  return copy_out(c, rgb3, c->pass_img.p, (size_t)c->cam.xreso * c->cam.yreso * 24);
+}
+
+int ppm_accum_reset(ppm_ctx* c) {
+  if (!c) return PPM_ERR_ARG;
+  CK(c, cudaSetDevice(c->device));
+  c->accum_pixels = 0;
+  if (c->have_camera) return ensure_accum(c);
+  return PPM_OK;
+}
+
+int ppm_accum_read(ppm_ctx* c, double* rgb3, uint32_t* n_pass) {
+  if (!c) return PPM_ERR_ARG;
+  if (!c->accum.p || !c->accum_pixels) return fail(c, PPM_ERR_STATE, "no accumulator yet");
+  CK(c, cudaSetDevice(c->device));
+  if (rgb3) { int rc = copy_out(c, rgb3, c->accum.p, (size_t)c->accum_pixels * 24); if (rc) return rc; }
+  if (n_pass) {
+    double np = 0.0;
+    CK(c, cudaMemcpyAsync(&np, c->accum.as<double>() + c->accum_pixels * 3, 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    *n_pass = (uint32_t)np;
+  }
+  return PPM_OK;
+}
+
+int ppm_accum_device(ppm_ctx* c, void** sum_dev, void** npass_dev, uint64_t* n_doubles) {
+  if (!c) return PPM_ERR_ARG;
+  CK(c, cudaSetDevice(c->device));
+  if (!c->have_camera) return fail(c, PPM_ERR_STATE, "camera not set");
+  int rc = ensure_accum(c);
+  if (rc) return rc;
+  CK(c, cudaStreamSynchronize(c->stream));
+  if (sum_dev) *sum_dev = c->accum.p;
+  if (npass_dev) *npass_dev = c->accum.as<double>() + c->accum_pixels * 3;
+  if (n_doubles) *n_doubles = c->accum_pixels * 3 + 1;
+  return PPM_OK;
+}
+
+int ppm_image_mean(ppm_ctx* c, double* rgb3) {
+  if (!c || !rgb3) return PPM_ERR_ARG;
+  if (!c->accum.p || !c->accum_pixels) return fail(c, PPM_ERR_STATE, "no accumulator yet");
+  CK(c, cudaSetDevice(c->device));
+  int64_t n = (int64_t)c->accum_pixels * 3;
+  void* d; int rc;
+  if ((rc = stage_out(c, rgb3, (size_t)n * 8, c->st_out0, &d))) return rc;
+  k_scale<<<nblk(n, 256), 256, 0, c->stream>>>(c->accum.as<double>(), c->accum.as<double>() + n, n, (double*)d);
+  KCHECK(c);
+  if ((rc = finish_out(c, rgb3, (size_t)n * 8, d))) return rc;
+  CK(c, cudaStreamSynchronize(c->stream));
+  return PPM_OK;
+}
+
+}  // extern "C"
