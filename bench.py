@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the PPM-PA hot path (BASELINE.json).
+
+A "step" is ONE whole progressive-photon-mapping pass of config 2
+(ex-glassbox, 1024x1024, 1 M emitted photons, use-classic on, r0 = 0.1 with the
+iterator.rb schedule): trace photons -> build map -> eye paths -> direct light
+-> gather -> combine + accumulate.  `value` = radiance-gathered pixels / s with
+everything resident on the device; `e2e` = the same through the public C ABI
+with host buffers (scene/camera set + render + pass image read back) per step.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+N > 1 is launched by torch.distributed.run (one rank per GPU).  Passes are
+independent: rank g renders its own passes with its own Philox streams, and the
+accumulated images are combined by one NCCL reduce per frame (inside the timed
+region).  --impl reference times the CPU oracle (restatement of the reference,
+the Rust original cannot be built here) on the host cores.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "radiance-gathered pixels/sec (whole PPM-PA pass: photon trace + map build + eye paths + direct light + gather + accumulate)"
+UNIT = "pixels/s"
+SEED = 0x5EED0001
+XRES = YRES = 1024
+NPHOTON = 1_000_000
+R0 = 0.1
+UC = True
+WORKLOAD = "configs[1]: ex-glassbox.scene, 1024x1024, 1M emitted photons/pass, use-classic on, filter none, r0=0.1 (iterator.rb schedule)"
+
+
+def env_int(name, dflt):
+    try:
+        return int(os.environ.get(name, dflt))
+    except ValueError:
+        return dflt
+
+
+def load_workload():
+    import ppmpa_b200 as P
+    sc = P.read_scene(os.path.join(ROOT, "examples", "ex-glassbox.scene"))
+    cam = P.read_camera(os.path.join(ROOT, "examples", "camera0.scr"), xreso=XRES, yreso=YRES, progressive=1,
+                        pfilter=P.FILTER_NONE)
+    return sc, cam
+
+
+def base_config(n_gpus):
+    return {"workload": WORKLOAD, "pixels_per_pass": XRES * YRES, "photons_per_pass": NPHOTON,
+            "passes_per_step": 1, "parallelism": f"pass-sharded x{n_gpus}",
+            "radius": "iterator.rb schedule indexed by the per-rank step, so per-GPU work is identical at every N",
+            "l2": "per-pass working set (~280 MB of records, sorted map, node lists, images; regenerated every pass) "
+                  "exceeds the 126 MB L2; nothing is reused between timed passes"}
+
+
+# ---------------------------------------------------------------------------
+# CPU side (oracle): cpu_baseline leg and --impl reference
+# ---------------------------------------------------------------------------
+def cpu_pass_sample(rows, cores, step):
+    """`cores` independent single-threaded oracle passes in parallel (the reference's own
+    parallelism, util/iterator.rb NPARA), each: full 1M-photon trace + map build + eye trace
+    of `rows` image rows.  Returns full-pass-equivalent seconds per pass."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+    import ppmpa_b200 as P
+    orc = oracle_lib.Oracle()
+    sc, cam = load_workload()
+    r2 = [float(P.radius_schedule(R0, step + 1)[step]) ** 2] * cores
+    row0 = (YRES - rows) // 2
+    t0 = time.perf_counter()
+    times, stats = orc.render_passes_parallel(sc, cam, SEED, step * cores, cores, NPHOTON, r2, UC, row0, row0 + rows)
+    wall = time.perf_counter() - t0
+    equiv = [t[0] + t[1] + t[2] * (YRES / rows) for t in times]
+    return sum(equiv) / len(equiv), wall
+
+
+def cpu_baseline_obj(rows, cores, t_equiv):
+    return {"value": cores * XRES * YRES / t_equiv, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{cores} concurrent single-threaded oracle passes (C++ restatement, -O2 -ffp-contract=off), each: "
+                      f"full 1M-photon trace + map build + eye trace/direct light/gather of {rows} of {YRES} image rows; "
+                      f"pass time extrapolated to {YRES} rows"}
+
+
+def run_reference(args):
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    rows = env_int("PPM_BENCH_CPU_ROWS", 64)
+    for w in range(min(args.warmup, 1)):
+        cpu_pass_sample(rows, cores, w)
+    eq = []
+    for s in range(args.steps):
+        t, _ = cpu_pass_sample(rows, cores, s)
+        eq.append(t)
+    t_equiv = sum(eq) / len(eq)
+    val = cores * XRES * YRES / t_equiv
+    cb = cpu_baseline_obj(rows, cores, t_equiv)
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": t_equiv * 1000.0 / cores, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": base_config(args.gpus),
+            "cpu_baseline": cb, "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+            "note": "CPU oracle (restatement of the Rust reference; cargo/rustc absent so the original cannot be built). "
+                    "ms_per_step = full-pass-equivalent seconds per pass / cores"}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ---------------------------------------------------------------------------
+# GPU side
+# ---------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                                       "-i", str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        return out
+
+
+class DevArray:
+    """__cuda_array_interface__ view of engine-owned device memory (for torch.as_tensor)."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 3, "strides": None}
+
+
+def run_gpu(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import ppmpa_b200 as P
+
+    world = env_int("WORLD_SIZE", 1)
+    rank = env_int("RANK", 0)
+    local = env_int("LOCAL_RANK", 0)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the engine has no CPU path)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    eng = P.Engine(local)
+    sc, cam = load_workload()
+    eng.set_scene(sc)
+    eng.set_camera(cam)
+    eng.accum_reset()
+    npix = XRES * YRES
+    K, W = args.steps, args.warmup
+    radii = P.radius_schedule(R0, W + K + 1)
+    stream = torch.cuda.ExternalStream(eng.stream, device=torch.device("cuda", local))
+    acc_ptr, acc_n = eng.accum_device()
+    acc = torch.as_tensor(DevArray(acc_ptr, acc_n), device=torch.device("cuda", local))
+
+    def one_pass(step):
+        # pass id (RNG stream) is globally unique; the radius depends on the per-rank step only
+        eng.iteration(SEED, step * world + rank, NPHOTON, float(radii[step]) ** 2, UC)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for s in range(W):
+        one_pass(s)
+    if world > 1:
+        with torch.cuda.stream(stream):
+            dist.reduce(acc, dst=0)                      # warm the communicator
+    eng.accum_reset()
+
+    # ---- device-resident timed region ----------------------------------------------------
+    sampler = ClockSampler(local)
+    phases = {}
+    counts = {}
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    sampler.start()
+    ev0.record(stream)
+    for s in range(K):
+        one_pass(W + s)
+        ms, ct = eng.last_pass_stats()
+        for k, v in ms.items():
+            phases[k] = phases.get(k, 0.0) + v
+        for k, v in ct.items():
+            counts[k] = counts.get(k, 0) + v
+    if world > 1:
+        with torch.cuda.stream(stream):
+            dist.reduce(acc, dst=0)                      # ONE reduce of (3*W*H + 1) doubles per frame
+    ev1.record(stream)
+    sync_all()
+    clocks = sampler.stop()
+    t_ms = torch.tensor([ev0.elapsed_time(ev1)], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    t_ms = float(t_ms.item())
+    value = world * npix * K / (t_ms / 1000.0)
+
+    # ---- end-to-end through the C ABI with host buffers --------------------------------
+    host_img = torch.empty((npix, 3), dtype=torch.float64).pin_memory().numpy()
+    h2d = (C.sizeof(P._capi.Prim) * sc.nprims + C.sizeof(P._capi.Material) * sc.nmats + C.sizeof(P._capi.Light) * sc.nlights
+           + C.sizeof(P._capi.Camera))
+    d2h = npix * 24
+    eng.accum_reset()
+    sync_all()
+    t0 = time.perf_counter()
+    for s in range(K):
+        eng.set_scene(sc)
+        eng.set_camera(cam)
+        one_pass(W + s)
+        eng.pass_image(host_img)
+    torch.cuda.synchronize()
+    te = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * npix * K / float(te.item())
+    checksum = float(host_img.sum())
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except (OSError, ValueError):
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        gather_s = phases["gather"] / 1000.0 / K
+        alg_bytes = (49.0 * counts["sum_k"] + 72.0 * counts["gather_nodes"]) / K          # per launch
+        achieved = alg_bytes / gather_s / 1e9
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "gather_traffic.json"))).get("dram_bytes_per_launch")
+        except (OSError, ValueError):
+            pass
+        roofline = {"bound": "hbm", "kernel": "k_gather", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": gather_s * 1000.0,
+                    "note": "algorithmic = 49 B x sum_q K_q + 72 B x N_q (logical gathered bytes, SURVEY 8d); the map is "
+                            "L2-sized and every photon is reused by many queries, so DRAM traffic is far below this"}
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            rows = env_int("PPM_BENCH_CPU_ROWS", 64)
+            cores = os.cpu_count() or 1
+            t_equiv, _ = cpu_pass_sample(rows, cores, W)
+            cpu = cpu_baseline_obj(rows, cores, t_equiv)
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": t_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "config": base_config(world), "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "checksum": checksum},
+                "gpu_launches": counts["launches"], "roofline": roofline, "cpu_baseline": cpu,
+                "photons_per_sec": world * NPHOTON * K / (t_ms / 1000.0),
+                "photon_trace_only_photons_per_sec": NPHOTON / (phases["photon_trace"] / 1000.0 / K),
+                "gather_only_pixels_per_sec": counts["gather_nodes"] / K / gather_s,
+                "time_to_100_passes_s": 100.0 / (world * K / (t_ms / 1000.0)),
+                "phases_ms_per_pass": {k: v / K for k, v in phases.items()},
+                "per_pass": {k: v / K for k, v in counts.items()}}
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_gpu(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -695,7 +695,6 @@ int do_map_build(ppm_ctx* c, double radius2) {
     CK(c, c->cub_tmp.ensure(tmp));
     CK(c, cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp, c->keys.as<uint64_t>(), c->keys2.as<uint64_t>(), c->vals.as<uint32_t>(),
                                           c->vals2.as<uint32_t>(), (int64_t)n, 0, end_bit, c->stream));
-    c->launches += 8;
     k_scatter<<<nblk((int64_t)n, 256), 256, 0, c->stream>>>(recbuf(c), c->vals2.as<uint32_t>(), n, mapsoa(c));
     KCHECK(c);
   }
@@ -704,7 +703,6 @@ int do_map_build(ppm_ctx* c, double radius2) {
     CK(c, cub::DeviceScan::ExclusiveSum(nullptr, tmp, c->hist.as<uint32_t>(), c->cell_start.as<uint32_t>(), (int64_t)g.ncells + 1, c->stream));
     CK(c, c->cub_tmp.ensure(tmp));
     CK(c, cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tmp, c->hist.as<uint32_t>(), c->cell_start.as<uint32_t>(), (int64_t)g.ncells + 1, c->stream));
-    c->launches += 2;
   }
   c->have_map = true;
   return PPM_OK;
@@ -749,7 +747,6 @@ int do_trace_rays(ppm_ctx* c, const double* drays, int64_t n, int64_t first_pixe
   CK(c, cub::DeviceScan::ExclusiveSum(nullptr, tmp, c->e_cnt.as<uint32_t>(), c->e_off.as<uint32_t>(), n + 1, c->stream));
   CK(c, c->cub_tmp.ensure(tmp));
   CK(c, cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tmp, c->e_cnt.as<uint32_t>(), c->e_off.as<uint32_t>(), n + 1, c->stream));
-  c->launches += 2;
   uint32_t nn = 0;
   CK(c, cudaMemcpyAsync(&nn, c->e_off.as<uint32_t>() + n, 4, cudaMemcpyDeviceToHost, c->stream));
   CK(c, cudaStreamSynchronize(c->stream));
