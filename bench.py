@@ -273,7 +273,7 @@ def run_gpu(args):
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-        gather_s = phases["gather"] / 1000.0 / K
+        gather_s = phases["gather_kernel"] / 1000.0 / K      # k_gather alone, CUDA events on the ctx stream
         alg_bytes = (49.0 * counts["sum_k"] + 72.0 * counts["gather_nodes"]) / K          # per launch
         achieved = alg_bytes / gather_s / 1e9
         traffic = None
@@ -300,7 +300,7 @@ def run_gpu(args):
                 "gpu_launches": counts["launches"], "roofline": roofline, "cpu_baseline": cpu,
                 "photons_per_sec": world * NPHOTON * K / (t_ms / 1000.0),
                 "photon_trace_only_photons_per_sec": NPHOTON / (phases["photon_trace"] / 1000.0 / K),
-                "gather_only_pixels_per_sec": counts["gather_nodes"] / K / gather_s,
+                "gather_only_queries_per_sec": counts["gather_nodes"] / K / (phases["gather"] / 1000.0 / K),
                 "time_to_100_passes_s": 100.0 / (world * K / (t_ms / 1000.0)),
                 "phases_ms_per_pass": {k: v / K for k, v in phases.items()},
                 "per_pass": {k: v / K for k, v in counts.items()}}

@@ -275,7 +275,8 @@ int  ppm_image_mean(ppm_ctx* ctx, double* rgb3_h_or_d);
 
 /* per-phase device times (ms, CUDA events on the ctx stream) of the last
  * ppm_render_pass: [0] photon trace, [1] map build, [2] eye expand,
- * [3] direct light, [4] gather, [5] combine+accumulate, [6] total;
+ * [3] direct light, [4] gather (query sort + kernel), [5] combine+accumulate, [6] total,
+ * [7] the k_gather kernel alone;
  * counters: [0] emitted, [1] stored records, [2] eye nodes, [3] gather nodes,
  * [4] sum of K (photons within r over all gather nodes), [5] kernel launches */
 int  ppm_last_pass_stats(ppm_ctx* ctx, double ms[8], uint64_t counters[8]);

@@ -116,6 +116,24 @@ __device__ __forceinline__ void consider(double t, int o, double& best_t, int& b
   if (best_o < 0 || t < best_t) { best_t = t; best_o = o; }
 }
 
+// consider(num / den) without the IEEE division whenever the outcome is certain.
+// A candidate only matters if NEARLY0 <= t and (no best yet or t < best_t).  The exact
+// quotient q = num/den satisfies fl(q) = q(1+e), |e| <= 2^-53, so with the 1e-9 guard
+// bands below every skipped case is provably one that consider() would also discard; all
+// other cases (and NaN/inf) take the exact division.  Results are bit-identical to the
+// plain `consider(num / den, ...)`.
+#define PPM_GUARD 1e-9
+__device__ __forceinline__ void consider_ratio(double num, double den, int o, double& best_t, int& best_o) {
+  const double an = fabs(num), ad = fabs(den);
+  if (num == 0.0 && ad > 0.0 && ad < 1e300) return;                                          // t = +-0 < NEARLY0
+  if (an > 0.0 && ad > 0.0 && an < 1e300 && ad < 1e300) {
+    if ((num < 0.0) != (den < 0.0)) return;                                                  // t < 0 (or -0)
+    if (an < ad * (PPM_NEARLY0 * (1.0 - PPM_GUARD))) return;                                 // t < NEARLY0
+    if (best_o >= 0 && best_t < 1e300 && an > (ad * best_t) * (1.0 + PPM_GUARD)) return;     // t > best_t
+  }
+  consider(num / den, o, best_t, best_o);
+}
+
 // geometry.rs:149-165 (u, v, t are computed before the rejection test)
 __device__ __forceinline__ bool moller(double l, D3 p0, D3 d1, D3 d2, D3 p, D3 d, double& t_out) {
   D3 re2 = cross(d, d2);
@@ -130,6 +148,55 @@ __device__ __forceinline__ bool moller(double l, D3 p0, D3 d1, D3 d2, D3 p, D3 d
   return true;
 }
 
+// Polygon / parallelogram candidate for the nearest-hit scan: same decisions and the same t
+// as `if (moller(...)) consider(t)`, but the three divisions are only executed when a
+// guard-banded sign/magnitude test cannot settle u, v, u+v or t (see consider_ratio).
+// Guard-banded classification of fl(x / det) against [0, 1]:
+//   -1 = certainly rejected (u < 0 or u > 1), +1 = certainly inside, 0 = undecided (divide).
+// Requires 1e-300 < |det| < 1e300.  A negative quotient is only "certain" when it cannot
+// underflow to -0 (which `u < 0.0` would not reject).
+__device__ __forceinline__ int classify01(double x, double det, double ad) {
+  const double ax = fabs(x);
+  if (!(ax < 1e300)) return 0;                               // inf / NaN -> exact path
+  if ((x < 0.0) != (det < 0.0)) return ax > ad * 1e-300 ? -1 : 0;
+  if (ax > ad * (1.0 + PPM_GUARD)) return -1;
+  return ax < ad * (1.0 - PPM_GUARD) ? 1 : 0;
+}
+__device__ __forceinline__ void consider_polygon(double l, D3 p0, D3 d1, D3 d2, D3 p, D3 d, int o, double& best_t, int& best_o) {
+  const D3 re2 = cross(d, d2);
+  const double det = dot(re2, d1);
+  if (det == 0.0) return;                                    // `det_a == 0.0 ||` -> None
+  const D3 pp = p - p0;
+  const double a = dot(re2, pp);                             // u = a / det
+  const double ad = fabs(det);
+  bool exact = !(ad < 1e300 && ad > 1e-300);
+  if (!exact) {
+    const int cu = classify01(a, det, ad);
+    if (cu < 0) return;
+    exact = cu == 0;
+  }
+  const D3 te1 = cross(pp, d1);
+  const double b = dot(te1, d);                              // v = b / det
+  if (!exact) {
+    const int cv = classify01(b, det, ad);
+    if (cv < 0) return;
+    exact = cv == 0;
+    if (!exact) {
+      const double sum = fabs(a) + fabs(b);                  // u + v against l (both quotients are >= 0 here)
+      if (sum > (ad * l) * (1.0 + PPM_GUARD)) return;
+      exact = !(sum < (ad * l) * (1.0 - PPM_GUARD));
+    }
+  }
+  const double c = dot(te1, d2);                             // t = c / det
+  if (exact) {
+    const double u = a / det, v = b / det, t = c / det;
+    if (u < 0.0 || u > 1.0 || v < 0.0 || v > 1.0 || u + v > l) return;
+    consider(t, o, best_t, best_o);
+    return;
+  }
+  consider_ratio(c, det, o, best_t, best_o);
+}
+
 __device__ __forceinline__ bool nearest_hit(const DevScene& sc, D3 pos, D3 dir, Isect& is) {
   double best_t = 0.0;
   int best_o = -1;
@@ -138,10 +205,10 @@ __device__ __forceinline__ bool nearest_hit(const DevScene& sc, D3 pos, D3 dir, 
     const ppm_prim& s = sc.prims[o];
     const int type = s.type;
     if (type == PPM_SHAPE_PLAIN) {
-      // geometry.rs:170-177
+      // geometry.rs:170-177: t = (dist + n.pos) / -cos0
       D3 n = ld3(s.nvec);
       double cos0 = dot(n, dir);
-      if (cos0 != 0.0) consider((s.scalar + dot(n, pos)) / -cos0, o, best_t, best_o);
+      if (cos0 != 0.0) consider_ratio(s.scalar + dot(n, pos), -cos0, o, best_t, best_o);
     } else if (type == PPM_SHAPE_SPHERE) {
       // geometry.rs:179-193
       D3 oc = ld3(s.position) - pos;
@@ -155,9 +222,7 @@ __device__ __forceinline__ bool nearest_hit(const DevScene& sc, D3 pos, D3 dir, 
       }
     } else if (type == PPM_SHAPE_POLYGON || type == PPM_SHAPE_PARALLELOGRAM) {
       // geometry.rs:195-202, l = 1 (triangle) / 2 (parallelogram), :141-143
-      double t;
-      if (moller(type == PPM_SHAPE_POLYGON ? 1.0 : 2.0, ld3(s.position), ld3(s.dir1), ld3(s.dir2), pos, dir, t))
-        consider(t, o, best_t, best_o);
+      consider_polygon(type == PPM_SHAPE_POLYGON ? 1.0 : 2.0, ld3(s.position), ld3(s.dir1), ld3(s.dir2), pos, dir, o, best_t, best_o);
     }
   }
   if (best_o < 0) return false;

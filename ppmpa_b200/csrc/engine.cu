@@ -18,7 +18,9 @@
 #include <cub/device/device_scan.cuh>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -166,8 +168,29 @@ __global__ void k_bbox(const double* __restrict__ pos3, uint64_t n, unsigned lon
     if ((threadIdx.x & 31) == 0) { atomicMin(&mm[k], lo[k]); atomicMax(&mm[3 + k], hi[k]); }
   }
 }
+// Per-axis histograms (AXIS_BINS bins over [lo, lo + AXIS_BINS*w)) for the trimmed grid region.
+#define AXIS_BINS 1024
+struct AxisRange { double lo[3], inv_w[3]; };
+__global__ void __launch_bounds__(256)
+k_axis_hist(const double* __restrict__ pos3, uint64_t n, AxisRange ar, uint32_t* __restrict__ hist) {
+  __shared__ uint32_t sh[3 * AXIS_BINS];
+  for (int i = threadIdx.x; i < 3 * AXIS_BINS; i += blockDim.x) sh[i] = 0;
+  __syncthreads();
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+    for (int k = 0; k < 3; ++k) {
+      double b = floor((pos3[i * 3 + k] - ar.lo[k]) * ar.inv_w[k]);
+      int bi = b < 0.0 ? 0 : (b > (double)(AXIS_BINS - 1) ? AXIS_BINS - 1 : (int)b);
+      atomicAdd(&sh[k * AXIS_BINS + bi], 1u);
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 3 * AXIS_BINS; i += blockDim.x)
+    if (sh[i]) atomicAdd(&hist[i], sh[i]);
+}
+// cell coordinate, clamped into the grid (see the note on the trimmed region in do_map_build)
 __device__ __forceinline__ int cell_coord(const Grid& g, double p, int ax) {
-  return (int)floor((p - g.org[ax]) * g.inv_cell);
+  const int nmax = (ax == 0 ? g.nx : (ax == 1 ? g.ny : g.nz)) - 1;
+  double f = floor((p - g.org[ax]) * g.inv_cell);
+  return f < 0.0 ? 0 : (f > (double)nmax ? nmax : (int)f);   // NaN -> 0
 }
 // sort key = (cell << 38) | (tag & (2^38-1)): photons ordered by cell, then by
 // (photon index, depth) -> the map is bit-reproducible whatever order the
@@ -177,25 +200,29 @@ __global__ void k_cell_key(Grid g, const double* __restrict__ pos3, const uint64
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   int cx = cell_coord(g, pos3[i * 3], 0), cy = cell_coord(g, pos3[i * 3 + 1], 1), cz = cell_coord(g, pos3[i * 3 + 2], 2);
-  cx = min(max(cx, 0), g.nx - 1); cy = min(max(cy, 0), g.ny - 1); cz = min(max(cz, 0), g.nz - 1);
   uint32_t c = ((uint32_t)cz * (uint32_t)g.ny + (uint32_t)cy) * (uint32_t)g.nx + (uint32_t)cx;
   keys[i] = ((uint64_t)c << 38) | (tag[i] & ((1ull << 38) - 1ull));
   vals[i] = (uint32_t)i;
   atomicAdd(&hist[c], 1u);
 }
-// Sorted structure-of-arrays photon map.
+// Sorted photon map, laid out for 16-byte vector loads: per photon two double2
+// for (px, py | pz, wavelength-bits) and two for (dx, dy | dz, 0).  64 B physical
+// per photon (49 B of information).
 struct MapSoA {
-  double *px, *py, *pz, *dx, *dy, *dz;
-  uint8_t* wl;
+  double2* P;       // [n][2]
+  double2* D;       // [n][2]
   uint32_t* orig;   // index in the unsorted (import/export) order
 };
 __global__ void k_scatter(RecBuf rec, const uint32_t* __restrict__ vals, uint64_t n, MapSoA m) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   uint32_t s = vals[i];
-  m.px[i] = rec.pos3[(uint64_t)s * 3]; m.py[i] = rec.pos3[(uint64_t)s * 3 + 1]; m.pz[i] = rec.pos3[(uint64_t)s * 3 + 2];
-  m.dx[i] = rec.dir3[(uint64_t)s * 3]; m.dy[i] = rec.dir3[(uint64_t)s * 3 + 1]; m.dz[i] = rec.dir3[(uint64_t)s * 3 + 2];
-  m.wl[i] = rec.wl[s];
+  const double* p = rec.pos3 + (uint64_t)s * 3;
+  const double* d = rec.dir3 + (uint64_t)s * 3;
+  m.P[i * 2] = make_double2(p[0], p[1]);
+  m.P[i * 2 + 1] = make_double2(p[2], __longlong_as_double((long long)rec.wl[s]));
+  m.D[i * 2] = make_double2(d[0], d[1]);
+  m.D[i * 2 + 1] = make_double2(d[2], 0.0);
   m.orig[i] = s;
 }
 
@@ -213,49 +240,121 @@ __device__ __forceinline__ double filter_gauss(double d, double rmax) {
   return e_r > E_BETA ? 0.0 : ALPHA * (1.0 - e_r / E_BETA) + CORR;
 }
 
-// v1: one thread per query, photons read straight from the sorted SoA (L1/L2).
+// Queries are keyed by their (padded) grid cell and radix sorted, so that the 32
+// lanes of a warp hold queries of the same cell (or of a few cells).
+__global__ void k_query_key(Grid g, const double* __restrict__ qpos3, int64_t n, uint32_t* __restrict__ keys,
+                            uint32_t* __restrict__ vals) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int cx = cell_coord(g, qpos3[i * 3], 0), cy = cell_coord(g, qpos3[i * 3 + 1], 1), cz = cell_coord(g, qpos3[i * 3 + 2], 2);
+  uint32_t key = ((uint32_t)cz * (uint32_t)g.ny + (uint32_t)cy) * (uint32_t)g.nx + (uint32_t)cx;
+  keys[i] = key;
+  vals[i] = (uint32_t)i;
+}
+
+// v2: warp-cooperative gather.  A warp owns 32 cell-sorted queries (one per lane).
+// For each distinct cell among them, the photons of the 3x3x3 neighbourhood (nine
+// x-contiguous runs of the sorted map) form one virtual candidate stream; 32
+// candidates at a time are fetched with coalesced 16-byte loads, staged in shared
+// memory, and every lane tests the SAME photon (broadcast LDS.128) against its own
+// query -- no per-lane loop lengths, no scattered global loads.
+#define GATHER_WARPS 4
 template <int FILTER>
-__global__ void __launch_bounds__(128)
-k_gather(Grid g, const uint32_t* __restrict__ cell_start, MapSoA m, const double* __restrict__ qpos3,
-         const double* __restrict__ qnrm3, int64_t n, double power, double r2, double* __restrict__ rgb3,
-         uint32_t* __restrict__ counts, unsigned long long* __restrict__ sum_k) {
-  int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(GATHER_WARPS * 32)
+k_gather(Grid g, const uint32_t* __restrict__ cell_start, MapSoA m, const uint32_t* __restrict__ qkey,
+         const uint32_t* __restrict__ qidx, const double* __restrict__ qpos3, const double* __restrict__ qnrm3, int64_t n,
+         double power, double r2, double* __restrict__ rgb3, uint32_t* __restrict__ counts,
+         unsigned long long* __restrict__ sum_k) {
+  __shared__ double2 sP[GATHER_WARPS][32][2];
+  __shared__ double2 sD[GATHER_WARPS][32][2];
+  const unsigned FULL = 0xffffffffu;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t s = ((int64_t)blockIdx.x * GATHER_WARPS + warp) * 32 + lane;
+  const bool valid = s < n;
+  const uint32_t key = valid ? qkey[s] : 0xFFFFFFFFu;
+  const uint32_t qi = valid ? qidx[s] : 0u;
+  double qx = 0.0, qy = 0.0, qz = 0.0;
+  D3 nv = mk3(0.0, 0.0, 0.0);
+  if (valid) {
+    qx = qpos3[(uint64_t)qi * 3]; qy = qpos3[(uint64_t)qi * 3 + 1]; qz = qpos3[(uint64_t)qi * 3 + 2];
+    nv = ld3(qnrm3 + (uint64_t)qi * 3);
+  }
+  double rr = 0.0, rg = 0.0, rb = 0.0;
   uint32_t cnt = 0;
-  if (q < n) {
-    const double qx = qpos3[q * 3], qy = qpos3[q * 3 + 1], qz = qpos3[q * 3 + 2];
-    const D3 nv = ld3(qnrm3 + q * 3);
-    double rr = 0.0, rg = 0.0, rb = 0.0;
-    int cx = cell_coord(g, qx, 0), cy = cell_coord(g, qy, 1), cz = cell_coord(g, qz, 2);
-    int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.nx - 1);
-    if (x0 <= x1) {
-      for (int z = max(cz - 1, 0); z <= min(cz + 1, g.nz - 1); ++z)
-        for (int y = max(cy - 1, 0); y <= min(cy + 1, g.ny - 1); ++y) {
-          uint32_t row = ((uint32_t)z * (uint32_t)g.ny + (uint32_t)y) * (uint32_t)g.nx;
-          uint32_t b = cell_start[row + x0], e = cell_start[row + x1 + 1];
-          for (uint32_t j = b; j < e; ++j) {
-            // squared_euclidean: ((qx-px)^2 + (qy-py)^2) + (qz-pz)^2, member iff d2 <= r2
-            double ax = qx - m.px[j], ay = qy - m.py[j], az = qz - m.pz[j];
-            double d2 = (ax * ax + ay * ay) + az * az;
-            if (d2 <= r2) {
-              ++cnt;
-              double wt = FILTER == PPM_FILTER_NONE ? 1.0 : (FILTER == PPM_FILTER_CONE ? filter_cone(d2, r2) : filter_gauss(d2, r2));
-              // photon_to_radiance, optics.rs:224-233
-              double cos0 = (nv.x * m.dx[j] + nv.y * m.dy[j]) + nv.z * m.dz[j];
-              double pw2 = cos0 < 0.0 ? (wt * power) * -cos0 : 0.0;
-              int w = m.wl[j];
-              if (w == 0) rr = rr + pw2; else if (w == 1) rg = rg + pw2; else rb = rb + pw2;
-            }
+  const uint32_t nxp = (uint32_t)g.nx, nyp = (uint32_t)g.ny;
+  unsigned pending = __ballot_sync(FULL, valid);
+  while (pending) {
+    const int leader = __ffs(pending) - 1;
+    const uint32_t ck = __shfl_sync(FULL, key, leader);
+    const bool act = key == ck;
+    pending &= ~__ballot_sync(FULL, act);
+    const int cx = (int)(ck % nxp), cy = (int)((ck / nxp) % nyp), cz = (int)(ck / (nxp * nyp));
+    const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.nx - 1);
+    // lane l < 9 looks up run l = (dz, dy) of the neighbourhood
+    uint32_t rbeg = 0, rlen = 0;
+    if (lane < 9 && x0 <= x1) {
+      const int z = cz + lane / 3 - 1, y = cy + lane % 3 - 1;
+      if (z >= 0 && z < g.nz && y >= 0 && y < g.ny) {
+        const uint32_t row = ((uint32_t)z * (uint32_t)g.ny + (uint32_t)y) * (uint32_t)g.nx;
+        rbeg = cell_start[row + x0];
+        rlen = cell_start[row + x1 + 1] - rbeg;
+      }
+    }
+    uint32_t pre = rlen;                               // inclusive prefix of run lengths over lanes 0..8
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1) {
+      uint32_t t = __shfl_up_sync(FULL, pre, o);
+      if (lane >= o) pre += t;
+    }
+    const uint32_t total = __shfl_sync(FULL, pre, 8);
+    uint32_t cend[9], off[9];                          // cumulative end and (start - exclusive prefix) of each run
+#pragma unroll
+    for (int r = 0; r < 9; ++r) {
+      cend[r] = __shfl_sync(FULL, pre, r);
+      off[r] = __shfl_sync(FULL, rbeg - (pre - rlen), r);
+    }
+    for (uint32_t base = 0; base < total; base += 32) {
+      const uint32_t v = base + lane;
+      if (v < total) {
+        uint32_t o = off[0];
+#pragma unroll
+        for (int r = 1; r < 9; ++r) o = v >= cend[r - 1] ? off[r] : o;
+        const uint64_t j = (uint64_t)(v + o) * 2;
+        sP[warp][lane][0] = m.P[j]; sP[warp][lane][1] = m.P[j + 1];
+        sD[warp][lane][0] = m.D[j]; sD[warp][lane][1] = m.D[j + 1];
+      }
+      __syncwarp();
+      const int mcount = (int)min(32u, total - base);
+      if (act) {
+        for (int t = 0; t < mcount; ++t) {
+          const double2 a = sP[warp][t][0], b = sP[warp][t][1];
+          // squared_euclidean: ((qx-px)^2 + (qy-py)^2) + (qz-pz)^2, member iff d2 <= r2
+          const double ax = qx - a.x, ay = qy - a.y, az = qz - b.x;
+          const double d2 = (ax * ax + ay * ay) + az * az;
+          if (d2 <= r2) {
+            ++cnt;
+            const double wt = FILTER == PPM_FILTER_NONE ? 1.0 : (FILTER == PPM_FILTER_CONE ? filter_cone(d2, r2) : filter_gauss(d2, r2));
+            const double2 c = sD[warp][t][0], d = sD[warp][t][1];
+            // photon_to_radiance, optics.rs:224-233
+            const double cos0 = (nv.x * c.x + nv.y * c.y) + nv.z * d.x;
+            const double pw2 = cos0 < 0.0 ? (wt * power) * -cos0 : 0.0;
+            const int w = (int)__double_as_longlong(b.y);
+            if (w == 0) rr = rr + pw2; else if (w == 1) rg = rg + pw2; else rb = rb + pw2;
           }
         }
+      }
+      __syncwarp();
     }
-    const double s = (1.0 / PPM_PI) / r2;     // rad * (ONE_PI / radius), tracer.rs:193
-    rgb3[q * 3] = rr * s; rgb3[q * 3 + 1] = rg * s; rgb3[q * 3 + 2] = rb * s;
-    if (counts) counts[q] = cnt;
+  }
+  if (valid) {
+    const double sc = (1.0 / PPM_PI) / r2;            // rad * (ONE_PI / radius), tracer.rs:193
+    rgb3[(uint64_t)qi * 3] = rr * sc; rgb3[(uint64_t)qi * 3 + 1] = rg * sc; rgb3[(uint64_t)qi * 3 + 2] = rb * sc;
+    if (counts) counts[qi] = cnt;
   }
   if (sum_k) {
     unsigned long long c = cnt;
-    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-    if ((threadIdx.x & 31) == 0 && c) atomicAdd(sum_k, c);
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(FULL, c, o);
+    if (lane == 0 && c) atomicAdd(sum_k, c);
   }
 }
 
@@ -273,7 +372,8 @@ __global__ void k_within(Grid g, const uint32_t* __restrict__ cell_start, MapSoA
         uint32_t row = ((uint32_t)z * (uint32_t)g.ny + (uint32_t)y) * (uint32_t)g.nx;
         uint32_t b = cell_start[row + x0], e = cell_start[row + x1 + 1];
         for (uint32_t j = b; j < e; ++j) {
-          double ax = qx - m.px[j], ay = qy - m.py[j], az = qz - m.pz[j];
+          const double2 a = m.P[(uint64_t)j * 2], b = m.P[(uint64_t)j * 2 + 1];
+          double ax = qx - a.x, ay = qy - a.y, az = qz - b.x;
           double d2 = (ax * ax + ay * ay) + az * az;
           if (d2 <= r2) {
             if (cnt < cap) idx[(uint64_t)q * cap + cnt] = m.orig[j];
@@ -392,68 +492,56 @@ k_eye_expand(const __grid_constant__ DevScene sc, const __grid_constant__ ppm_ca
   }
 }
 
-// ---- direct light: one warp per gather node, one lane per light sample -------------
+// ---- direct light: one thread per gather node, samples walked sequentially ----------
 // get_radiance_from_light (tracer.rs:263-270) pairs [0, L(d0), L(d1), ...] with
-// [c0, c1, c2, ...] (the RADIANCE0 seed of light.rs:132): the i-th surviving
-// sample is weighted with the radiance of the (i-1)-th.  Point and sun lights
-// have one sample, which is paired with the zero -> they contribute nothing.
-__device__ __forceinline__ double ts5(unsigned i) {   // the literals 0.1, 0.3, 0.5, 0.7, 0.9
+// [c0, c1, c2, ...] (the RADIANCE0 seed of light.rs:132): the i-th surviving sample is
+// weighted with the radiance of the (i-1)-th.  Walking the 25 samples in order inside one
+// thread turns that pairing into a register recurrence and reproduces the reference's
+// summation order.  Point and sun lights have a single sample, which is paired with the
+// zero -> they contribute nothing and are skipped.
+__device__ __forceinline__ double ts5(unsigned i) {   // the literals 0.1, 0.3, 0.5, 0.7, 0.9 (light.rs:164-170)
   return i == 0 ? 0.1 : (i == 1 ? 0.3 : (i == 2 ? 0.5 : (i == 3 ? 0.7 : 0.9)));
 }
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 k_direct_light(const __grid_constant__ DevScene sc, const double* __restrict__ pos3, const double* __restrict__ nrm3,
                int64_t n, double* __restrict__ out3) {
-  const int64_t node = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const unsigned lane = threadIdx.x & 31u;
+  const int64_t node = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (node >= n) return;
   const D3 p = ld3(pos3 + node * 3), nv = ld3(nrm3 + node * 3);
   D3 total = mk3(0.0, 0.0, 0.0);
   for (int li = 0; li < sc.nlights; ++li) {
     const ppm_light& l = sc.lights[li];
     if (l.type != PPM_LIGHT_PARALLELOGRAM) continue;
-    bool valid = lane < 25;
-    double sq_ldist = 0.0, cc = 0.0;
-    if (valid) {
-      // TSS[lane] = (TS[lane/5], TS[lane%5]), light.rs:164-170
-      D3 gp = (ld3(l.pos) + ts5(lane / 5) * ld3(l.dir1)) + ts5(lane % 5) * ld3(l.dir2);   // gen_pos, light.rs:152-154
-      D3 d = gp - p;
-      valid = dot(ld3(l.nvec), d) < 0.0;
+    const D3 lpos = ld3(l.pos), ldir1 = ld3(l.dir1), ldir2 = ld3(l.dir2), lnv = ld3(l.nvec);
+    const double PI4 = PPM_PI * 4.0;
+    const double lnum = 2.0 * l.flux * 0.2 * 0.2;           // 2 * flux * PARA_DIV * PARA_DIV, light.rs:142
+    D3 rad = mk3(0.0, 0.0, 0.0);
+    bool have_prev = false;
+    double dprev = 0.0;
+    for (unsigned s = 0; s < 25; ++s) {
+      const D3 gp = (lpos + ts5(s / 5) * ldir1) + ts5(s % 5) * ldir2;   // gen_pos, light.rs:152-154
+      const D3 d = gp - p;
+      if (!(dot(lnv, d) < 0.0)) continue;                   // light.rs:112
       D3 ld;
-      if (valid) valid = normalize(d, ld);
-      if (valid) {
-        double cos0 = dot(nv, ld);
-        if (cos0 < 0.0) valid = false;
-        else {
-          Isect is;
-          if (!nearest_hit(sc, p, ld, is)) valid = false;     // no hit counts as occluded, tracer.rs:282
-          else {
-            sq_ldist = dot(d, d);
-            D3 po = is.pos - p;
-            double sq_odist = dot(po, po);
-            if (sq_ldist - sq_odist > 0.002) valid = false;
-            cc = cos0 * cos0;
-          }
-        }
+      if (!normalize(d, ld)) continue;                      // tracer.rs:275-276
+      const double cos0 = dot(nv, ld);
+      if (cos0 < 0.0) continue;
+      Isect is;
+      if (!nearest_hit(sc, p, ld, is)) continue;            // no hit counts as occluded, tracer.rs:282
+      const double sq_ldist = dot(d, d);
+      const D3 po = is.pos - p;
+      if (sq_ldist - dot(po, po) > 0.002) continue;
+      if (have_prev) {
+        const double l0 = lnum / (PI4 * dprev);
+        const double cc = cos0 * cos0;
+        rad = rad + mk3((l.color[0] * l0) * cc, (l.color[1] * l0) * cc, (l.color[2] * l0) * cc);
       }
+      have_prev = true;
+      dprev = sq_ldist;
     }
-    unsigned mask = __ballot_sync(0xffffffffu, valid);
-    unsigned lower = mask & ((1u << lane) - 1u);
-    int src = lower ? 31 - __clz(lower) : (int)lane;
-    double dprev = __shfl_sync(0xffffffffu, sq_ldist, src);
-    D3 term = mk3(0.0, 0.0, 0.0);
-    if (valid && lower) {
-      const double PI4 = PPM_PI * 4.0;
-      double l0 = (2.0 * l.flux * 0.2 * 0.2) / (PI4 * dprev);    // light.rs:142
-      term = mk3((l.color[0] * l0) * cc, (l.color[1] * l0) * cc, (l.color[2] * l0) * cc);
-    }
-    for (int o = 16; o > 0; o >>= 1) {
-      term.x += __shfl_xor_sync(0xffffffffu, term.x, o);
-      term.y += __shfl_xor_sync(0xffffffffu, term.y, o);
-      term.z += __shfl_xor_sync(0xffffffffu, term.z, o);
-    }
-    total = total + term;
+    total = total + rad;
   }
-  if (lane == 0) st3(out3 + node * 3, total);
+  st3(out3 + node * 3, total);
 }
 
 // ---- combine + accumulate ------------------------------------------------------------
@@ -493,7 +581,7 @@ struct DBuf {
     if (bytes <= cap) return cudaSuccess;
     if (p) cudaFree(p);
     p = nullptr; cap = 0;
-    size_t want = bytes + bytes / 4 + 256;
+    size_t want = bytes * 2 + 256;   // geometric growth: steady state never reallocates
     cudaError_t e = cudaMalloc(&p, want);
     if (e == cudaSuccess) cap = want;
     return e;
@@ -514,8 +602,9 @@ struct ppm_ctx {
   uint64_t n_rec = 0;
   double power = 0.0;
   // map
-  DBuf keys, keys2, vals, vals2, cub_tmp, cell_start, hist, bbox;
-  DBuf m_px, m_py, m_pz, m_dx, m_dy, m_dz, m_wl, m_orig;
+  DBuf keys, keys2, vals, vals2, cub_tmp, cell_start, hist, bbox, axis_hist;
+  DBuf m_P, m_D, m_orig;
+  DBuf q_key, q_key2, q_idx, q_idx2;
   Grid grid;
   double r2 = 0.0;
   // staging for h_or_d arguments
@@ -528,6 +617,7 @@ struct ppm_ctx {
   double ms[8] = {0};
   uint64_t counters[8] = {0};
   cudaEvent_t ev[8] = {nullptr};
+  bool ev_gather_inner = false;   // record ev[7] right before the k_gather launch (render_pass only)
   uint64_t launches = 0;
 };
 
@@ -595,9 +685,7 @@ int ensure_records(ppm_ctx* c, uint64_t cap) {
 }
 MapSoA mapsoa(ppm_ctx* c) {
   MapSoA m;
-  m.px = c->m_px.as<double>(); m.py = c->m_py.as<double>(); m.pz = c->m_pz.as<double>();
-  m.dx = c->m_dx.as<double>(); m.dy = c->m_dy.as<double>(); m.dz = c->m_dz.as<double>();
-  m.wl = c->m_wl.as<uint8_t>(); m.orig = c->m_orig.as<uint32_t>();
+  m.P = c->m_P.as<double2>(); m.D = c->m_D.as<double2>(); m.orig = c->m_orig.as<uint32_t>();
   return m;
 }
 int light_split(ppm_ctx* c, const int64_t* n_per_light, LightSplit* ls, int64_t* total) {
@@ -635,7 +723,22 @@ int do_trace_photons(ppm_ctx* c, uint64_t seed, uint32_t pass, int uc, const int
   return PPM_OK;
 }
 
+struct HostTrace {
+  bool on; std::chrono::steady_clock::time_point t0; std::string log; cudaStream_t st;
+  explicit HostTrace(cudaStream_t s) : on(std::getenv("PPM_TRACE") != nullptr), t0(std::chrono::steady_clock::now()), st(s) {}
+  void mark(const char* what) {
+    if (!on) return;
+    cudaStreamSynchronize(st);
+    auto t1 = std::chrono::steady_clock::now();
+    char b[96];
+    std::snprintf(b, sizeof b, " %s=%.3f", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    log += b; t0 = t1;
+  }
+  ~HostTrace() { if (on) std::fprintf(stderr, "[ppm trace]%s\n", log.c_str()); }
+};
+
 int do_map_build(ppm_ctx* c, double radius2) {
+  HostTrace tr(c->stream);
   if (!(radius2 > 0.0)) return fail(c, PPM_ERR_ARG, "radius2 must be > 0");
   const uint64_t n = c->n_rec;
   c->r2 = radius2;
@@ -655,33 +758,85 @@ int do_map_build(ppm_ctx* c, double radius2) {
     CK(c, cudaStreamSynchronize(c->stream));
     double lo[3], hi[3];
     for (int k = 0; k < 3; ++k) { lo[k] = dec_ord(mm[k]); hi[k] = dec_ord(mm[3 + k]); }
+    tr.mark("bbox");
     for (int k = 0; k < 3; ++k)
       if (!(lo[k] == lo[k]) || !(hi[k] == hi[k]) || std::isinf(lo[k]) || std::isinf(hi[k]))
         return fail(c, PPM_ERR_ARG, "photon positions are not finite");
+    // Region covered by the dense grid.  The reference leaks a few photons (~1e-4) through
+    // wall corners (a bounce closer than NEARLY0 to the next wall skips it), and those land
+    // tens of metres outside the room on the infinite planes, so the raw bounding box is
+    // erratic and mostly empty.  The grid therefore covers a per-axis TRIMMED range (at most
+    // n/1024 photons cut on each side, found with device histograms); photons and queries
+    // outside are clamped into the boundary cells, which keeps the 27-cell walk exact
+    // (clamping never increases the cell distance of two points).
+    const uint64_t trim = n >= 4096 ? n / 1024 : 0;
+    if (trim > 0) {
+      CK(c, c->axis_hist.ensure(3 * AXIS_BINS * 4));
+      std::vector<uint32_t> hh(3 * AXIS_BINS);
+      for (int iter = 0; iter < 4; ++iter) {
+        AxisRange ar;
+        double w[3];
+        bool fine = true;
+        for (int k = 0; k < 3; ++k) {
+          w[k] = (hi[k] - lo[k]) / (double)AXIS_BINS;
+          if (!(w[k] > 0.0)) w[k] = 1.0;
+          ar.lo[k] = lo[k]; ar.inv_w[k] = 1.0 / w[k];
+          if (w[k] > 0.5 * cell) fine = false;
+        }
+        if (iter > 0 && fine) break;
+        CK(c, cudaMemsetAsync(c->axis_hist.p, 0, 3 * AXIS_BINS * 4, c->stream));
+        k_axis_hist<<<std::min<unsigned>(nblk((int64_t)n, 256 * 8), 148 * 4), 256, 0, c->stream>>>(c->r_pos.as<double>(), n, ar,
+                                                                                              c->axis_hist.as<uint32_t>());
+        KCHECK(c);
+        CK(c, cudaMemcpyAsync(hh.data(), c->axis_hist.p, 3 * AXIS_BINS * 4, cudaMemcpyDeviceToHost, c->stream));
+        CK(c, cudaStreamSynchronize(c->stream));
+        for (int k = 0; k < 3; ++k) {
+          const uint32_t* h = hh.data() + k * AXIS_BINS;
+          uint64_t acc = 0;
+          int a = 0, b = AXIS_BINS - 1;
+          while (a < AXIS_BINS - 1 && acc + h[a] <= trim) acc += h[a++];
+          acc = 0;
+          while (b > a && acc + h[b] <= trim) acc += h[b--];
+          double nlo = lo[k] + (double)a * w[k], nhi = lo[k] + (double)(b + 1) * w[k];
+          lo[k] = std::max(lo[k], nlo); hi[k] = std::min(hi[k], nhi);
+        }
+        if (fine) break;
+      }
+      tr.mark("trim");
+    }
+    // The origin is padded by half a cell: surfaces that bound the photon cloud (the room's
+    // walls) then sit mid-cell, so the +-1 ulp noise of hit points on such a plane cannot
+    // straddle a cell boundary (which would split every warp of queries on that wall).
     const double CELL_CAP = 67108864.0;   // 2^26 cells
     for (;;) {
       double dims[3];
-      for (int k = 0; k < 3; ++k) dims[k] = std::floor((hi[k] - lo[k]) / cell) + 2.0;
+      for (int k = 0; k < 3; ++k) dims[k] = std::floor((hi[k] - (lo[k] - 0.5 * cell)) / cell) + 2.0;
       if (dims[0] * dims[1] * dims[2] <= CELL_CAP && dims[0] < 2e9 && dims[1] < 2e9 && dims[2] < 2e9) {
         g.nx = (int32_t)dims[0]; g.ny = (int32_t)dims[1]; g.nz = (int32_t)dims[2];
         break;
       }
       cell *= 2.0;
     }
-    for (int k = 0; k < 3; ++k) g.org[k] = lo[k];
+    for (int k = 0; k < 3; ++k) g.org[k] = lo[k] - 0.5 * cell;
     g.inv_cell = 1.0 / cell;
     g.ncells = (uint32_t)g.nx * (uint32_t)g.ny * (uint32_t)g.nz;
   }
   c->grid = g;
-  CK(c, c->hist.ensure(((size_t)g.ncells + 1) * 4));
-  CK(c, c->cell_start.ensure(((size_t)g.ncells + 1) * 4));
+  {
+    // cudaFree/cudaMalloc stall for 10-400 ms on this platform: size the cell tables for at
+    // least 2^23 cells up front so the shrinking radius does not regrow them every few passes
+    size_t want = std::max<size_t>((size_t)g.ncells + 1, (size_t)1 << 23) * 4;
+    CK(c, c->hist.ensure(want));
+    CK(c, c->cell_start.ensure(want));
+  }
+  tr.mark("alloc_cells");
   CK(c, cudaMemsetAsync(c->hist.p, 0, ((size_t)g.ncells + 1) * 4, c->stream));
+  tr.mark("memset");
   size_t nn = n ? n : 1;
   CK(c, c->keys.ensure(nn * 8)); CK(c, c->keys2.ensure(nn * 8));
   CK(c, c->vals.ensure(nn * 4)); CK(c, c->vals2.ensure(nn * 4));
-  CK(c, c->m_px.ensure(nn * 8)); CK(c, c->m_py.ensure(nn * 8)); CK(c, c->m_pz.ensure(nn * 8));
-  CK(c, c->m_dx.ensure(nn * 8)); CK(c, c->m_dy.ensure(nn * 8)); CK(c, c->m_dz.ensure(nn * 8));
-  CK(c, c->m_wl.ensure(nn)); CK(c, c->m_orig.ensure(nn * 4));
+  CK(c, c->m_P.ensure(nn * 32)); CK(c, c->m_D.ensure(nn * 32)); CK(c, c->m_orig.ensure(nn * 4));
+  tr.mark("alloc_map");
   if (n > 0) {
     k_cell_key<<<nblk((int64_t)n, 256), 256, 0, c->stream>>>(g, c->r_pos.as<double>(), c->r_tag.as<uint64_t>(), n,
                                                             c->keys.as<uint64_t>(), c->vals.as<uint32_t>(), c->hist.as<uint32_t>());
@@ -693,10 +848,13 @@ int do_map_build(ppm_ctx* c, double radius2) {
     CK(c, cub::DeviceRadixSort::SortPairs(nullptr, tmp, c->keys.as<uint64_t>(), c->keys2.as<uint64_t>(), c->vals.as<uint32_t>(),
                                           c->vals2.as<uint32_t>(), (int64_t)n, 0, end_bit, c->stream));
     CK(c, c->cub_tmp.ensure(tmp));
+    tr.mark("key");
     CK(c, cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp, c->keys.as<uint64_t>(), c->keys2.as<uint64_t>(), c->vals.as<uint32_t>(),
                                           c->vals2.as<uint32_t>(), (int64_t)n, 0, end_bit, c->stream));
+    tr.mark("sort");
     k_scatter<<<nblk((int64_t)n, 256), 256, 0, c->stream>>>(recbuf(c), c->vals2.as<uint32_t>(), n, mapsoa(c));
     KCHECK(c);
+    tr.mark("scatter");
   }
   {
     size_t tmp = 0;
@@ -704,6 +862,7 @@ int do_map_build(ppm_ctx* c, double radius2) {
     CK(c, c->cub_tmp.ensure(tmp));
     CK(c, cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tmp, c->hist.as<uint32_t>(), c->cell_start.as<uint32_t>(), (int64_t)g.ncells + 1, c->stream));
   }
+  tr.mark("scan");
   c->have_map = true;
   return PPM_OK;
 }
@@ -711,19 +870,38 @@ int do_map_build(ppm_ctx* c, double radius2) {
 int launch_gather(ppm_ctx* c, const double* dpos, const double* dnrm, int64_t n, int filter, double* drgb, uint32_t* dcounts,
                   unsigned long long* dsumk) {
   if (n <= 0) return PPM_OK;
-  const int B = 128;
+  if (n >= (1ll << 32)) return fail(c, PPM_ERR_CAPACITY, "at most 2^32-1 gather queries per call");
+  if (filter < PPM_FILTER_NONE || filter > PPM_FILTER_GAUSS) return fail(c, PPM_ERR_ARG, "bad filter");
+  // 1. key the queries by cell and sort them (stable: ties keep query order -> deterministic)
+  CK(c, c->q_key.ensure((size_t)n * 4)); CK(c, c->q_key2.ensure((size_t)n * 4));
+  CK(c, c->q_idx.ensure((size_t)n * 4)); CK(c, c->q_idx2.ensure((size_t)n * 4));
+  k_query_key<<<nblk(n, 256), 256, 0, c->stream>>>(c->grid, dpos, n, c->q_key.as<uint32_t>(), c->q_idx.as<uint32_t>());
+  KCHECK(c);
+  unsigned long long maxkey = c->grid.ncells;
+  int bits = 1;
+  while (bits < 32 && (1ull << bits) < maxkey) ++bits;
+  size_t tmp = 0;
+  CK(c, cub::DeviceRadixSort::SortPairs(nullptr, tmp, c->q_key.as<uint32_t>(), c->q_key2.as<uint32_t>(), c->q_idx.as<uint32_t>(),
+                                        c->q_idx2.as<uint32_t>(), n, 0, bits, c->stream));
+  CK(c, c->cub_tmp.ensure(tmp));
+  CK(c, cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp, c->q_key.as<uint32_t>(), c->q_key2.as<uint32_t>(), c->q_idx.as<uint32_t>(),
+                                        c->q_idx2.as<uint32_t>(), n, 0, bits, c->stream));
+  // 2. warp-cooperative gather over the sorted queries
+  if (c->ev_gather_inner) cudaEventRecord(c->ev[7], c->stream);
+  const int B = GATHER_WARPS * 32;
   const uint32_t* cs = c->cell_start.as<uint32_t>();
+  const uint32_t* qk = c->q_key2.as<uint32_t>();
+  const uint32_t* qx = c->q_idx2.as<uint32_t>();
   switch (filter) {
     case PPM_FILTER_NONE:
-      k_gather<PPM_FILTER_NONE><<<nblk(n, B), B, 0, c->stream>>>(c->grid, cs, mapsoa(c), dpos, dnrm, n, c->power, c->r2, drgb, dcounts, dsumk);
+      k_gather<PPM_FILTER_NONE><<<nblk(n, B), B, 0, c->stream>>>(c->grid, cs, mapsoa(c), qk, qx, dpos, dnrm, n, c->power, c->r2, drgb, dcounts, dsumk);
       break;
     case PPM_FILTER_CONE:
-      k_gather<PPM_FILTER_CONE><<<nblk(n, B), B, 0, c->stream>>>(c->grid, cs, mapsoa(c), dpos, dnrm, n, c->power, c->r2, drgb, dcounts, dsumk);
+      k_gather<PPM_FILTER_CONE><<<nblk(n, B), B, 0, c->stream>>>(c->grid, cs, mapsoa(c), qk, qx, dpos, dnrm, n, c->power, c->r2, drgb, dcounts, dsumk);
       break;
-    case PPM_FILTER_GAUSS:
-      k_gather<PPM_FILTER_GAUSS><<<nblk(n, B), B, 0, c->stream>>>(c->grid, cs, mapsoa(c), dpos, dnrm, n, c->power, c->r2, drgb, dcounts, dsumk);
+    default:
+      k_gather<PPM_FILTER_GAUSS><<<nblk(n, B), B, 0, c->stream>>>(c->grid, cs, mapsoa(c), qk, qx, dpos, dnrm, n, c->power, c->r2, drgb, dcounts, dsumk);
       break;
-    default: return fail(c, PPM_ERR_ARG, "bad filter");
   }
   KCHECK(c);
   return PPM_OK;
@@ -759,7 +937,7 @@ int do_trace_rays(ppm_ctx* c, const double* drays, int64_t n, int64_t first_pixe
   KCHECK(c);
   if (timed) cudaEventRecord(c->ev[3], c->stream);
   if (uc && nn) {
-    k_direct_light<<<nblk((int64_t)nn * 32, 256), 256, 0, c->stream>>>(c->scene, nodes.pos3, nodes.nrm3, nn, c->e_direct.as<double>());
+    k_direct_light<<<nblk((int64_t)nn, 128), 128, 0, c->stream>>>(c->scene, nodes.pos3, nodes.nrm3, nn, c->e_direct.as<double>());
     KCHECK(c);
   }
   if (timed) cudaEventRecord(c->ev[4], c->stream);
@@ -802,7 +980,7 @@ void ppm_destroy(ppm_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   DBuf* all[] = {&c->r_pos, &c->r_dir, &c->r_wl, &c->r_tag, &c->counter, &c->keys, &c->keys2, &c->vals, &c->vals2, &c->cub_tmp,
-                 &c->cell_start, &c->hist, &c->bbox, &c->m_px, &c->m_py, &c->m_pz, &c->m_dx, &c->m_dy, &c->m_dz, &c->m_wl, &c->m_orig,
+                 &c->cell_start, &c->hist, &c->bbox, &c->axis_hist, &c->m_P, &c->m_D, &c->m_orig, &c->q_key, &c->q_key2, &c->q_idx, &c->q_idx2,
                  &c->st_in0, &c->st_in1, &c->st_out0, &c->st_out1, &c->st_out2, &c->st_out3, &c->st_out4,
                  &c->e_cnt, &c->e_off, &c->e_pos, &c->e_nrm, &c->e_w, &c->e_emit, &c->e_direct, &c->e_photon, &c->e_rays,
                  &c->pass_img, &c->accum, &c->npass, &c->stats};
@@ -1061,7 +1239,10 @@ int ppm_render_pass(ppm_ctx* c, uint64_t seed, uint32_t pass, int64_t nphoton, d
   if ((rc = do_trace_photons(c, seed, pass, uc, ns, power))) return rc;
   cudaEventRecord(c->ev[1], c->stream);
   if ((rc = do_map_build(c, radius2))) return rc;
-  if ((rc = do_trace_rays(c, nullptr, npix, 0, seed, pass, uc, c->pass_img.as<double>(), c->accum.as<double>(), true))) return rc;
+  c->ev_gather_inner = true;
+  rc = do_trace_rays(c, nullptr, npix, 0, seed, pass, uc, c->pass_img.as<double>(), c->accum.as<double>(), true);
+  c->ev_gather_inner = false;
+  if (rc) return rc;
   k_bump<<<1, 1, 0, c->stream>>>(c->accum.as<double>() + (size_t)npix * 3);
   KCHECK(c);
   cudaEventRecord(c->ev[6], c->stream);
@@ -1070,7 +1251,9 @@ int ppm_render_pass(ppm_ctx* c, uint64_t seed, uint32_t pass, int64_t nphoton, d
   CK(c, cudaStreamSynchronize(c->stream));
   float f;
   for (int i = 0; i < 6; ++i) { cudaEventElapsedTime(&f, c->ev[i], c->ev[i + 1]); c->ms[i] = f; }
-  cudaEventElapsedTime(&f, c->ev[0], c->ev[6]); c->ms[6] = f; c->ms[7] = 0.0;
+  cudaEventElapsedTime(&f, c->ev[0], c->ev[6]); c->ms[6] = f;
+  c->ms[7] = 0.0;
+  if (c->counters[3]) { cudaEventElapsedTime(&f, c->ev[7], c->ev[5]); c->ms[7] = f; }
   int64_t emitted = 0;
   for (int i = 0; i < c->scene.nlights; ++i) emitted += ns[i];
   c->counters[0] = (uint64_t)emitted; c->counters[1] = c->n_rec; c->counters[2] = st[0];

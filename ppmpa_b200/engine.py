@@ -293,6 +293,6 @@ class Engine:
     def last_pass_stats(self):
         ms = (C.c_double * 8)(); ct = (C.c_uint64 * 8)()
         self._ck(lib.ppm_last_pass_stats(self._h, ms, ct))
-        names = ["photon_trace", "map_build", "eye_expand", "direct_light", "gather", "combine", "total"]
+        names = ["photon_trace", "map_build", "eye_expand", "direct_light", "gather", "combine", "total", "gather_kernel"]
         cn = ["emitted", "stored", "eye_nodes", "gather_nodes", "sum_k", "launches"]
         return {k: ms[i] for i, k in enumerate(names)}, {k: int(ct[i]) for i, k in enumerate(cn)}

@@ -186,6 +186,33 @@ def test_within_sets_identical(engine, oracle, r):
     assert cnt[-1] >= 1 and cnt[len(q) - 22] == 0
 
 
+def test_within_outliers_are_clamped_not_lost(engine, oracle):
+    """The reference leaks ~1e-4 of its photons through wall corners, far outside the room.  The
+    grid covers a trimmed region and clamps outliers into boundary cells: neighbour sets of
+    queries inside, on the boundary and far outside must still be exact."""
+    ph, power = wall_photons(60000, seed=13)
+    rng = np.random.default_rng(2)
+    far = rng.integers(0, len(ph), 40)                      # < n/1024 outliers: they WILL be trimmed
+    ph["pos"][far] += rng.normal(scale=30.0, size=(40, 3))
+    ph["pos"][far[:3]] = [[1e6, -1e6, 3e5], [2.5, 4.5, 5.5], [-2.05, -0.05, -6.05]]
+    r = 0.1
+    engine.import_photons(ph, power)
+    engine.build_photonmap(r * r)
+    m = oracle.map_build(ph, power, r * r)
+    q = np.concatenate([ph["pos"][far] + rng.normal(scale=r / 10, size=(40, 3)),       # around the outliers
+                        ph["pos"][:200] + rng.normal(scale=r / 3, size=(200, 3)),      # inside the room
+                        [[-2.0, 0.0, -6.0], [2.0, 4.0, 5.0], [2.04, 4.04, 5.04]]])      # room corners
+    idx, cnt = engine.within(q, 2048)
+    g, gc = engine.estimate_radiance(q, np.tile([0.0, 1.0, 0.0], (len(q), 1)))
+    o, oc = m.gather(q, np.tile([0.0, 1.0, 0.0], (len(q), 1)), K.FILTER_NONE)
+    for i in range(len(q)):
+        oi, _, k = m.within(q[i])
+        assert cnt[i] == k == gc[i] == oc[i], i
+        assert np.array_equal(idx[i, :k], np.sort(oi)), i
+    assert cnt[:40].min() >= 1
+    assert_rel(g, o, RTOL)
+
+
 @pytest.mark.parametrize("pfilter", [K.FILTER_NONE, K.FILTER_CONE, K.FILTER_GAUSS])
 @pytest.mark.parametrize("r", [0.05, 0.1])
 def test_gather_parity(engine, oracle, pfilter, r):
