@@ -73,46 +73,75 @@ struct RecBuf {
   uint64_t* tag;    // [cap]  (photon index << 4) | depth
 };
 
-// One thread = one photon path (its own Philox stream).  Records are appended
-// with one atomic per warp (warp-aggregated).
-__global__ void __launch_bounds__(256)
+// Persistent photon tracer with path regeneration.  Every photon path is still its own
+// counter-based Philox stream (seed, pass, photon index), so results do not depend on which
+// lane traces it: a lane whose photon is absorbed immediately claims the next photon index
+// from a global ticket counter (one atomic per warp per refill) instead of idling until the
+// longest path of its warp ends.  One loop iteration = (optional) emission + one bounce.
+// Records are appended with one atomic per warp (warp-aggregated compaction).
+__global__ void __launch_bounds__(128)
 k_trace_photons(const __grid_constant__ DevScene sc, const __grid_constant__ LightSplit ls, uint64_t seed, uint32_t pass,
-                int uc, int64_t n, RecBuf rec, unsigned long long* __restrict__ counter, unsigned long long cap) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  bool alive = i < n;
-  Philox rng(seed, pass, PPM_DOMAIN_PHOTON, (uint64_t)(alive ? i : 0), 0);
-  int wl = 0, medium = -1;
-  D3 pos = mk3(0, 0, 0), dir = mk3(1, 0, 0);
-  if (alive) generate_photon(sc.lights[light_of(ls, sc.nlights, i)], rng, wl, pos, dir);
+                int uc, int64_t n, RecBuf rec, unsigned long long* __restrict__ counter, unsigned long long cap,
+                unsigned long long* __restrict__ ticket) {
+  const unsigned FULL = 0xffffffffu;
   const unsigned lane = threadIdx.x & 31u;
-  for (int l = 0; l < PPM_MAX_TRACE; ++l) {
-    if (!__any_sync(0xffffffffu, alive)) break;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  bool alive = false, exhausted = false;
+  int64_t idx = 0;
+  int wl = 0, medium = -1, depth = 0;
+  D3 pos = mk3(0, 0, 0), dir = mk3(1, 0, 0);
+  Philox rng(seed, pass, PPM_DOMAIN_PHOTON, 0, 0);
+  for (;;) {
+    // ---- refill dead lanes --------------------------------------------------------------
+    const unsigned need = __ballot_sync(FULL, !alive && !exhausted);
+    if (need) {
+      unsigned long long base = 0;
+      const int leader = __ffs(need) - 1;
+      if ((int)lane == leader) base = atomicAdd(ticket, (unsigned long long)__popc(need));
+      base = __shfl_sync(FULL, base, leader);
+      if (!alive && !exhausted) {
+        const int64_t i = (int64_t)(base + __popc(need & lt_mask));
+        if (i < n) {
+          idx = i;
+          rng = Philox(seed, pass, PPM_DOMAIN_PHOTON, (uint64_t)i, 0);
+          generate_photon(sc.lights[light_of(ls, sc.nlights, i)], rng, wl, pos, dir);
+          medium = -1; depth = 0; alive = true;
+        } else {
+          exhausted = true;
+        }
+      }
+    }
+    if (!__any_sync(FULL, alive)) break;
+    // ---- one bounce ----------------------------------------------------------------------
     Isect is;
     bool store = false;
-    D3 in_dir = dir;
+    const D3 in_dir = dir;
+    const int l = depth;
     if (alive) {
       if (!nearest_hit(sc, pos, dir, is)) {
         alive = false;
       } else {
         store = (uc == 0 || l > 0) && surf_store_photon(sc.mats[is.mat]);
         D3 nd;
-        bool go = photon_bounce(sc, is, wl, dir, rng, medium, nd);
+        const bool go = photon_bounce(sc, is, wl, dir, rng, medium, nd);
         pos = is.pos;
-        if (go) dir = nd; else alive = false;
+        ++depth;
+        if (go && depth < PPM_MAX_TRACE) dir = nd; else alive = false;   // `if l >= MAX_TRACE { return vec![] }`
       }
     }
-    unsigned m = __ballot_sync(0xffffffffu, store);
+    const unsigned m = __ballot_sync(FULL, store);
     if (m) {
       unsigned long long base = 0;
-      if (lane == (unsigned)(__ffs(m) - 1)) base = atomicAdd(counter, (unsigned long long)__popc(m));
-      base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+      const int leader = __ffs(m) - 1;
+      if ((int)lane == leader) base = atomicAdd(counter, (unsigned long long)__popc(m));
+      base = __shfl_sync(FULL, base, leader);
       if (store) {
-        unsigned long long slot = base + __popc(m & ((1u << lane) - 1u));
+        const unsigned long long slot = base + __popc(m & lt_mask);
         if (slot < cap) {
           st3(rec.pos3 + slot * 3, is.pos);
           st3(rec.dir3 + slot * 3, in_dir);
           rec.wl[slot] = (uint8_t)wl;
-          rec.tag[slot] = ((uint64_t)i << 4) | (uint64_t)l;
+          rec.tag[slot] = ((uint64_t)idx << 4) | (uint64_t)l;
         }
       }
     }
@@ -592,6 +621,7 @@ struct DBuf {
 
 struct ppm_ctx {
   int device = 0;
+  int sm_count = 148;
   cudaStream_t stream = nullptr;
   std::string err;
   bool have_scene = false, have_camera = false, have_map = false;
@@ -616,8 +646,13 @@ struct ppm_ctx {
   // last pass stats
   double ms[8] = {0};
   uint64_t counters[8] = {0};
-  cudaEvent_t ev[8] = {nullptr};
-  bool ev_gather_inner = false;   // record ev[7] right before the k_gather launch (render_pass only)
+  // Two streams: the photon branch (trace -> map build) and the eye branch (expand -> direct
+  // light) of a pass are independent until the gather, so render_pass runs them concurrently.
+  cudaStream_t stream2 = nullptr;
+  DBuf cub_tmp2;
+  enum { EV_A0, EV_A1, EV_A2, EV_A3, EV_A4, EV_A5, EV_A6, EV_B0, EV_B1, EV_B2, EV_COUNT };
+  cudaEvent_t ev[EV_COUNT] = {nullptr};
+  bool timed = false;             // record the phase events (render_pass only)
   uint64_t launches = 0;
 };
 
@@ -700,7 +735,7 @@ int light_split(ppm_ctx* c, const int64_t* n_per_light, LightSplit* ls, int64_t*
 }
 
 // -- internal (device-resident) building blocks shared by the probes and render_pass --
-int do_trace_photons(ppm_ctx* c, uint64_t seed, uint32_t pass, int uc, const int64_t* n_per_light, double power) {
+int trace_photons_launch(ppm_ctx* c, uint64_t seed, uint32_t pass, int uc, const int64_t* n_per_light, uint64_t* cap_out) {
   LightSplit ls;
   int64_t total = 0;
   int rc = light_split(c, n_per_light, &ls, &total);
@@ -709,18 +744,32 @@ int do_trace_photons(ppm_ctx* c, uint64_t seed, uint32_t pass, int uc, const int
   if (cap == 0) cap = 1;
   rc = ensure_records(c, cap);
   if (rc) return rc;
-  CK(c, cudaMemsetAsync(c->counter.p, 0, 8, c->stream));
+  CK(c, cudaMemsetAsync(c->counter.p, 0, 16, c->stream));     // [0] record counter, [1] photon ticket
   if (total > 0) {
-    k_trace_photons<<<nblk(total, 256), 256, 0, c->stream>>>(c->scene, ls, seed, pass, uc, total, recbuf(c),
-                                                             c->counter.as<unsigned long long>(), cap);
+    // persistent grid: enough CTAs to fill every SM (resident CTAs are limited by registers),
+    // never more threads than photons
+    const unsigned blocks = (unsigned)std::min<int64_t>((total + 127) / 128, (int64_t)c->sm_count * 8);
+    k_trace_photons<<<blocks, 128, 0, c->stream>>>(c->scene, ls, seed, pass, uc, total, recbuf(c),
+                                                   c->counter.as<unsigned long long>(), cap,
+                                                   c->counter.as<unsigned long long>() + 1);
     KCHECK(c);
   }
+  *cap_out = cap;
+  return PPM_OK;
+}
+int trace_photons_finish(ppm_ctx* c, uint64_t cap, double power) {
   unsigned long long n = 0;
   CK(c, cudaMemcpyAsync(&n, c->counter.p, 8, cudaMemcpyDeviceToHost, c->stream));
   CK(c, cudaStreamSynchronize(c->stream));
   if (n > cap) return fail(c, PPM_ERR_CAPACITY, "photon record capacity exceeded");
   c->n_rec = n; c->power = power; c->have_map = false;
   return PPM_OK;
+}
+int do_trace_photons(ppm_ctx* c, uint64_t seed, uint32_t pass, int uc, const int64_t* n_per_light, double power) {
+  uint64_t cap = 0;
+  int rc = trace_photons_launch(c, seed, pass, uc, n_per_light, &cap);
+  if (rc) return rc;
+  return trace_photons_finish(c, cap, power);
 }
 
 struct HostTrace {
@@ -887,7 +936,7 @@ int launch_gather(ppm_ctx* c, const double* dpos, const double* dnrm, int64_t n,
   CK(c, cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp, c->q_key.as<uint32_t>(), c->q_key2.as<uint32_t>(), c->q_idx.as<uint32_t>(),
                                         c->q_idx2.as<uint32_t>(), n, 0, bits, c->stream));
   // 2. warp-cooperative gather over the sorted queries
-  if (c->ev_gather_inner) cudaEventRecord(c->ev[7], c->stream);
+  if (c->timed) cudaEventRecord(c->ev[ppm_ctx::EV_A4], c->stream);
   const int B = GATHER_WARPS * 32;
   const uint32_t* cs = c->cell_start.as<uint32_t>();
   const uint32_t* qk = c->q_key2.as<uint32_t>();
@@ -907,48 +956,65 @@ int launch_gather(ppm_ctx* c, const double* dpos, const double* dnrm, int64_t n,
   return PPM_OK;
 }
 
-// eye rays (device, or NULL = generate from the camera) -> radiance image (device) [+ accumulate]
-int do_trace_rays(ppm_ctx* c, const double* drays, int64_t n, int64_t first_pixel, uint64_t seed, uint32_t pass, int uc,
-                  double* dout, double* daccum, bool timed) {
-  if (n <= 0) return PPM_OK;
+// Eye branch, part 1 (stream `st`): expand the eye paths into the gather-node list and
+// compute the classic direct light at every node.  drays == NULL generates camera rays.
+int eye_front(ppm_ctx* c, cudaStream_t st, DBuf& tmpbuf, const double* drays, int64_t n, int64_t first_pixel, uint64_t seed,
+              uint32_t pass, int uc, uint32_t* nn_out) {
   CK(c, c->e_cnt.ensure((size_t)(n + 1) * 4)); CK(c, c->e_off.ensure((size_t)(n + 1) * 4));
   CK(c, c->e_emit.ensure((size_t)n * 24)); CK(c, c->stats.ensure(64));
-  CK(c, cudaMemsetAsync(c->stats.p, 0, 64, c->stream));
-  CK(c, cudaMemsetAsync(c->e_cnt.p, 0, (size_t)(n + 1) * 4, c->stream));
+  CK(c, cudaMemsetAsync(c->stats.p, 0, 64, st));
+  CK(c, cudaMemsetAsync(c->e_cnt.p, 0, (size_t)(n + 1) * 4, st));
   unsigned long long* dstats = c->stats.as<unsigned long long>();
   EyeNodes none = {nullptr, nullptr, nullptr};
-  if (timed) cudaEventRecord(c->ev[2], c->stream);
-  k_eye_expand<false><<<nblk(n, 128), 128, 0, c->stream>>>(c->scene, c->cam, drays, n, first_pixel, seed, pass,
-                                                          c->e_cnt.as<uint32_t>(), nullptr, none, nullptr, dstats);
+  if (c->timed) cudaEventRecord(c->ev[ppm_ctx::EV_B0], st);
+  k_eye_expand<false><<<nblk(n, 128), 128, 0, st>>>(c->scene, c->cam, drays, n, first_pixel, seed, pass,
+                                                   c->e_cnt.as<uint32_t>(), nullptr, none, nullptr, dstats);
   KCHECK(c);
   size_t tmp = 0;
-  CK(c, cub::DeviceScan::ExclusiveSum(nullptr, tmp, c->e_cnt.as<uint32_t>(), c->e_off.as<uint32_t>(), n + 1, c->stream));
-  CK(c, c->cub_tmp.ensure(tmp));
-  CK(c, cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tmp, c->e_cnt.as<uint32_t>(), c->e_off.as<uint32_t>(), n + 1, c->stream));
+  CK(c, cub::DeviceScan::ExclusiveSum(nullptr, tmp, c->e_cnt.as<uint32_t>(), c->e_off.as<uint32_t>(), n + 1, st));
+  CK(c, tmpbuf.ensure(tmp));
+  CK(c, cub::DeviceScan::ExclusiveSum(tmpbuf.p, tmp, c->e_cnt.as<uint32_t>(), c->e_off.as<uint32_t>(), n + 1, st));
   uint32_t nn = 0;
-  CK(c, cudaMemcpyAsync(&nn, c->e_off.as<uint32_t>() + n, 4, cudaMemcpyDeviceToHost, c->stream));
-  CK(c, cudaStreamSynchronize(c->stream));
+  CK(c, cudaMemcpyAsync(&nn, c->e_off.as<uint32_t>() + n, 4, cudaMemcpyDeviceToHost, st));
+  CK(c, cudaStreamSynchronize(st));
   size_t cap = nn ? nn : 1;
   CK(c, c->e_pos.ensure(cap * 24)); CK(c, c->e_nrm.ensure(cap * 24)); CK(c, c->e_w.ensure(cap * 24));
   CK(c, c->e_direct.ensure(cap * 24)); CK(c, c->e_photon.ensure(cap * 24));
   EyeNodes nodes = {c->e_pos.as<double>(), c->e_nrm.as<double>(), c->e_w.as<double>()};
-  k_eye_expand<true><<<nblk(n, 128), 128, 0, c->stream>>>(c->scene, c->cam, drays, n, first_pixel, seed, pass, nullptr,
-                                                         c->e_off.as<uint32_t>(), nodes, c->e_emit.as<double>(), nullptr);
+  k_eye_expand<true><<<nblk(n, 128), 128, 0, st>>>(c->scene, c->cam, drays, n, first_pixel, seed, pass, nullptr,
+                                                  c->e_off.as<uint32_t>(), nodes, c->e_emit.as<double>(), nullptr);
   KCHECK(c);
-  if (timed) cudaEventRecord(c->ev[3], c->stream);
+  if (c->timed) cudaEventRecord(c->ev[ppm_ctx::EV_B1], st);
   if (uc && nn) {
-    k_direct_light<<<nblk((int64_t)nn, 128), 128, 0, c->stream>>>(c->scene, nodes.pos3, nodes.nrm3, nn, c->e_direct.as<double>());
+    k_direct_light<<<nblk((int64_t)nn, 128), 128, 0, st>>>(c->scene, nodes.pos3, nodes.nrm3, nn, c->e_direct.as<double>());
     KCHECK(c);
   }
-  if (timed) cudaEventRecord(c->ev[4], c->stream);
-  int rc = launch_gather(c, nodes.pos3, nodes.nrm3, nn, c->cam.pfilter, c->e_photon.as<double>(), nullptr, dstats + 1);
+  cudaEventRecord(c->ev[ppm_ctx::EV_B2], st);
+  *nn_out = nn;
+  return PPM_OK;
+}
+// Eye branch, part 2 (main stream; the photon map must be built): gather at every node,
+// combine per pixel, optionally add into the accumulator.
+int eye_back(ppm_ctx* c, int64_t n, int64_t first_pixel, uint32_t nn, int uc, double* dout, double* daccum) {
+  if (c->timed) cudaEventRecord(c->ev[ppm_ctx::EV_A3], c->stream);
+  int rc = launch_gather(c, c->e_pos.as<double>(), c->e_nrm.as<double>(), nn, c->cam.pfilter, c->e_photon.as<double>(), nullptr,
+                         c->stats.as<unsigned long long>() + 1);
   if (rc) return rc;
-  if (timed) cudaEventRecord(c->ev[5], c->stream);
-  k_combine<<<nblk(n, 256), 256, 0, c->stream>>>(c->e_off.as<uint32_t>(), nodes.w3, uc ? c->e_direct.as<double>() : nullptr,
+  if (c->timed) cudaEventRecord(c->ev[ppm_ctx::EV_A5], c->stream);
+  k_combine<<<nblk(n, 256), 256, 0, c->stream>>>(c->e_off.as<uint32_t>(), c->e_w.as<double>(), uc ? c->e_direct.as<double>() : nullptr,
                                                 c->e_photon.as<double>(), c->e_emit.as<double>(), n, dout, daccum, first_pixel);
   KCHECK(c);
   c->counters[3] = nn;
   return PPM_OK;
+}
+// serial version on the main stream (ppm_trace_rays)
+int do_trace_rays(ppm_ctx* c, const double* drays, int64_t n, int64_t first_pixel, uint64_t seed, uint32_t pass, int uc,
+                  double* dout, double* daccum) {
+  if (n <= 0) return PPM_OK;
+  uint32_t nn = 0;
+  int rc = eye_front(c, c->stream, c->cub_tmp, drays, n, first_pixel, seed, pass, uc, &nn);
+  if (rc) return rc;
+  return eye_back(c, n, first_pixel, nn, uc, dout, daccum);
 }
 
 }  // namespace
@@ -967,8 +1033,15 @@ int ppm_create(int device, ppm_ctx** out) {
   if (cudaSetDevice(device) != cudaSuccess) return PPM_ERR_CUDA;
   ppm_ctx* c = new ppm_ctx();
   c->device = device;
-  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return PPM_ERR_CUDA; }
-  for (int i = 0; i < 8; ++i) cudaEventCreate(&c->ev[i]);
+  cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+  if (c->sm_count <= 0) c->sm_count = 148;
+  // The main stream gets the highest priority: in render_pass its small photon-branch kernels
+  // must be dispatched ahead of the remaining blocks of the long eye-branch kernels on stream2.
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+  if (cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess) { delete c; return PPM_ERR_CUDA; }
+  if (cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, prio_lo) != cudaSuccess) { cudaStreamDestroy(c->stream); delete c; return PPM_ERR_CUDA; }
+  for (int i = 0; i < ppm_ctx::EV_COUNT; ++i) cudaEventCreate(&c->ev[i]);
   std::memset(&c->scene, 0, sizeof c->scene);
   ppm_camera_default(&c->cam);
   *out = c;
@@ -983,9 +1056,11 @@ void ppm_destroy(ppm_ctx* c) {
                  &c->cell_start, &c->hist, &c->bbox, &c->axis_hist, &c->m_P, &c->m_D, &c->m_orig, &c->q_key, &c->q_key2, &c->q_idx, &c->q_idx2,
                  &c->st_in0, &c->st_in1, &c->st_out0, &c->st_out1, &c->st_out2, &c->st_out3, &c->st_out4,
                  &c->e_cnt, &c->e_off, &c->e_pos, &c->e_nrm, &c->e_w, &c->e_emit, &c->e_direct, &c->e_photon, &c->e_rays,
-                 &c->pass_img, &c->accum, &c->npass, &c->stats};
+                 &c->pass_img, &c->accum, &c->npass, &c->stats, &c->cub_tmp2};
   for (DBuf* b : all) b->release();
-  for (int i = 0; i < 8; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+  for (int i = 0; i < ppm_ctx::EV_COUNT; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+  cudaStreamSynchronize(c->stream2);
+  cudaStreamDestroy(c->stream2);
   cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -1205,7 +1280,7 @@ int ppm_trace_rays(ppm_ctx* c, const double* rays6, int64_t n, int64_t first_pix
   const void* dr; void* dout; int rc;
   if ((rc = stage_in(c, rays6, (size_t)n * 48, c->st_in0, &dr))) return rc;
   if ((rc = stage_out(c, rgb3, (size_t)n * 24, c->st_out0, &dout))) return rc;
-  if ((rc = do_trace_rays(c, (const double*)dr, n, first_pixel, seed, pass, uc, (double*)dout, nullptr, false))) return rc;
+  if ((rc = do_trace_rays(c, (const double*)dr, n, first_pixel, seed, pass, uc, (double*)dout, nullptr))) return rc;
   if ((rc = finish_out(c, rgb3, (size_t)n * 24, dout))) return rc;
   CK(c, cudaStreamSynchronize(c->stream));
   return PPM_OK;
@@ -1235,25 +1310,44 @@ int ppm_render_pass(ppm_ctx* c, uint64_t seed, uint32_t pass, int64_t nphoton, d
   const int64_t npix = (int64_t)c->cam.xreso * c->cam.yreso;
   CK(c, c->pass_img.ensure((size_t)npix * 24));
   const uint64_t l0 = c->launches;
-  cudaEventRecord(c->ev[0], c->stream);
-  if ((rc = do_trace_photons(c, seed, pass, uc, ns, power))) return rc;
-  cudaEventRecord(c->ev[1], c->stream);
-  if ((rc = do_map_build(c, radius2))) return rc;
-  c->ev_gather_inner = true;
-  rc = do_trace_rays(c, nullptr, npix, 0, seed, pass, uc, c->pass_img.as<double>(), c->accum.as<double>(), true);
-  c->ev_gather_inner = false;
-  if (rc) return rc;
+  typedef ppm_ctx E;
+  c->timed = true;
+  // photon branch on the main stream (async), eye branch on stream2, joined before the gather
+  cudaEventRecord(c->ev[E::EV_A0], c->stream);
+  CK(c, cudaStreamWaitEvent(c->stream2, c->ev[E::EV_A0], 0));
+  uint64_t cap = 0;
+  uint32_t nn = 0;
+  rc = trace_photons_launch(c, seed, pass, uc, ns, &cap);
+  cudaEventRecord(c->ev[E::EV_A1], c->stream);
+  if (!rc) rc = eye_front(c, c->stream2, c->cub_tmp2, nullptr, npix, 0, seed, pass, uc, &nn);
+  if (!rc) rc = trace_photons_finish(c, cap, power);
+  if (!rc) rc = do_map_build(c, radius2);
+  cudaEventRecord(c->ev[E::EV_A2], c->stream);
+  if (!rc) {
+    cudaStreamWaitEvent(c->stream, c->ev[E::EV_B2], 0);
+    rc = eye_back(c, npix, 0, nn, uc, c->pass_img.as<double>(), c->accum.as<double>());
+  }
+  c->timed = false;
+  if (rc) { cudaStreamSynchronize(c->stream2); cudaStreamSynchronize(c->stream); return rc; }
   k_bump<<<1, 1, 0, c->stream>>>(c->accum.as<double>() + (size_t)npix * 3);
   KCHECK(c);
-  cudaEventRecord(c->ev[6], c->stream);
+  cudaEventRecord(c->ev[E::EV_A6], c->stream);
   unsigned long long st[2];
   CK(c, cudaMemcpyAsync(st, c->stats.p, 16, cudaMemcpyDeviceToHost, c->stream));
   CK(c, cudaStreamSynchronize(c->stream));
-  float f;
-  for (int i = 0; i < 6; ++i) { cudaEventElapsedTime(&f, c->ev[i], c->ev[i + 1]); c->ms[i] = f; }
-  cudaEventElapsedTime(&f, c->ev[0], c->ev[6]); c->ms[6] = f;
-  c->ms[7] = 0.0;
-  if (c->counters[3]) { cudaEventElapsedTime(&f, c->ev[7], c->ev[5]); c->ms[7] = f; }
+  auto el = [&](int a, int b) { float f = 0.f; cudaEventElapsedTime(&f, c->ev[a], c->ev[b]); return (double)f; };
+  c->ms[0] = el(E::EV_A0, E::EV_A1);                 // photon trace
+  c->ms[1] = el(E::EV_A1, E::EV_A2);                 // map build (includes waiting for host readbacks)
+  c->ms[2] = el(E::EV_B0, E::EV_B1);                 // eye expand (stream2, concurrent with the photon branch)
+  c->ms[3] = el(E::EV_B1, E::EV_B2);                 // direct light (stream2)
+  c->ms[4] = el(E::EV_A3, E::EV_A5);                 // gather: query sort + kernel
+  c->ms[5] = el(E::EV_A5, E::EV_A6);                 // combine + accumulate
+  c->ms[6] = el(E::EV_A0, E::EV_A6);                 // whole pass
+  c->ms[7] = nn ? el(E::EV_A4, E::EV_A5) : 0.0;      // k_gather alone
+  if (std::getenv("PPM_TRACE"))
+    std::fprintf(stderr, "[ppm timeline ms since A0] A1=%.3f A2=%.3f B0=%.3f B1=%.3f B2=%.3f A3=%.3f A4=%.3f A5=%.3f A6=%.3f\n",
+                 el(E::EV_A0, E::EV_A1), el(E::EV_A0, E::EV_A2), el(E::EV_A0, E::EV_B0), el(E::EV_A0, E::EV_B1), el(E::EV_A0, E::EV_B2),
+                 el(E::EV_A0, E::EV_A3), nn ? el(E::EV_A0, E::EV_A4) : 0.0, el(E::EV_A0, E::EV_A5), el(E::EV_A0, E::EV_A6));
   int64_t emitted = 0;
   for (int i = 0; i < c->scene.nlights; ++i) emitted += ns[i];
   c->counters[0] = (uint64_t)emitted; c->counters[1] = c->n_rec; c->counters[2] = st[0];
