@@ -180,6 +180,7 @@ def run_gpu(args):
     import torch.distributed as dist
 
     import ppmpa_b200 as P
+    from ppmpa_b200 import parallel
 
     world = env_int("WORLD_SIZE", 1)
     rank = env_int("RANK", 0)
@@ -213,9 +214,8 @@ def run_gpu(args):
 
     for s in range(W):
         one_pass(s)
-    if world > 1:
-        with torch.cuda.stream(stream):
-            dist.reduce(acc, dst=0)                      # warm the communicator
+    with torch.cuda.stream(stream):
+        parallel.reduce_accumulators(acc, dst=0)         # warm the communicator (no-op at N=1)
     eng.accum_reset()
 
     # ---- device-resident timed region ----------------------------------------------------
@@ -233,9 +233,8 @@ def run_gpu(args):
             phases[k] = phases.get(k, 0.0) + v
         for k, v in ct.items():
             counts[k] = counts.get(k, 0) + v
-    if world > 1:
-        with torch.cuda.stream(stream):
-            dist.reduce(acc, dst=0)                      # ONE reduce of (3*W*H + 1) doubles per frame
+    with torch.cuda.stream(stream):
+        parallel.reduce_accumulators(acc, dst=0)         # ONE sum-reduce of (3*W*H + 1) doubles per frame
     ev1.record(stream)
     sync_all()
     clocks = sampler.stop()
