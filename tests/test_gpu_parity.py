@@ -338,6 +338,24 @@ def test_direct_light_off_by_one_quirk(engine, oracle):
     assert np.count_nonzero(g) == np.count_nonzero(o)
 
 
+@pytest.mark.parametrize("name", [None, "ex-glassbox", "sample1", "mirror-ball"])
+def test_direct_light_matches_oracle(engine, oracle, name):
+    """Classic direct light alone (empty photon map): 25 shadow rays per node incl. the off-by-one pairing."""
+    sc = load_scene(name)
+    cam = P.read_camera(os.path.join(EX, "camera0.scr"), xreso=160, yreso=160, progressive=1, pfilter=K.FILTER_NONE)
+    engine.set_scene(sc); engine.set_camera(cam)
+    engine.import_photons(np.zeros(0, K.PHOTON_DTYPE), 1.0); engine.build_photonmap(0.01)
+    rays = oracle.generate_rays(cam, 7, 0)
+    first = len(rays) // 3
+    sub = slice(first, first + 4000)                         # contiguous: pixel ids (RNG streams) stay aligned
+    g = engine.trace_rays(rays[sub], 7, 0, True, first_pixel=first)
+    m = oracle.map_build(np.zeros(0, K.PHOTON_DTYPE), 1.0, 0.01)
+    o, _ = oracle.trace_rays(sc, m, K.FILTER_NONE, rays[sub], 7, 0, True, first_pixel=first, nthreads=4)
+    assert o.max() > 0
+    err = np.abs(g - o) / np.maximum(np.maximum(np.abs(o), np.abs(g)), 1e-300)
+    assert np.mean(np.any(err > RTOL, axis=1)) <= 2e-3
+
+
 def test_render_pass_matches_oracle_and_accumulates(engine, oracle):
     sc = load_scene("ex-glassbox")
     cam = P.read_camera(os.path.join(EX, "camera0.scr"), xreso=40, yreso=40, pfilter=K.FILTER_NONE, progressive=1)
