@@ -440,29 +440,34 @@ __global__ void k_gen_rays(const __grid_constant__ ppm_camera cam, uint64_t seed
 }
 
 // ---- eye path expansion ------------------------------------------------------------
-// The binary recursion of trace_ray becomes a per-pixel depth-first walk with an
-// explicit stack and a top-down RGB throughput W.  Each visited node that has a
-// non-zero diffuse coefficient becomes one "gather node" (hit point, normal,
-// W (.) kd).  WRITE=false counts nodes per pixel, WRITE=true (after an exclusive
-// scan) writes them at deterministic offsets in reference recursion order.
+// The binary recursion of trace_ray becomes a per-pixel depth-first walk with an explicit
+// stack and a top-down RGB throughput W.  Each visited node that has a non-zero diffuse
+// coefficient becomes one "gather node" (hit point, normal, W (.) kd) in a global pool.
+// Single pass: slots are claimed with one atomic per warp (opportunistic warp aggregation);
+// every node stores the slot of the previous node of its pixel, and the pixel stores the last
+// one, so k_combine can walk a pixel's nodes in a fixed order (reverse creation order) --
+// the image does not depend on where the atomics placed the nodes.
 struct EyeNodes {
-  double* pos3;     // [N][3] hit position     (gather / direct-light query)
-  double* nrm3;     // [N][3] facing normal
-  double* w3;       // [N][3] W (.) kd
+  double* pos3;     // [cap][3] hit position     (gather / direct-light query)
+  double* nrm3;     // [cap][3] facing normal
+  double* w3;       // [cap][3] W (.) kd
+  uint32_t* prev;   // [cap]    previous node of the same pixel, EYE_NONE = first
 };
+#define EYE_NONE 0xFFFFFFFFu
 struct EyeStack {
   D3 pos, dir, W;
   int medium, depth;
   uint32_t node;
 };
-template <bool WRITE>
 __global__ void __launch_bounds__(128)
 k_eye_expand(const __grid_constant__ DevScene sc, const __grid_constant__ ppm_camera cam, const double* __restrict__ rays6,
-             int64_t n, int64_t first_pixel, uint64_t seed, uint32_t pass, uint32_t* __restrict__ node_count,
-             const uint32_t* __restrict__ node_off, EyeNodes nodes, double* __restrict__ emit3,
+             int64_t n, int64_t first_pixel, uint64_t seed, uint32_t pass, EyeNodes nodes, uint32_t cap,
+             uint32_t* __restrict__ head, double* __restrict__ emit3, unsigned long long* __restrict__ pool_counter,
              unsigned long long* __restrict__ n_visited) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned lt_mask = (1u << lane) - 1u;
   const int64_t pix = first_pixel + i;
   EyeStack st[PPM_MAX_TRACE + 2];
   int sp = 0;
@@ -471,8 +476,7 @@ k_eye_expand(const __grid_constant__ DevScene sc, const __grid_constant__ ppm_ca
   st[0].W = mk3(1.0, 1.0, 1.0); st[0].medium = -1; st[0].depth = 0; st[0].node = 1;
   sp = 1;
   D3 emit = mk3(0.0, 0.0, 0.0);
-  uint32_t cnt = 0, visited = 0;
-  const uint32_t off = WRITE ? node_off[i] : 0;
+  uint32_t last = EYE_NONE, visited = 0;
   const double SR_HALF = 1.0 / (2.0 * PPM_PI);
   while (sp > 0) {
     EyeStack e = st[--sp];
@@ -485,13 +489,25 @@ k_eye_expand(const __grid_constant__ DevScene sc, const __grid_constant__ ppm_ca
     eye_node(sc, is, e.dir, e.medium, rng, nd);
     const ppm_material& m = sc.mats[is.mat];
     emit = emit + cmul(e.W, ld3(m.emittance) * SR_HALF);
-    D3 wd = cmul(e.W, nd.kd);
-    if (any_nz(wd)) {
-      if (WRITE) {
-        uint64_t s = (uint64_t)off + cnt;
-        st3(nodes.pos3 + s * 3, is.pos); st3(nodes.nrm3 + s * 3, is.nvec); st3(nodes.w3 + s * 3, wd);
+    const D3 wd = cmul(e.W, nd.kd);
+    {
+      const bool create = any_nz(wd);
+      const unsigned conv = __activemask();                 // lanes that reached this point together
+      const unsigned cm = __ballot_sync(conv, create);
+      if (cm) {
+        unsigned long long base = 0;
+        const int leader = __ffs(cm) - 1;
+        if ((int)lane == leader) base = atomicAdd(pool_counter, (unsigned long long)__popc(cm));
+        base = __shfl_sync(conv, base, leader);
+        if (create) {
+          const unsigned long long s = base + __popc(cm & lt_mask);
+          if (s < cap) {
+            st3(nodes.pos3 + s * 3, is.pos); st3(nodes.nrm3 + s * 3, is.nvec); st3(nodes.w3 + s * 3, wd);
+            nodes.prev[s] = last;
+            last = (uint32_t)s;
+          }                                                 // else: pool overflow, the host grows it and re-runs
+        }
       }
-      ++cnt;
     }
     // push the refract child first so that the reflect subtree is walked first
     // (reference order: si is evaluated before ti, tracer.rs:152-171)
@@ -510,14 +526,16 @@ k_eye_expand(const __grid_constant__ DevScene sc, const __grid_constant__ ppm_ca
       }
     }
   }
-  if (WRITE) {
-    st3(emit3 + i * 3, emit);
-  } else {
-    node_count[i] = cnt;
-    if (n_visited) {
-      unsigned long long v = visited;
-      atomicAdd(n_visited, v);
+  head[i] = last;
+  st3(emit3 + i * 3, emit);
+  if (n_visited) {
+    const unsigned conv = __activemask();
+    unsigned long long v = visited;
+    for (int o = 16; o > 0; o >>= 1) {
+      unsigned long long t = __shfl_down_sync(conv, v, o);
+      if (lane + o < 32 && ((conv >> (lane + o)) & 1u)) v += t;
     }
+    if (lane == (unsigned)(__ffs(conv) - 1)) atomicAdd(n_visited, v);
   }
 }
 
@@ -576,14 +594,14 @@ k_direct_light(const __grid_constant__ DevScene sc, const double* __restrict__ p
 // ---- combine + accumulate ------------------------------------------------------------
 // pixel = sum_nodes W(.)kd (.) (direct + photon estimate) + sum emittance terms;
 // then the pass image is added to the running sum (util/averager2.rb:49-62).
-__global__ void k_combine(const uint32_t* __restrict__ node_off, const double* __restrict__ w3,
+__global__ void k_combine(const uint32_t* __restrict__ head, const uint32_t* __restrict__ prev, const double* __restrict__ w3,
                           const double* __restrict__ direct3, const double* __restrict__ photon3,
                           const double* __restrict__ emit3, int64_t n, double* __restrict__ out3,
                           double* __restrict__ accum3, int64_t accum_first) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   D3 rad = ld3(emit3 + i * 3);
-  for (uint32_t s = node_off[i]; s < node_off[i + 1]; ++s) {
+  for (uint32_t s = head[i]; s != EYE_NONE; s = prev[s]) {
     D3 di = ld3(photon3 + (uint64_t)s * 3);
     if (direct3) di = ld3(direct3 + (uint64_t)s * 3) + di;     // di = direct + estimate, tracer.rs:136-145
     rad = rad + cmul(ld3(w3 + (uint64_t)s * 3), di);
@@ -640,7 +658,8 @@ struct ppm_ctx {
   // staging for h_or_d arguments
   DBuf st_in0, st_in1, st_out0, st_out1, st_out2, st_out3, st_out4;
   // eye path
-  DBuf e_cnt, e_off, e_pos, e_nrm, e_w, e_emit, e_direct, e_photon, e_rays;
+  DBuf e_head, e_prev, e_pos, e_nrm, e_w, e_emit, e_direct, e_photon, e_rays;
+  uint64_t eye_cap = 0;            // capacity of the gather-node pool
   DBuf pass_img, accum, npass, stats;
   uint64_t accum_pixels = 0;
   // last pass stats
@@ -960,30 +979,32 @@ int launch_gather(ppm_ctx* c, const double* dpos, const double* dnrm, int64_t n,
 // compute the classic direct light at every node.  drays == NULL generates camera rays.
 int eye_front(ppm_ctx* c, cudaStream_t st, DBuf& tmpbuf, const double* drays, int64_t n, int64_t first_pixel, uint64_t seed,
               uint32_t pass, int uc, uint32_t* nn_out) {
-  CK(c, c->e_cnt.ensure((size_t)(n + 1) * 4)); CK(c, c->e_off.ensure((size_t)(n + 1) * 4));
+  (void)tmpbuf;
+  CK(c, c->e_head.ensure((size_t)n * 4));
   CK(c, c->e_emit.ensure((size_t)n * 24)); CK(c, c->stats.ensure(64));
-  CK(c, cudaMemsetAsync(c->stats.p, 0, 64, st));
-  CK(c, cudaMemsetAsync(c->e_cnt.p, 0, (size_t)(n + 1) * 4, st));
   unsigned long long* dstats = c->stats.as<unsigned long long>();
-  EyeNodes none = {nullptr, nullptr, nullptr};
+  if (c->eye_cap < (uint64_t)n * 2) c->eye_cap = (uint64_t)n * 2;      // first guess: two gather nodes per pixel
   if (c->timed) cudaEventRecord(c->ev[ppm_ctx::EV_B0], st);
-  k_eye_expand<false><<<nblk(n, 128), 128, 0, st>>>(c->scene, c->cam, drays, n, first_pixel, seed, pass,
-                                                   c->e_cnt.as<uint32_t>(), nullptr, none, nullptr, dstats);
-  KCHECK(c);
-  size_t tmp = 0;
-  CK(c, cub::DeviceScan::ExclusiveSum(nullptr, tmp, c->e_cnt.as<uint32_t>(), c->e_off.as<uint32_t>(), n + 1, st));
-  CK(c, tmpbuf.ensure(tmp));
-  CK(c, cub::DeviceScan::ExclusiveSum(tmpbuf.p, tmp, c->e_cnt.as<uint32_t>(), c->e_off.as<uint32_t>(), n + 1, st));
   uint32_t nn = 0;
-  CK(c, cudaMemcpyAsync(&nn, c->e_off.as<uint32_t>() + n, 4, cudaMemcpyDeviceToHost, st));
-  CK(c, cudaStreamSynchronize(st));
-  size_t cap = nn ? nn : 1;
-  CK(c, c->e_pos.ensure(cap * 24)); CK(c, c->e_nrm.ensure(cap * 24)); CK(c, c->e_w.ensure(cap * 24));
-  CK(c, c->e_direct.ensure(cap * 24)); CK(c, c->e_photon.ensure(cap * 24));
-  EyeNodes nodes = {c->e_pos.as<double>(), c->e_nrm.as<double>(), c->e_w.as<double>()};
-  k_eye_expand<true><<<nblk(n, 128), 128, 0, st>>>(c->scene, c->cam, drays, n, first_pixel, seed, pass, nullptr,
-                                                  c->e_off.as<uint32_t>(), nodes, c->e_emit.as<double>(), nullptr);
-  KCHECK(c);
+  for (int attempt = 0;; ++attempt) {
+    const size_t cap = (size_t)c->eye_cap;
+    if (cap >= 0xFFFFFFFFull) return fail(c, PPM_ERR_CAPACITY, "more than 2^32-1 gather nodes");
+    CK(c, c->e_pos.ensure(cap * 24)); CK(c, c->e_nrm.ensure(cap * 24)); CK(c, c->e_w.ensure(cap * 24));
+    CK(c, c->e_prev.ensure(cap * 4));
+    CK(c, c->e_direct.ensure(cap * 24)); CK(c, c->e_photon.ensure(cap * 24));
+    CK(c, cudaMemsetAsync(c->stats.p, 0, 64, st));
+    EyeNodes nodes = {c->e_pos.as<double>(), c->e_nrm.as<double>(), c->e_w.as<double>(), c->e_prev.as<uint32_t>()};
+    k_eye_expand<<<nblk(n, 128), 128, 0, st>>>(c->scene, c->cam, drays, n, first_pixel, seed, pass, nodes, (uint32_t)cap,
+                                              c->e_head.as<uint32_t>(), c->e_emit.as<double>(), dstats + 2, dstats);
+    KCHECK(c);
+    unsigned long long made = 0;
+    CK(c, cudaMemcpyAsync(&made, dstats + 2, 8, cudaMemcpyDeviceToHost, st));
+    CK(c, cudaStreamSynchronize(st));
+    if (made <= cap) { nn = (uint32_t)made; break; }
+    if (attempt >= 2) return fail(c, PPM_ERR_CAPACITY, "gather-node pool keeps overflowing");
+    c->eye_cap = made + made / 4;                           // pool overflow: grow and walk again
+  }
+  EyeNodes nodes = {c->e_pos.as<double>(), c->e_nrm.as<double>(), c->e_w.as<double>(), c->e_prev.as<uint32_t>()};
   cudaEventRecord(c->ev[ppm_ctx::EV_B1], st);
   if (uc && nn) {
     k_direct_light<<<nblk((int64_t)nn, 128), 128, 0, st>>>(c->scene, nodes.pos3, nodes.nrm3, nn, c->e_direct.as<double>());
@@ -1008,7 +1029,7 @@ int eye_gather(ppm_ctx* c, uint32_t nn) {
 // Eye branch, part 3 (main stream, after direct light AND gather): combine per pixel,
 // optionally add into the accumulator.
 int eye_combine(ppm_ctx* c, int64_t n, int64_t first_pixel, int uc, double* dout, double* daccum) {
-  k_combine<<<nblk(n, 256), 256, 0, c->stream>>>(c->e_off.as<uint32_t>(), c->e_w.as<double>(), uc ? c->e_direct.as<double>() : nullptr,
+  k_combine<<<nblk(n, 256), 256, 0, c->stream>>>(c->e_head.as<uint32_t>(), c->e_prev.as<uint32_t>(), c->e_w.as<double>(), uc ? c->e_direct.as<double>() : nullptr,
                                                 c->e_photon.as<double>(), c->e_emit.as<double>(), n, dout, daccum, first_pixel);
   KCHECK(c);
   return PPM_OK;
@@ -1062,7 +1083,7 @@ void ppm_destroy(ppm_ctx* c) {
   DBuf* all[] = {&c->r_pos, &c->r_dir, &c->r_wl, &c->r_tag, &c->counter, &c->keys, &c->keys2, &c->vals, &c->vals2, &c->cub_tmp,
                  &c->cell_start, &c->hist, &c->bbox, &c->axis_hist, &c->m_P, &c->m_D, &c->m_orig, &c->q_key, &c->q_key2, &c->q_idx, &c->q_idx2,
                  &c->st_in0, &c->st_in1, &c->st_out0, &c->st_out1, &c->st_out2, &c->st_out3, &c->st_out4,
-                 &c->e_cnt, &c->e_off, &c->e_pos, &c->e_nrm, &c->e_w, &c->e_emit, &c->e_direct, &c->e_photon, &c->e_rays,
+                 &c->e_head, &c->e_prev, &c->e_pos, &c->e_nrm, &c->e_w, &c->e_emit, &c->e_direct, &c->e_photon, &c->e_rays,
                  &c->pass_img, &c->accum, &c->npass, &c->stats, &c->cub_tmp2};
   for (DBuf* b : all) b->release();
   for (int i = 0; i < ppm_ctx::EV_COUNT; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
