@@ -168,6 +168,7 @@ struct Grid {
   double inv_cell;
   int32_t nx, ny, nz;
   uint32_t ncells;
+  int32_t reach;      // cell edge >= r / reach: neighbours are within +-reach cells on every axis
 };
 __device__ __forceinline__ unsigned long long enc_ord(double v) {
   unsigned long long b = (unsigned long long)__double_as_longlong(v);
@@ -282,13 +283,15 @@ __global__ void k_query_key(Grid g, const double* __restrict__ qpos3, int64_t n,
 }
 
 // v2: warp-cooperative gather.  A warp owns 32 cell-sorted queries (one per lane).
-// For each distinct cell among them, the photons of the 3x3x3 neighbourhood (nine
-// x-contiguous runs of the sorted map) form one virtual candidate stream; 32
-// candidates at a time are fetched with coalesced 16-byte loads, staged in shared
-// memory, and every lane tests the SAME photon (broadcast LDS.128) against its own
-// query -- no per-lane loop lengths, no scattered global loads.
+// For each distinct cell among them, the photons of the (2R+1)^3 neighbourhood -- (2R+1)^2
+// x-contiguous runs of the sorted map, R = 1 (cell edge r: 9 runs of 3 cells) or R = 2 (cell
+// edge r/2: 25 runs of 5 cells, 30 % fewer candidates) -- form one virtual candidate stream;
+// 32 candidates at a time are fetched with coalesced 16-byte loads, staged in shared memory,
+// and every lane tests the SAME photon (broadcast LDS.128) against its own query -- no
+// per-lane loop lengths, no scattered global loads.
 #define GATHER_WARPS 4
-template <int FILTER>
+#define GATHER_SPAN 3        // a group may span cells cx .. cx+3 of one row
+template <int FILTER, int REACH>
 __global__ void __launch_bounds__(GATHER_WARPS * 32)
 k_gather(Grid g, const uint32_t* __restrict__ cell_start, MapSoA m, const uint32_t* __restrict__ qkey,
          const uint32_t* __restrict__ qidx, const double* __restrict__ qpos3, const double* __restrict__ qnrm3, int64_t n,
@@ -296,6 +299,9 @@ k_gather(Grid g, const uint32_t* __restrict__ cell_start, MapSoA m, const uint32
          unsigned long long* __restrict__ sum_k) {
   __shared__ double2 sP[GATHER_WARPS][32][2];
   __shared__ double2 sD[GATHER_WARPS][32][2];
+  __shared__ uint32_t sEnd[GATHER_WARPS][32], sOff[GATHER_WARPS][32];   // per run: cumulative end, start - exclusive prefix
+  constexpr int W = 2 * REACH + 1, ROWS = W * W;
+  static_assert(ROWS <= 32, "one lane per run");
   const unsigned FULL = 0xffffffffu;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t s = ((int64_t)blockIdx.x * GATHER_WARPS + warp) * 32 + lane;
@@ -315,39 +321,45 @@ k_gather(Grid g, const uint32_t* __restrict__ cell_start, MapSoA m, const uint32
   while (pending) {
     const int leader = __ffs(pending) - 1;
     const uint32_t ck = __shfl_sync(FULL, key, leader);
-    const bool act = key == ck;
-    pending &= ~__ballot_sync(FULL, act);
+    // Group = the pending lanes whose cell lies in the leader's row (same cy, cz) at most
+    // GATHER_SPAN cells to the right of the leader's cell (keys are sorted, x fastest).  They
+    // share ONE candidate stream covering [cx_leader - R, cx_last + R]: a superset of every
+    // lane's own neighbourhood, so the extra candidates simply fail the distance test.
+    const bool act = valid && key >= ck && key - ck <= (uint32_t)GATHER_SPAN && key / nxp == ck / nxp;
+    const unsigned grp = __ballot_sync(FULL, act);
+    pending &= ~grp;
+    const uint32_t klast = __shfl_sync(FULL, key, 31 - __clz((int)grp));
     const int cx = (int)(ck % nxp), cy = (int)((ck / nxp) % nyp), cz = (int)(ck / (nxp * nyp));
-    const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.nx - 1);
-    // lane l < 9 looks up run l = (dz, dy) of the neighbourhood
+    const int x0 = max(cx - REACH, 0), x1 = min((int)(klast % nxp) + REACH, g.nx - 1);
+    // lane l < ROWS looks up run l = (dz, dy) of the neighbourhood
     uint32_t rbeg = 0, rlen = 0;
-    if (lane < 9 && x0 <= x1) {
-      const int z = cz + lane / 3 - 1, y = cy + lane % 3 - 1;
+    if (lane < ROWS && x0 <= x1) {
+      const int z = cz + lane / W - REACH, y = cy + lane % W - REACH;
       if (z >= 0 && z < g.nz && y >= 0 && y < g.ny) {
         const uint32_t row = ((uint32_t)z * (uint32_t)g.ny + (uint32_t)y) * (uint32_t)g.nx;
         rbeg = cell_start[row + x0];
         rlen = cell_start[row + x1 + 1] - rbeg;
       }
     }
-    uint32_t pre = rlen;                               // inclusive prefix of run lengths over lanes 0..8
+    uint32_t pre = rlen;                               // inclusive prefix of the run lengths
 #pragma unroll
-    for (int o = 1; o < 16; o <<= 1) {
+    for (int o = 1; o < 32; o <<= 1) {
       uint32_t t = __shfl_up_sync(FULL, pre, o);
       if (lane >= o) pre += t;
     }
-    const uint32_t total = __shfl_sync(FULL, pre, 8);
-    uint32_t cend[9], off[9];                          // cumulative end and (start - exclusive prefix) of each run
-#pragma unroll
-    for (int r = 0; r < 9; ++r) {
-      cend[r] = __shfl_sync(FULL, pre, r);
-      off[r] = __shfl_sync(FULL, rbeg - (pre - rlen), r);
-    }
+    const uint32_t total = __shfl_sync(FULL, pre, 31);
+    __syncwarp();
+    sEnd[warp][lane] = pre;
+    sOff[warp][lane] = rbeg - (pre - rlen);
+    __syncwarp();
     for (uint32_t base = 0; base < total; base += 32) {
       const uint32_t v = base + lane;
       if (v < total) {
-        uint32_t o = off[0];
+        int run = 0;                                   // number of runs that end at or before v (binary search)
 #pragma unroll
-        for (int r = 1; r < 9; ++r) o = v >= cend[r - 1] ? off[r] : o;
+        for (int step = 16; step > 0; step >>= 1)
+          if (sEnd[warp][run + step - 1] <= v) run += step;
+        const uint32_t o = sOff[warp][run];
         const uint64_t j = (uint64_t)(v + o) * 2;
         sP[warp][lane][0] = m.P[j]; sP[warp][lane][1] = m.P[j + 1];
         sD[warp][lane][0] = m.D[j]; sD[warp][lane][1] = m.D[j + 1];
@@ -394,10 +406,11 @@ __global__ void k_within(Grid g, const uint32_t* __restrict__ cell_start, MapSoA
   const double qx = qpos3[q * 3], qy = qpos3[q * 3 + 1], qz = qpos3[q * 3 + 2];
   uint32_t cnt = 0;
   int cx = cell_coord(g, qx, 0), cy = cell_coord(g, qy, 1), cz = cell_coord(g, qz, 2);
-  int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.nx - 1);
+  const int R = g.reach;
+  int x0 = max(cx - R, 0), x1 = min(cx + R, g.nx - 1);
   if (x0 <= x1)
-    for (int z = max(cz - 1, 0); z <= min(cz + 1, g.nz - 1); ++z)
-      for (int y = max(cy - 1, 0); y <= min(cy + 1, g.ny - 1); ++y) {
+    for (int z = max(cz - R, 0); z <= min(cz + R, g.nz - 1); ++z)
+      for (int y = max(cy - R, 0); y <= min(cy + R, g.ny - 1); ++y) {
         uint32_t row = ((uint32_t)z * (uint32_t)g.ny + (uint32_t)y) * (uint32_t)g.nx;
         uint32_t b = cell_start[row + x0], e = cell_start[row + x1 + 1];
         for (uint32_t j = b; j < e; ++j) {
@@ -813,7 +826,7 @@ int do_map_build(ppm_ctx* c, double radius2) {
   Grid g;
   std::memset(&g, 0, sizeof g);
   double cell = std::sqrt(radius2) * (1.0 + 1.0 / 1024.0);   // edge slightly > r: the 27-cell walk can never miss
-  g.nx = g.ny = g.nz = 1; g.inv_cell = 1.0 / cell; g.ncells = 1;
+  g.nx = g.ny = g.nz = 1; g.inv_cell = 1.0 / cell; g.ncells = 1; g.reach = 1;
   if (n > 0) {
     CK(c, c->bbox.ensure(48));
     unsigned long long init[6] = {~0ull, ~0ull, ~0ull, 0ull, 0ull, 0ull};
@@ -876,6 +889,14 @@ int do_map_build(ppm_ctx* c, double radius2) {
     // walls) then sit mid-cell, so the +-1 ulp noise of hit points on such a plane cannot
     // straddle a cell boundary (which would split every warp of queries on that wall).
     const double CELL_CAP = 67108864.0;   // 2^26 cells
+    {
+      // Half-size cells (reach 2: 25 runs of 5 cells, candidate area 6.25 r^2 instead of 9 r^2) while
+      // the cell table stays small (<= 2^23 cells); otherwise cells of edge r (reach 1).
+      const char* force = std::getenv("PPM_GATHER_REACH");
+      double half = 0.5 * cell, prod = 1.0;
+      for (int k = 0; k < 3; ++k) prod *= std::floor((hi[k] - (lo[k] - 0.5 * half)) / half) + 2.0;
+      if (prod <= 8388608.0 && force && force[0] == '2') { cell = half; g.reach = 2; }   // opt-in: measured slower (fewer queries per cell)
+    }
     for (;;) {
       double dims[3];
       for (int k = 0; k < 3; ++k) dims[k] = std::floor((hi[k] - (lo[k] - 0.5 * cell)) / cell) + 2.0;
@@ -883,7 +904,7 @@ int do_map_build(ppm_ctx* c, double radius2) {
         g.nx = (int32_t)dims[0]; g.ny = (int32_t)dims[1]; g.nz = (int32_t)dims[2];
         break;
       }
-      cell *= 2.0;
+      cell *= 2.0; g.reach = 1;
     }
     for (int k = 0; k < 3; ++k) g.org[k] = lo[k] - 0.5 * cell;
     g.inv_cell = 1.0 / cell;
@@ -960,17 +981,14 @@ int launch_gather(ppm_ctx* c, const double* dpos, const double* dnrm, int64_t n,
   const uint32_t* cs = c->cell_start.as<uint32_t>();
   const uint32_t* qk = c->q_key2.as<uint32_t>();
   const uint32_t* qx = c->q_idx2.as<uint32_t>();
+#define GATHER_LAUNCH(F, R) k_gather<F, R><<<nblk(n, B), B, 0, c->stream>>>(c->grid, cs, mapsoa(c), qk, qx, dpos, dnrm, n, c->power, c->r2, drgb, dcounts, dsumk)
+  const bool r2x = c->grid.reach == 2;
   switch (filter) {
-    case PPM_FILTER_NONE:
-      k_gather<PPM_FILTER_NONE><<<nblk(n, B), B, 0, c->stream>>>(c->grid, cs, mapsoa(c), qk, qx, dpos, dnrm, n, c->power, c->r2, drgb, dcounts, dsumk);
-      break;
-    case PPM_FILTER_CONE:
-      k_gather<PPM_FILTER_CONE><<<nblk(n, B), B, 0, c->stream>>>(c->grid, cs, mapsoa(c), qk, qx, dpos, dnrm, n, c->power, c->r2, drgb, dcounts, dsumk);
-      break;
-    default:
-      k_gather<PPM_FILTER_GAUSS><<<nblk(n, B), B, 0, c->stream>>>(c->grid, cs, mapsoa(c), qk, qx, dpos, dnrm, n, c->power, c->r2, drgb, dcounts, dsumk);
-      break;
+    case PPM_FILTER_NONE: if (r2x) GATHER_LAUNCH(PPM_FILTER_NONE, 2); else GATHER_LAUNCH(PPM_FILTER_NONE, 1); break;
+    case PPM_FILTER_CONE: if (r2x) GATHER_LAUNCH(PPM_FILTER_CONE, 2); else GATHER_LAUNCH(PPM_FILTER_CONE, 1); break;
+    default:              if (r2x) GATHER_LAUNCH(PPM_FILTER_GAUSS, 2); else GATHER_LAUNCH(PPM_FILTER_GAUSS, 1); break;
   }
+#undef GATHER_LAUNCH
   KCHECK(c);
   return PPM_OK;
 }
