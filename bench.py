@@ -120,13 +120,16 @@ def run_reference(args):
 # GPU side
 # ---------------------------------------------------------------------------
 class ClockSampler:
-    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi sampling in the background.  Started BEFORE the warm-up (nvidia-smi takes a second to
+    start on an 8-GPU box); only samples whose timestamp falls inside the timed window are reported."""
+    FIELDS = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.p = None
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
@@ -135,10 +138,18 @@ class ClockSampler:
         except OSError:
             self.p = None
 
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
+
     def stop(self):
+        import datetime
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.p is None:
             return out
+        time.sleep(0.05)
         self.p.terminate()
         try:
             self.p.wait(timeout=5)
@@ -146,20 +157,30 @@ class ClockSampler:
             self.p.kill()
         self.f.flush()
         self.f.seek(0)
-        sm, mx, reasons = [], [], set()
+        rows = []
         for line in self.f.read().splitlines():
             c = [x.strip() for x in line.split(",")]
-            if len(c) < 9:
+            if len(c) < 10:
                 continue
             try:
-                sm.append(float(c[1])); mx.append(float(c[2]))
+                ts = datetime.datetime.strptime(c[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(c[2]), float(c[3]), c[6:10]))
             except ValueError:
                 continue
-            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], c[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        if sm:
-            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        t0, t1 = self.t0 or 0.0, self.t1 or 1e18
+        inside = [r for r in rows if t0 - 0.02 <= r[0] <= t1 + 0.02]
+        window = "timed region"
+        if not inside:                                   # timed region shorter than one sampling period
+            inside = [r for r in rows if t0 - 1.0 <= r[0] <= t1 + 1.0]
+            window = "timed region +-1 s"
+        if inside:
+            reasons = set()
+            for r in inside:
+                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[3]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            out.update(sm_mhz=statistics.median([r[1] for r in inside]), sm_max_mhz=max(r[2] for r in inside),
+                       reasons=sorted(reasons), samples=len(inside), window=window)
         try:
             os.unlink(self.f.name)
         except OSError:
@@ -217,6 +238,8 @@ def run_gpu(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    sampler.start()
     for s in range(W):
         one_pass(s)
     with torch.cuda.stream(stream):
@@ -224,12 +247,11 @@ def run_gpu(args):
     eng.accum_reset()
 
     # ---- device-resident timed region ----------------------------------------------------
-    sampler = ClockSampler(local)
     phases = {}
     counts = {}
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
-    sampler.start()
+    sampler.mark_begin()
     ev0.record(stream)
     for s in range(K):
         one_pass(W + s)
@@ -242,6 +264,7 @@ def run_gpu(args):
         parallel.reduce_accumulators(acc, dst=0)         # ONE sum-reduce of (3*W*H + 1) doubles per frame
     ev1.record(stream)
     sync_all()
+    sampler.mark_end()
     clocks = sampler.stop()
     t_ms = torch.tensor([ev0.elapsed_time(ev1)], device="cuda", dtype=torch.float64)
     if world > 1:
