@@ -257,6 +257,13 @@ int  ppm_trace_rays(ppm_ctx* ctx, const double* rays6_h_or_d, int64_t n,
                     int64_t first_pixel, uint64_t seed, uint32_t pass, int uc,
                     double* rgb3_h_or_d);
 
+/* -- trace_ray_classic, tracer.rs:221-259 (the `rtc` binary, rtc.rs:17-38): Whitted-style
+ *    tracing without a photon map: di = classic direct light + camera ambient; mirror
+ *    direction without the glossy lobe; Fresnel from cos1. */
+int  ppm_trace_rays_classic(ppm_ctx* ctx, const double* rays6_h_or_d, int64_t n,
+                            int64_t first_pixel, uint64_t seed, uint32_t pass,
+                            double* rgb3_h_or_d);
+
 /* -- one whole PPM-PA pass = `ppmpa` main, ppmpa.rs:21-46,74-84:
  *    trace photons, build map, generate + trace every eye ray, and add the
  *    pass image into the on-device accumulator (util/averager2.rb:49-62). */

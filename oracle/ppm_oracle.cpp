@@ -853,6 +853,36 @@ Rad trace_ray(EyeCtx& cx, const ppm_material* m0, int l, const Ray& r, uint32_t 
   return radd(em, surf_bsdf(mate, is1.nvec, r.dir, rdir, c, di, si, ti));
 }
 
+// tracer.rs:221-259 (the `rtc` renderer): no photon map, no glossy lobe, Fresnel from cos1
+Rad trace_ray_classic(const Scene& sc, const double ambient[3], const ppm_material* m0, int l, const Ray& r) {
+  if (l >= 10) return RAD0;
+  Intersection is1;
+  if (!calc_intersection(r, sc, &is1)) return RAD0;
+  const ppm_material& mate = *is1.mate;
+  V3 rdir; Flt cos1;
+  specular_reflection(is1.nvec, r.dir, &rdir, &cos1);
+  Rad di = RAD0;
+  for (int i = 0; i < sc.nlights; ++i) di = radd(di, get_radiance_from_light(sc, is1.pos, is1.nvec, sc.lights[i]));
+  Rad amb = {{ambient[0], ambient[1], ambient[2]}};
+  di = radd(di, amb);
+  Rad si = RAD0;
+  if (surf_reflect(mate, cos1)) {
+    Ray nr = {is1.pos, rdir};
+    si = trace_ray_classic(sc, ambient, m0, l + 1, nr);
+  }
+  Flt eta = relative_ior_average(m0->ior, mate.ior);
+  V3 tdir; Flt cos2;
+  bool has_t = specular_refraction(is1.nvec, r.dir, eta, &tdir, &cos2);
+  Rad ti = RAD0;
+  if (has_t && surf_refract(mate, cos1)) {
+    const ppm_material* m02 = dot(tdir, is1.nvec) < 0.0 ? &mate : &M_AIR;
+    Ray nr = {is1.pos, tdir};
+    ti = trace_ray_classic(sc, ambient, m02, l + 1, nr);
+  }
+  Rad em = {{mate.emittance[0] * SR_HALF, mate.emittance[1] * SR_HALF, mate.emittance[2] * SR_HALF}};
+  return radd(em, surf_bsdf(mate, is1.nvec, r.dir, rdir, cos1, di, si, ti));
+}
+
 // camera.rs:58-75
 Ray generate_ray(const ppm_camera& cam, Flt y, Flt x, Rng& rng) {
   V3 blur = V_O;
@@ -1143,6 +1173,16 @@ void orc_trace_rays(const ppm_prim* prims, int np, const ppm_material* mats, int
   }
   for (auto& x : th) x.join();
   if (stats3) { stats3[0] = stats3[1] = stats3[2] = 0; for (int t = 0; t < nthreads; ++t) for (int k = 0; k < 3; ++k) stats3[k] += st[(size_t)t * 3 + k]; }
+}
+// trace_ray_classic over a batch of rays (rtc.rs:29-30)
+void orc_trace_rays_classic(const ppm_prim* prims, int np, const ppm_material* mats, int nm, const ppm_light* lights, int nl,
+                            const double ambient[3], const double* rays6, int64_t n, double* rgb3) {
+  Scene sc = mk_scene(prims, np, mats, nm, lights, nl);
+  for (int64_t i = 0; i < n; ++i) {
+    Ray r = {mk(rays6[i * 6], rays6[i * 6 + 1], rays6[i * 6 + 2]), mk(rays6[i * 6 + 3], rays6[i * 6 + 4], rays6[i * 6 + 5])};
+    Rad c = trace_ray_classic(sc, ambient, &M_AIR, 0, r);
+    rgb3[i * 3] = c.c[0]; rgb3[i * 3 + 1] = c.c[1]; rgb3[i * 3 + 2] = c.c[2];
+  }
 }
 // direct light probe: get_radiance_from_light summed over lights (tracer.rs:136-141)
 void orc_direct_light(const ppm_prim* prims, int np, const ppm_material* mats, int nm, const ppm_light* lights, int nl,

@@ -426,23 +426,28 @@ struct EyeNode {
   bool reflect, refract;
   int t_medium;
 };
-__device__ __forceinline__ void eye_node(const DevScene& sc, const Isect& is, D3 in_dir, int medium, Philox& rng, EyeNode& nd) {
+// classic = trace_ray_classic (tracer.rs:221-259, the `rtc` binary): mirror direction without the
+// glossy lobe (no random draws), refraction about the geometric normal, Fresnel from cos1, and the
+// next medium chosen by the sign of tdir.nvec.
+__device__ __forceinline__ void eye_node(const DevScene& sc, const Isect& is, D3 in_dir, int medium, Philox& rng, EyeNode& nd,
+                                         bool classic = false) {
   const ppm_material& m = sc.mats[is.mat];
   D3 rdir0; double cos1;
   specular_reflection(is.nvec, in_dir, rdir0, cos1);
-  nd.rdir = reflection_glossy(is.nvec, rdir0, surf_power_glossy(m), rng);
+  nd.rdir = classic ? rdir0 : reflection_glossy(is.nvec, rdir0, surf_power_glossy(m), rng);
   nd.reflect = surf_reflect(m, cos1);
   // relative_ior_average, physics.rs:192-196
   double a1 = medium < 0 ? (1.0 + 1.0 + 1.0) / 3.0 : (sc.mats[medium].ior[0] + sc.mats[medium].ior[1] + sc.mats[medium].ior[2]) / 3.0;
   double a2 = (m.ior[0] + m.ior[1] + m.ior[2]) / 3.0;
   double eta = relative_ior(a1, a2);
-  D3 hvec = mk3(1.0, 0.0, 0.0);
-  bool hv = normalize(nd.rdir - in_dir, hvec);
+  D3 hvec = is.nvec;
+  bool hv = classic ? true : normalize(nd.rdir - in_dir, hvec);
   double cos2;
   bool has_t = specular_refraction(hvec, in_dir, eta, nd.tdir, cos2);
   nd.refract = hv && has_t && surf_refract(m, cos1);
   nd.t_medium = is.io == 0 ? is.mat : -1;          // tracer.rs:164-167
-  double c = cos1 < cos2 ? cos1 : cos2;
+  if (classic && has_t) nd.t_medium = dot(nd.tdir, is.nvec) < 0.0 ? is.mat : -1;   // tracer.rs:251
+  double c = classic ? cos1 : (cos1 < cos2 ? cos1 : cos2);                          // tracer.rs:258 vs :173
   const double ONE_PI = 1.0 / PPM_PI;
   nd.kd = nd.ks = nd.kt = mk3(0.0, 0.0, 0.0);
   if (m.surface == PPM_SURF_SIMPLE) {

@@ -476,7 +476,7 @@ __global__ void __launch_bounds__(128)
 k_eye_expand(const __grid_constant__ DevScene sc, const __grid_constant__ ppm_camera cam, const double* __restrict__ rays6,
              int64_t n, int64_t first_pixel, uint64_t seed, uint32_t pass, EyeNodes nodes, uint32_t cap,
              uint32_t* __restrict__ head, double* __restrict__ emit3, unsigned long long* __restrict__ pool_counter,
-             unsigned long long* __restrict__ n_visited) {
+             unsigned long long* __restrict__ n_visited, int classic) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const unsigned lane = threadIdx.x & 31u;
@@ -499,7 +499,7 @@ k_eye_expand(const __grid_constant__ DevScene sc, const __grid_constant__ ppm_ca
     ++visited;
     Philox rng(seed, pass, PPM_DOMAIN_EYE, (uint64_t)pix, e.node);
     EyeNode nd;
-    eye_node(sc, is, e.dir, e.medium, rng, nd);
+    eye_node(sc, is, e.dir, e.medium, rng, nd, classic != 0);
     const ppm_material& m = sc.mats[is.mat];
     emit = emit + cmul(e.W, ld3(m.emittance) * SR_HALF);
     const D3 wd = cmul(e.W, nd.kd);
@@ -610,13 +610,18 @@ k_direct_light(const __grid_constant__ DevScene sc, const double* __restrict__ p
 __global__ void k_combine(const uint32_t* __restrict__ head, const uint32_t* __restrict__ prev, const double* __restrict__ w3,
                           const double* __restrict__ direct3, const double* __restrict__ photon3,
                           const double* __restrict__ emit3, int64_t n, double* __restrict__ out3,
-                          double* __restrict__ accum3, int64_t accum_first) {
+                          double* __restrict__ accum3, int64_t accum_first, D3 ambient) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   D3 rad = ld3(emit3 + i * 3);
   for (uint32_t s = head[i]; s != EYE_NONE; s = prev[s]) {
-    D3 di = ld3(photon3 + (uint64_t)s * 3);
-    if (direct3) di = ld3(direct3 + (uint64_t)s * 3) + di;     // di = direct + estimate, tracer.rs:136-145
+    D3 di;
+    if (photon3) {
+      di = ld3(photon3 + (uint64_t)s * 3);
+      if (direct3) di = ld3(direct3 + (uint64_t)s * 3) + di;   // di = direct + estimate, tracer.rs:136-145
+    } else {
+      di = ld3(direct3 + (uint64_t)s * 3) + ambient;           // classic: di = direct + cam.ambient, tracer.rs:234-238
+    }
     rad = rad + cmul(ld3(w3 + (uint64_t)s * 3), di);
   }
   st3(out3 + i * 3, rad);
@@ -996,7 +1001,7 @@ int launch_gather(ppm_ctx* c, const double* dpos, const double* dnrm, int64_t n,
 // Eye branch, part 1 (stream `st`): expand the eye paths into the gather-node list and
 // compute the classic direct light at every node.  drays == NULL generates camera rays.
 int eye_front(ppm_ctx* c, cudaStream_t st, DBuf& tmpbuf, const double* drays, int64_t n, int64_t first_pixel, uint64_t seed,
-              uint32_t pass, int uc, uint32_t* nn_out) {
+              uint32_t pass, int uc, uint32_t* nn_out, int classic = 0) {
   (void)tmpbuf;
   CK(c, c->e_head.ensure((size_t)n * 4));
   CK(c, c->e_emit.ensure((size_t)n * 24)); CK(c, c->stats.ensure(64));
@@ -1013,7 +1018,7 @@ int eye_front(ppm_ctx* c, cudaStream_t st, DBuf& tmpbuf, const double* drays, in
     CK(c, cudaMemsetAsync(c->stats.p, 0, 64, st));
     EyeNodes nodes = {c->e_pos.as<double>(), c->e_nrm.as<double>(), c->e_w.as<double>(), c->e_prev.as<uint32_t>()};
     k_eye_expand<<<nblk(n, 128), 128, 0, st>>>(c->scene, c->cam, drays, n, first_pixel, seed, pass, nodes, (uint32_t)cap,
-                                              c->e_head.as<uint32_t>(), c->e_emit.as<double>(), dstats + 2, dstats);
+                                              c->e_head.as<uint32_t>(), c->e_emit.as<double>(), dstats + 2, dstats, classic);
     KCHECK(c);
     unsigned long long made = 0;
     CK(c, cudaMemcpyAsync(&made, dstats + 2, 8, cudaMemcpyDeviceToHost, st));
@@ -1046,21 +1051,24 @@ int eye_gather(ppm_ctx* c, uint32_t nn) {
 }
 // Eye branch, part 3 (main stream, after direct light AND gather): combine per pixel,
 // optionally add into the accumulator.
-int eye_combine(ppm_ctx* c, int64_t n, int64_t first_pixel, int uc, double* dout, double* daccum) {
-  k_combine<<<nblk(n, 256), 256, 0, c->stream>>>(c->e_head.as<uint32_t>(), c->e_prev.as<uint32_t>(), c->e_w.as<double>(), uc ? c->e_direct.as<double>() : nullptr,
-                                                c->e_photon.as<double>(), c->e_emit.as<double>(), n, dout, daccum, first_pixel);
+int eye_combine(ppm_ctx* c, int64_t n, int64_t first_pixel, int uc, double* dout, double* daccum, int classic = 0) {
+  const D3 amb = {c->cam.ambient[0], c->cam.ambient[1], c->cam.ambient[2]};
+  k_combine<<<nblk(n, 256), 256, 0, c->stream>>>(c->e_head.as<uint32_t>(), c->e_prev.as<uint32_t>(), c->e_w.as<double>(),
+                                                (uc || classic) ? c->e_direct.as<double>() : nullptr,
+                                                classic ? nullptr : c->e_photon.as<double>(), c->e_emit.as<double>(), n, dout, daccum,
+                                                first_pixel, amb);
   KCHECK(c);
   return PPM_OK;
 }
 // serial version on the main stream (ppm_trace_rays)
 int do_trace_rays(ppm_ctx* c, const double* drays, int64_t n, int64_t first_pixel, uint64_t seed, uint32_t pass, int uc,
-                  double* dout, double* daccum) {
+                  double* dout, double* daccum, int classic = 0) {
   if (n <= 0) return PPM_OK;
   uint32_t nn = 0;
-  int rc = eye_front(c, c->stream, c->cub_tmp, drays, n, first_pixel, seed, pass, uc, &nn);
+  int rc = eye_front(c, c->stream, c->cub_tmp, drays, n, first_pixel, seed, pass, classic ? 1 : uc, &nn, classic);
   if (rc) return rc;
-  if ((rc = eye_gather(c, nn))) return rc;
-  return eye_combine(c, n, first_pixel, uc, dout, daccum);
+  if (!classic && (rc = eye_gather(c, nn))) return rc;
+  return eye_combine(c, n, first_pixel, uc, dout, daccum, classic);
 }
 
 }  // namespace
@@ -1312,6 +1320,21 @@ int ppm_generate_rays(ppm_ctx* c, uint64_t seed, uint32_t pass, double* rays6) {
   k_gen_rays<<<nblk(n, 128), 128, 0, c->stream>>>(c->cam, seed, pass, n, (double*)d);
   KCHECK(c);
   if ((rc = finish_out(c, rays6, (size_t)n * 48, d))) return rc;
+  CK(c, cudaStreamSynchronize(c->stream));
+  return PPM_OK;
+}
+
+int ppm_trace_rays_classic(ppm_ctx* c, const double* rays6, int64_t n, int64_t first_pixel, uint64_t seed, uint32_t pass, double* rgb3) {
+  if (!c) return PPM_ERR_ARG;
+  if (!c->have_scene) return fail(c, PPM_ERR_STATE, "scene not set");
+  if (n < 0 || first_pixel < 0 || (n > 0 && (!rays6 || !rgb3))) return fail(c, PPM_ERR_ARG, "null argument");
+  if (n == 0) return PPM_OK;
+  CK(c, cudaSetDevice(c->device));
+  const void* dr; void* dout; int rc;
+  if ((rc = stage_in(c, rays6, (size_t)n * 48, c->st_in0, &dr))) return rc;
+  if ((rc = stage_out(c, rgb3, (size_t)n * 24, c->st_out0, &dout))) return rc;
+  if ((rc = do_trace_rays(c, (const double*)dr, n, first_pixel, seed, pass, 1, (double*)dout, nullptr, 1))) return rc;
+  if ((rc = finish_out(c, rgb3, (size_t)n * 24, dout))) return rc;
   CK(c, cudaStreamSynchronize(c->stream));
   return PPM_OK;
 }

@@ -10,6 +10,7 @@ Names follow the reference (file:line under the reference tree):
   Engine.estimate_radiance           tracer.rs:179
   Engine.generate_rays               camera.rs:58
   Engine.trace_rays                  tracer.rs:129
+  Engine.trace_rays_classic          tracer.rs:221 (rtc)
   Engine.iteration                   ppmpa.rs:74   (one whole pass)
 
 Arrays are numpy (host) or anything exposing a CUDA device pointer via
@@ -258,6 +259,14 @@ class Engine:
         n = rays6.shape[0]
         out = np.empty((n, 3))
         self._ck(lib.ppm_trace_rays(self._h, _ptr(rays6), n, first_pixel, seed, npass, 1 if uc else 0, _ptr(out)))
+        return out
+
+    def trace_rays_classic(self, rays6, seed, npass, first_pixel=0):
+        """trace_ray_classic (tracer.rs:221), the `rtc` renderer: no photon map."""
+        rays6 = _f64(rays6, (6,))
+        n = rays6.shape[0]
+        out = np.empty((n, 3))
+        self._ck(lib.ppm_trace_rays_classic(self._h, _ptr(rays6), n, first_pixel, seed, npass, _ptr(out)))
         return out
 
     # ---- whole pass --------------------------------------------------------------

@@ -71,6 +71,7 @@ def load():
         "orc_generate_rays": (None, [P(K.Camera), u64, u32, vp]),
         "orc_trace_rays": (None, [P(K.Prim), C.c_int, P(K.Material), C.c_int, P(K.Light), C.c_int, vp, C.c_int, vp, i64,
                                   i64, u64, u32, C.c_int, vp, C.c_int, vp]),
+        "orc_trace_rays_classic": (None, [P(K.Prim), C.c_int, P(K.Material), C.c_int, P(K.Light), C.c_int, D3, vp, i64, vp]),
         "orc_direct_light": (None, [P(K.Prim), C.c_int, P(K.Material), C.c_int, P(K.Light), C.c_int, vp, vp, i64, vp]),
         "orc_render_pass": (C.c_int, [P(K.Prim), C.c_int, P(K.Material), C.c_int, P(K.Light), C.c_int, P(K.Camera), u64,
                                       u32, i64, dbl, C.c_int, C.c_int, C.c_int, vp, vp, vp]),
@@ -147,6 +148,13 @@ class Oracle:
         self.L.orc_trace_rays(scene.prims, scene.nprims, scene.mats, scene.nmats, scene.lights, scene.nlights, omap.h,
                               pfilter, _p(rays6), n, first_pixel, seed, npass, 1 if uc else 0, _p(out), nthreads, _p(stats))
         return out, stats
+
+    def trace_rays_classic(self, scene, ambient, rays6):
+        rays6 = np.ascontiguousarray(rays6, np.float64)
+        out = np.empty((len(rays6), 3))
+        self.L.orc_trace_rays_classic(scene.prims, scene.nprims, scene.mats, scene.nmats, scene.lights, scene.nlights,
+                                      d3(ambient), _p(rays6), len(rays6), _p(out))
+        return out
 
     def direct_light(self, scene, pos3, nrm3):
         pos3 = np.ascontiguousarray(pos3, np.float64); nrm3 = np.ascontiguousarray(nrm3, np.float64)

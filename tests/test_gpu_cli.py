@@ -75,3 +75,19 @@ def test_ppmpa_matches_render_pass(engine):
     # usage on too few arguments, exit status 0 like the reference
     r = subprocess.run([os.path.join(BIN, "ppmpa"), "-h"], capture_output=True)
     assert r.returncode == 0 and b"Usage: ppmpa" in r.stderr
+
+
+def test_rtc_matches_library(engine):
+    """rtc <screen file> <scene file> (src/bin/rtc.rs): classic tracer, header first, RGB ints when not progressive."""
+    scene, cam_file = os.path.join(EX, "coral-ball.scene"), os.path.join(EX, "screen1.scr")
+    r = subprocess.run([os.path.join(BIN, "rtc"), cam_file, scene], capture_output=True, env=ENV, check=True)
+    out = r.stdout.decode().splitlines()
+    assert out[:5] == ["P3", "## max radiance = 0.01", "## image parameters = 1/250, F4, ISO100", "256 256", "255"]
+    rgb = np.array([[int(x) for x in l.split()] for l in out[5:]])
+    cam = P.read_camera(cam_file)
+    engine.set_scene(P.read_scene(scene)); engine.set_camera(cam)
+    img = engine.trace_rays_classic(engine.generate_rays(12345, 3), 12345, 3)
+    want = np.floor(np.minimum(img / cam.max_radiance, 1.0) ** (1 / 2.2) * 255).astype(int)
+    assert rgb.shape == (256 * 256, 3) and np.array_equal(rgb, want)
+    r = subprocess.run([os.path.join(BIN, "rtc")], capture_output=True)
+    assert r.returncode == 0 and b"Usage: rtc" in r.stdout

@@ -356,6 +356,19 @@ def test_direct_light_matches_oracle(engine, oracle, name):
     assert np.mean(np.any(err > RTOL, axis=1)) <= 2e-3
 
 
+@pytest.mark.parametrize("name", [None, "ex-glassbox", "sample1", "mirror-ball", "ex-sunwindow"])
+def test_trace_rays_classic_parity(engine, oracle, name):
+    """trace_ray_classic (tracer.rs:221-259, the `rtc` renderer): deterministic given the rays."""
+    sc = load_scene(name)
+    cam = P.read_camera(os.path.join(EX, "screen1.scr"), xreso=64, yreso=64)       # ambient 0.001
+    engine.set_scene(sc); engine.set_camera(cam)
+    rays = oracle.generate_rays(cam, 3, 0)
+    g = engine.trace_rays_classic(rays, 3, 0)
+    o = oracle.trace_rays_classic(sc, list(cam.ambient), rays)
+    assert o.max() > 0 and list(cam.ambient) == [0.001, 0.001, 0.001]
+    assert_rel(g, o, 1e-12)
+
+
 def test_render_pass_matches_oracle_and_accumulates(engine, oracle):
     sc = load_scene("ex-glassbox")
     cam = P.read_camera(os.path.join(EX, "camera0.scr"), xreso=40, yreso=40, pfilter=K.FILTER_NONE, progressive=1)
