@@ -153,14 +153,15 @@ __device__ __forceinline__ bool moller(double l, D3 p0, D3 d1, D3 d2, D3 p, D3 d
 // guard-banded sign/magnitude test cannot settle u, v, u+v or t (see consider_ratio).
 // Guard-banded classification of fl(x / det) against [0, 1]:
 //   -1 = certainly rejected (u < 0 or u > 1), +1 = certainly inside, 0 = undecided (divide).
-// Requires 1e-300 < |det| < 1e300.  A negative quotient is only "certain" when it cannot
-// underflow to -0 (which `u < 0.0` would not reject).
-__device__ __forceinline__ int classify01(double x, double det, double ad) {
+// Requires 1e-300 < |det| < 1e300; ad_hi = |det|(1+G), ad_lo = |det|(1-G) are shared by the u
+// and v tests.  A negative quotient is only "certain" when it cannot underflow to -0 (which
+// `u < 0.0` would not reject).
+__device__ __forceinline__ int classify01(double x, double det, double ad, double ad_hi, double ad_lo) {
   const double ax = fabs(x);
   if (!(ax < 1e300)) return 0;                               // inf / NaN -> exact path
   if ((x < 0.0) != (det < 0.0)) return ax > ad * 1e-300 ? -1 : 0;
-  if (ax > ad * (1.0 + PPM_GUARD)) return -1;
-  return ax < ad * (1.0 - PPM_GUARD) ? 1 : 0;
+  if (ax > ad_hi) return -1;
+  return ax < ad_lo ? 1 : 0;
 }
 __device__ __forceinline__ void consider_polygon(double l, D3 p0, D3 d1, D3 d2, D3 p, D3 d, int o, double& best_t, int& best_o) {
   const D3 re2 = cross(d, d2);
@@ -169,22 +170,23 @@ __device__ __forceinline__ void consider_polygon(double l, D3 p0, D3 d1, D3 d2, 
   const D3 pp = p - p0;
   const double a = dot(re2, pp);                             // u = a / det
   const double ad = fabs(det);
+  const double ad_hi = ad * (1.0 + PPM_GUARD), ad_lo = ad * (1.0 - PPM_GUARD);
   bool exact = !(ad < 1e300 && ad > 1e-300);
   if (!exact) {
-    const int cu = classify01(a, det, ad);
+    const int cu = classify01(a, det, ad, ad_hi, ad_lo);
     if (cu < 0) return;
     exact = cu == 0;
   }
   const D3 te1 = cross(pp, d1);
   const double b = dot(te1, d);                              // v = b / det
   if (!exact) {
-    const int cv = classify01(b, det, ad);
+    const int cv = classify01(b, det, ad, ad_hi, ad_lo);
     if (cv < 0) return;
     exact = cv == 0;
     if (!exact) {
       const double sum = fabs(a) + fabs(b);                  // u + v against l (both quotients are >= 0 here)
-      if (sum > (ad * l) * (1.0 + PPM_GUARD)) return;
-      exact = !(sum < (ad * l) * (1.0 - PPM_GUARD));
+      if (sum > ad_hi * l) return;
+      exact = !(sum < ad_lo * l);
     }
   }
   const double c = dot(te1, d2);                             // t = c / det
