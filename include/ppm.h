@@ -269,6 +269,13 @@ int  ppm_trace_rays_classic(ppm_ctx* ctx, const double* rays6_h_or_d, int64_t n,
  *    pass image into the on-device accumulator (util/averager2.rb:49-62). */
 int  ppm_render_pass(ppm_ctx* ctx, uint64_t seed, uint32_t pass, int64_t nphoton,
                      double radius2, int uc);
+/* -- a batch of passes = the loop of util/iterator.rb:96-117 (pass i of the batch uses Philox
+ *    pass id first_pass + i*pass_stride and radius2[i]).  Alternate passes run on two lanes of
+ *    the same GPU so that phases of different passes overlap; the result (accumulator, last
+ *    pass image) is the same as calling ppm_render_pass npass times, except that the
+ *    accumulator is summed per lane first.  ppm_last_pass_stats then returns batch totals. */
+int  ppm_render_passes(ppm_ctx* ctx, uint64_t seed, uint32_t first_pass, uint32_t pass_stride,
+                       int32_t npass, int64_t nphoton, const double* radius2, int uc);
 /* last pass image (what ppmpa / rt print), rgb3[yreso*xreso][3] */
 int  ppm_pass_image_read(ppm_ctx* ctx, double* rgb3_h_or_d);
 /* accumulator: sum over passes + number of passes summed */

@@ -24,6 +24,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 // ===========================================================================
@@ -631,6 +632,11 @@ __global__ void k_combine(const uint32_t* __restrict__ head, const uint32_t* __r
   }
 }
 __global__ void k_bump(double* npass) { npass[0] += 1.0; }
+// acc += other; other = 0   (merging the twin lane's accumulator, incl. the pass counter)
+__global__ void k_accum_merge(double* __restrict__ acc, double* __restrict__ other, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { acc[i] += other[i]; other[i] = 0.0; }
+}
 __global__ void k_scale(const double* __restrict__ in, const double* __restrict__ npass, int64_t n, double* __restrict__ out) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = in[i] / npass[0];
@@ -691,6 +697,7 @@ struct ppm_ctx {
   cudaEvent_t ev[EV_COUNT] = {nullptr};
   bool timed = false;             // record the phase events (render_pass only)
   uint64_t launches = 0;
+  ppm_ctx* twin = nullptr;        // second lane on the same GPU (ppm_render_passes), owned
 };
 
 namespace {
@@ -1104,6 +1111,7 @@ int ppm_create(int device, ppm_ctx** out) {
 
 void ppm_destroy(ppm_ctx* c) {
   if (!c) return;
+  if (c->twin) { ppm_destroy(c->twin); c->twin = nullptr; }
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   DBuf* all[] = {&c->r_pos, &c->r_dir, &c->r_wl, &c->r_tag, &c->counter, &c->keys, &c->keys2, &c->vals, &c->vals2, &c->cub_tmp,
@@ -1426,6 +1434,69 @@ int ppm_render_pass(ppm_ctx* c, uint64_t seed, uint32_t pass, int64_t nphoton, d
   for (int i = 0; i < c->scene.nlights; ++i) emitted += ns[i];
   c->counters[0] = (uint64_t)emitted; c->counters[1] = c->n_rec; c->counters[2] = st[0];
   c->counters[4] = st[1]; c->counters[5] = c->launches - l0;
+  return PPM_OK;
+}
+
+// A batch of passes with cross-pass overlap.  Passes are independent, and within one pass the
+// FP64-bound kernels (direct light, gather) and the latency-bound ones (photon tracing, eye-path
+// expansion, map build) cannot fill the GPU together.  Two lanes -- this context and an internal
+// twin on the same GPU, each with its own streams and buffers, each driven by its own host
+// thread -- render alternating passes so that different phases of two passes co-schedule.  The
+// twin's accumulator is merged afterwards, so ppm_accum_read / ppm_image_mean see every pass.
+int ppm_render_passes(ppm_ctx* c, uint64_t seed, uint32_t first_pass, uint32_t pass_stride, int32_t npass, int64_t nphoton,
+                      const double* radius2, int uc) {
+  if (!c) return PPM_ERR_ARG;
+  if (npass < 0 || (npass > 0 && !radius2)) return fail(c, PPM_ERR_ARG, "bad pass batch");
+  if (npass == 0) return PPM_OK;
+  if (!c->have_scene || !c->have_camera) return fail(c, PPM_ERR_STATE, "scene and camera must be set");
+  const char* lanes_env = std::getenv("PPM_LANES");
+  const bool two = npass >= 2 && !(lanes_env && lanes_env[0] == '1');
+  double ms_sum[8] = {0}; uint64_t ct_sum[8] = {0};
+  auto add_stats = [&](ppm_ctx* x) { for (int k = 0; k < 8; ++k) { ms_sum[k] += x->ms[k]; ct_sum[k] += x->counters[k]; } };
+  if (!two) {
+    for (int32_t i = 0; i < npass; ++i) {
+      int rc = ppm_render_pass(c, seed, first_pass + (uint32_t)i * pass_stride, nphoton, radius2[i], uc);
+      if (rc) return rc;
+      add_stats(c);
+    }
+  } else {
+    if (!c->twin) {
+      int rc = ppm_create(c->device, &c->twin);
+      if (rc) return fail(c, rc, "cannot create the second lane");
+    }
+    ppm_ctx* t = c->twin;
+    t->scene = c->scene; t->have_scene = true; t->cam = c->cam; t->have_camera = true;
+    int rc_twin = PPM_OK, rc_main = PPM_OK;
+    double tms[8] = {0}; uint64_t tct[8] = {0};
+    std::thread worker([&]() {
+      cudaSetDevice(t->device);
+      for (int32_t i = 1; i < npass; i += 2) {
+        rc_twin = ppm_render_pass(t, seed, first_pass + (uint32_t)i * pass_stride, nphoton, radius2[i], uc);
+        if (rc_twin) return;
+        for (int k = 0; k < 8; ++k) { tms[k] += t->ms[k]; tct[k] += t->counters[k]; }
+      }
+    });
+    for (int32_t i = 0; i < npass; i += 2) {
+      rc_main = ppm_render_pass(c, seed, first_pass + (uint32_t)i * pass_stride, nphoton, radius2[i], uc);
+      if (rc_main) break;
+      add_stats(c);
+    }
+    worker.join();
+    if (rc_main) return rc_main;
+    if (rc_twin) return fail(c, rc_twin, std::string("second lane: ") + t->err);
+    for (int k = 0; k < 8; ++k) { ms_sum[k] += tms[k]; ct_sum[k] += tct[k]; }
+    // merge the twin's accumulator (and pass counter) into ours; last pass image follows the last pass
+    CK(c, cudaSetDevice(c->device));
+    const int64_t nacc = (int64_t)c->accum_pixels * 3 + 1;
+    CK(c, cudaStreamSynchronize(t->stream));
+    k_accum_merge<<<nblk(nacc, 256), 256, 0, c->stream>>>(c->accum.as<double>(), t->accum.as<double>(), nacc);
+    KCHECK(c);
+    if (((npass - 1) & 1) == 1)
+      CK(c, cudaMemcpyAsync(c->pass_img.p, t->pass_img.p, (size_t)c->accum_pixels * 24, cudaMemcpyDeviceToDevice, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+  }
+  std::memcpy(c->ms, ms_sum, sizeof ms_sum);          // batch totals (sum over the passes of both lanes)
+  std::memcpy(c->counters, ct_sum, sizeof ct_sum);
   return PPM_OK;
 }
 

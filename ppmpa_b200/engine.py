@@ -274,6 +274,11 @@ class Engine:
         """One PPM-PA pass (ppmpa.rs:74-84), accumulated on the device."""
         self._ck(lib.ppm_render_pass(self._h, seed, npass, int(nphoton), float(radius2), 1 if uc else 0))
 
+    def iterate(self, seed, first_pass, npass, nphoton, radius2_list, uc=True, pass_stride=1):
+        """A batch of passes (the loop of util/iterator.rb:96-117) with cross-pass overlap."""
+        r2 = (C.c_double * npass)(*[float(x) for x in radius2_list])
+        self._ck(lib.ppm_render_passes(self._h, seed, int(first_pass), int(pass_stride), int(npass), int(nphoton), r2, 1 if uc else 0))
+
     def pass_image(self, out=None):
         if out is None:
             out = np.empty((self.npixels, 3))

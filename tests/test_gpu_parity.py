@@ -400,3 +400,32 @@ def test_two_contexts_are_independent():
         assert ha.max() > 12 and hb.max() <= 12
     finally:
         a.close(); b.close()
+
+
+def test_render_passes_two_lanes_equal_sequential(engine):
+    """ppm_render_passes (two lanes on one GPU) == the same passes rendered one by one."""
+    sc = load_scene("ex-glassbox")
+    cam = P.read_camera(os.path.join(EX, "camera0.scr"), xreso=64, yreso=64, pfilter=K.FILTER_NONE, progressive=1)
+    engine.set_scene(sc); engine.set_camera(cam)
+    radii = P.radius_schedule(0.2, 5)
+    engine.accum_reset()
+    imgs = []
+    for p in range(5):
+        engine.iteration(SEED, 10 + 2 * p, 20000, radii[p] ** 2, uc=True)
+        imgs.append(engine.pass_image())
+    engine.accum_reset()
+    engine.iterate(SEED, 10, 5, 20000, radii ** 2, uc=True, pass_stride=2)
+    acc, n = engine.accum_read()
+    assert n == 5
+    assert np.array_equal(engine.pass_image(), imgs[4])                    # last pass of the batch
+    lane0 = (imgs[0] + imgs[2]) + imgs[4]
+    lane1 = imgs[1] + imgs[3]
+    assert np.array_equal(acc, lane0 + lane1)                              # per-lane sums, then merged
+    ms, ct = engine.last_pass_stats()
+    assert ct["emitted"] == 5 * 20000 and ct["launches"] >= 5 * 10
+    # odd batch sizes / single pass / empty batch
+    engine.accum_reset()
+    engine.iterate(SEED, 10, 1, 20000, radii[:1] ** 2)
+    assert np.array_equal(engine.pass_image(), imgs[0])
+    engine.iterate(SEED, 10, 0, 20000, [])
+    assert engine.accum_read()[1] == 1
