@@ -246,6 +246,16 @@ int  ppm_within(ppm_ctx* ctx, const double* q3_h_or_d, int64_t nq,
 int  ppm_gather(ppm_ctx* ctx, const double* pos3_h_or_d, const double* nrm3_h_or_d,
                 int64_t n, int filter, double* rgb3_h_or_d, uint32_t* counts_h_or_d);
 
+/* -- k-NN radiance estimate (config 4's sweep).  The reference only plumbs n_sample_photon
+ *    (photonmap.rs:18, camera.rs:181) and never reads it, so there is NO reference
+ *    implementation; semantics follow SURVEY.md 8c: the k nearest photons within r; if k are
+ *    found, r_k^2 (the k-th smallest squared distance, returned in r2k, exact) replaces r^2 in
+ *    the membership test (ties included), the filter and the 1/(pi r^2) normaliser; otherwise
+ *    the fixed radius is used (r2k = r^2).  counts = photons used. */
+int  ppm_gather_knn(ppm_ctx* ctx, const double* pos3_h_or_d, const double* nrm3_h_or_d,
+                    int64_t n, uint32_t k, int filter, double* rgb3_h_or_d,
+                    double* r2k_h_or_d, uint32_t* counts_h_or_d);
+
 /* -- Camera::generate_ray, camera.rs:58-75 for every (y,x) of screen_map
  *    (row-major, y outer).  rays6[yreso*xreso][6]. */
 int  ppm_generate_rays(ppm_ctx* ctx, uint64_t seed, uint32_t pass,

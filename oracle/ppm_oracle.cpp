@@ -1136,6 +1136,33 @@ void orc_gather(void* map, const double* pos3, const double* nrm3, int64_t n, in
   for (auto& x : th) x.join();
 }
 
+// k-NN estimate.  NO REFERENCE IMPLEMENTATION EXISTS (n_sample_photon is dead code, photonmap.rs:18,
+// camera.rs:181); this is the brute-force statement of the semantics defined in SURVEY.md 8c /
+// include/ppm.h: k nearest within r; r_k^2 = k-th smallest d2 replaces r^2 (ties included); fewer
+// than k (or r_k^2 == 0) -> fixed radius.
+void orc_gather_knn(void* map, const double* pos3, const double* nrm3, int64_t n, uint32_t k, int filter, double* rgb3,
+                    double* r2k, uint32_t* counts) {
+  const PhotonMap* m = (const PhotonMap*)map;
+  std::vector<std::pair<Flt, uint32_t>> nb;
+  for (int64_t i = 0; i < n; ++i) {
+    V3 q = mk(pos3[i * 3], pos3[i * 3 + 1], pos3[i * 3 + 2]), nv = mk(nrm3[i * 3], nrm3[i * 3 + 1], nrm3[i * 3 + 2]);
+    m->within(q, nb);
+    Flt rk = m->radius;
+    if (nb.size() >= k && nb[k - 1].first > 0.0) rk = nb[k - 1].first;
+    Rad rad = RAD0;
+    uint32_t used = 0;
+    for (size_t j = 0; j < nb.size() && nb[j].first <= rk; ++j, ++used) {
+      Flt d = nb[j].first;
+      Flt wt = filter == PPM_FILTER_NONE ? 1.0 : (filter == PPM_FILTER_CONE ? filter_cone(d, rk) : filter_gauss(d, rk));
+      rad = radd(rad, photon_to_radiance(nv, wt * m->power, m->phs[nb[j].second]));
+    }
+    rad = rmul(rad, ONE_PI / rk);
+    rgb3[i * 3] = rad.c[0]; rgb3[i * 3 + 1] = rad.c[1]; rgb3[i * 3 + 2] = rad.c[2];
+    if (r2k) r2k[i] = rk;
+    if (counts) counts[i] = used;
+  }
+}
+
 // ---- camera rays + trace_ray --------------------------------------------------
 void orc_generate_rays(const ppm_camera* cam, uint64_t seed, uint32_t pass, double* rays6) {
   for (int y = 0; y < cam->yreso; ++y)

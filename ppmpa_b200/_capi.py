@@ -109,6 +109,7 @@ SIGNATURES = {
     "ppm_map_build": (C.c_int, [vp, dbl]),
     "ppm_within": (C.c_int, [vp, vp, i64, vp, vp, u32]),
     "ppm_gather": (C.c_int, [vp, vp, vp, i64, C.c_int, vp, vp]),
+    "ppm_gather_knn": (C.c_int, [vp, vp, vp, i64, u32, C.c_int, vp, vp, vp]),
     "ppm_generate_rays": (C.c_int, [vp, u64, u32, vp]),
     "ppm_trace_rays": (C.c_int, [vp, vp, i64, i64, u64, u32, C.c_int, vp]),
     "ppm_trace_rays_classic": (C.c_int, [vp, vp, i64, i64, u64, u32, vp]),

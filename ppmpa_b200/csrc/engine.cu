@@ -169,7 +169,6 @@ struct Grid {
   double inv_cell;
   int32_t nx, ny, nz;
   uint32_t ncells;
-  int32_t reach;      // cell edge >= r / reach: neighbours are within +-reach cells on every axis
 };
 __device__ __forceinline__ unsigned long long enc_ord(double v) {
   unsigned long long b = (unsigned long long)__double_as_longlong(v);
@@ -292,12 +291,16 @@ __global__ void k_query_key(Grid g, const double* __restrict__ qpos3, int64_t n,
 // per-lane loop lengths, no scattered global loads.
 #define GATHER_WARPS 4
 #define GATHER_SPAN 3        // a group may span cells cx .. cx+3 of one row
-template <int FILTER, int REACH>
+// MODE 0: fixed radius r2 (estimate_radiance).  MODE 1: per-query squared radius r2q[] (k-NN estimate:
+// membership, filter rmax and normaliser all use the query's own radius).  MODE 2: count only,
+// members are d2 <= r2q[] (the bisection steps of the k-NN radius search).
+template <int FILTER, int MODE>
 __global__ void __launch_bounds__(GATHER_WARPS * 32)
 k_gather(Grid g, const uint32_t* __restrict__ cell_start, MapSoA m, const uint32_t* __restrict__ qkey,
          const uint32_t* __restrict__ qidx, const double* __restrict__ qpos3, const double* __restrict__ qnrm3, int64_t n,
-         double power, double r2, double* __restrict__ rgb3, uint32_t* __restrict__ counts,
+         double power, double r2_fixed, const double* __restrict__ r2q, double* __restrict__ rgb3, uint32_t* __restrict__ counts,
          unsigned long long* __restrict__ sum_k) {
+  constexpr int REACH = 1;
   __shared__ double2 sP[GATHER_WARPS][32][2];
   __shared__ double2 sD[GATHER_WARPS][32][2];
   __shared__ uint32_t sEnd[GATHER_WARPS][32], sOff[GATHER_WARPS][32];   // per run: cumulative end, start - exclusive prefix
@@ -311,9 +314,11 @@ k_gather(Grid g, const uint32_t* __restrict__ cell_start, MapSoA m, const uint32
   const uint32_t qi = valid ? qidx[s] : 0u;
   double qx = 0.0, qy = 0.0, qz = 0.0;
   D3 nv = mk3(0.0, 0.0, 0.0);
+  double r2 = r2_fixed;
   if (valid) {
     qx = qpos3[(uint64_t)qi * 3]; qy = qpos3[(uint64_t)qi * 3 + 1]; qz = qpos3[(uint64_t)qi * 3 + 2];
-    nv = ld3(qnrm3 + (uint64_t)qi * 3);
+    if (MODE != 2) nv = ld3(qnrm3 + (uint64_t)qi * 3);
+    if (MODE != 0) r2 = r2q[qi];
   }
   double rr = 0.0, rg = 0.0, rb = 0.0;
   uint32_t cnt = 0;
@@ -363,7 +368,7 @@ k_gather(Grid g, const uint32_t* __restrict__ cell_start, MapSoA m, const uint32
         const uint32_t o = sOff[warp][run];
         const uint64_t j = (uint64_t)(v + o) * 2;
         sP[warp][lane][0] = m.P[j]; sP[warp][lane][1] = m.P[j + 1];
-        sD[warp][lane][0] = m.D[j]; sD[warp][lane][1] = m.D[j + 1];
+        if (MODE != 2) { sD[warp][lane][0] = m.D[j]; sD[warp][lane][1] = m.D[j + 1]; }
       }
       __syncwarp();
       const int mcount = (int)min(32u, total - base);
@@ -375,6 +380,7 @@ k_gather(Grid g, const uint32_t* __restrict__ cell_start, MapSoA m, const uint32
           const double d2 = (ax * ax + ay * ay) + az * az;
           if (d2 <= r2) {
             ++cnt;
+            if (MODE == 2) continue;
             const double wt = FILTER == PPM_FILTER_NONE ? 1.0 : (FILTER == PPM_FILTER_CONE ? filter_cone(d2, r2) : filter_gauss(d2, r2));
             const double2 c = sD[warp][t][0], d = sD[warp][t][1];
             // photon_to_radiance, optics.rs:224-233
@@ -389,8 +395,10 @@ k_gather(Grid g, const uint32_t* __restrict__ cell_start, MapSoA m, const uint32
     }
   }
   if (valid) {
-    const double sc = (1.0 / PPM_PI) / r2;            // rad * (ONE_PI / radius), tracer.rs:193
-    rgb3[(uint64_t)qi * 3] = rr * sc; rgb3[(uint64_t)qi * 3 + 1] = rg * sc; rgb3[(uint64_t)qi * 3 + 2] = rb * sc;
+    if (MODE != 2) {
+      const double sc = (1.0 / PPM_PI) / r2;          // rad * (ONE_PI / radius), tracer.rs:193
+      rgb3[(uint64_t)qi * 3] = rr * sc; rgb3[(uint64_t)qi * 3 + 1] = rg * sc; rgb3[(uint64_t)qi * 3 + 2] = rb * sc;
+    }
     if (counts) counts[qi] = cnt;
   }
   if (sum_k) {
@@ -400,6 +408,37 @@ k_gather(Grid g, const uint32_t* __restrict__ cell_start, MapSoA m, const uint32
   }
 }
 
+// ---- k-NN radius search: exact k-th smallest d2 per query by bisection on the bit pattern of d2 --------
+// (non-negative doubles order like their bit patterns).  State per query: [lo, hi] as uint64 bits,
+// hi always satisfies count(d2 <= hi) >= k.  done[] = 1 when fewer than k photons lie within r (fixed radius).
+__global__ void k_knn_init(int64_t n, double r2, const uint32_t* __restrict__ cnt, uint32_t k, unsigned long long* __restrict__ lo,
+                           unsigned long long* __restrict__ hi, double* __restrict__ thr, unsigned int* __restrict__ n_active) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned long long rb = (unsigned long long)__double_as_longlong(r2);
+  if (cnt[i] < k) { lo[i] = hi[i] = rb; thr[i] = r2; return; }        // fewer than k within r: fixed radius
+  lo[i] = 0ull; hi[i] = rb;
+  thr[i] = __longlong_as_double((long long)(rb >> 1));
+  atomicAdd(n_active, 1u);
+}
+__global__ void k_knn_step(int64_t n, const uint32_t* __restrict__ cnt, uint32_t k, unsigned long long* __restrict__ lo,
+                           unsigned long long* __restrict__ hi, double* __restrict__ thr, unsigned int* __restrict__ n_active) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  unsigned long long l = lo[i], h = hi[i];
+  if (l >= h) return;
+  const unsigned long long mid = l + ((h - l) >> 1);                   // thr[i] was asdouble(mid)
+  if (cnt[i] >= k) h = mid; else l = mid + 1;
+  lo[i] = l; hi[i] = h;
+  if (l < h) { thr[i] = __longlong_as_double((long long)(l + ((h - l) >> 1))); atomicAdd(n_active, 1u); }
+  else thr[i] = __longlong_as_double((long long)h);
+}
+// a k-th distance of exactly zero (k coincident photons at the query) cannot normalise: fall back to r2
+__global__ void k_knn_finish(int64_t n, double r2, double* __restrict__ thr) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && !(thr[i] > 0.0)) thr[i] = r2;
+}
+
 __global__ void k_within(Grid g, const uint32_t* __restrict__ cell_start, MapSoA m, const double* __restrict__ qpos3,
                          int64_t n, double r2, uint32_t* __restrict__ idx, uint32_t* __restrict__ counts, uint32_t cap) {
   int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -407,7 +446,7 @@ __global__ void k_within(Grid g, const uint32_t* __restrict__ cell_start, MapSoA
   const double qx = qpos3[q * 3], qy = qpos3[q * 3 + 1], qz = qpos3[q * 3 + 2];
   uint32_t cnt = 0;
   int cx = cell_coord(g, qx, 0), cy = cell_coord(g, qy, 1), cz = cell_coord(g, qz, 2);
-  const int R = g.reach;
+  const int R = 1;
   int x0 = max(cx - R, 0), x1 = min(cx + R, g.nx - 1);
   if (x0 <= x1)
     for (int z = max(cz - R, 0); z <= min(cz + R, g.nz - 1); ++z)
@@ -677,6 +716,7 @@ struct ppm_ctx {
   DBuf keys, keys2, vals, vals2, cub_tmp, cell_start, hist, bbox, axis_hist;
   DBuf m_P, m_D, m_orig;
   DBuf q_key, q_key2, q_idx, q_idx2;
+  DBuf knn_lo, knn_hi, knn_thr, knn_cnt;
   Grid grid;
   double r2 = 0.0;
   // staging for h_or_d arguments
@@ -838,7 +878,7 @@ int do_map_build(ppm_ctx* c, double radius2) {
   Grid g;
   std::memset(&g, 0, sizeof g);
   double cell = std::sqrt(radius2) * (1.0 + 1.0 / 1024.0);   // edge slightly > r: the 27-cell walk can never miss
-  g.nx = g.ny = g.nz = 1; g.inv_cell = 1.0 / cell; g.ncells = 1; g.reach = 1;
+  g.nx = g.ny = g.nz = 1; g.inv_cell = 1.0 / cell; g.ncells = 1;
   if (n > 0) {
     CK(c, c->bbox.ensure(48));
     unsigned long long init[6] = {~0ull, ~0ull, ~0ull, 0ull, 0ull, 0ull};
@@ -901,14 +941,6 @@ int do_map_build(ppm_ctx* c, double radius2) {
     // walls) then sit mid-cell, so the +-1 ulp noise of hit points on such a plane cannot
     // straddle a cell boundary (which would split every warp of queries on that wall).
     const double CELL_CAP = 67108864.0;   // 2^26 cells
-    {
-      // Half-size cells (reach 2: 25 runs of 5 cells, candidate area 6.25 r^2 instead of 9 r^2) while
-      // the cell table stays small (<= 2^23 cells); otherwise cells of edge r (reach 1).
-      const char* force = std::getenv("PPM_GATHER_REACH");
-      double half = 0.5 * cell, prod = 1.0;
-      for (int k = 0; k < 3; ++k) prod *= std::floor((hi[k] - (lo[k] - 0.5 * half)) / half) + 2.0;
-      if (prod <= 8388608.0 && force && force[0] == '2') { cell = half; g.reach = 2; }   // opt-in: measured slower (fewer queries per cell)
-    }
     for (;;) {
       double dims[3];
       for (int k = 0; k < 3; ++k) dims[k] = std::floor((hi[k] - (lo[k] - 0.5 * cell)) / cell) + 2.0;
@@ -916,7 +948,7 @@ int do_map_build(ppm_ctx* c, double radius2) {
         g.nx = (int32_t)dims[0]; g.ny = (int32_t)dims[1]; g.nz = (int32_t)dims[2];
         break;
       }
-      cell *= 2.0; g.reach = 1;
+      cell *= 2.0;
     }
     for (int k = 0; k < 3; ++k) g.org[k] = lo[k] - 0.5 * cell;
     g.inv_cell = 1.0 / cell;
@@ -968,12 +1000,9 @@ int do_map_build(ppm_ctx* c, double radius2) {
   return PPM_OK;
 }
 
-int launch_gather(ppm_ctx* c, const double* dpos, const double* dnrm, int64_t n, int filter, double* drgb, uint32_t* dcounts,
-                  unsigned long long* dsumk) {
-  if (n <= 0) return PPM_OK;
+// key the queries by cell and sort them (stable: ties keep query order -> deterministic)
+int gather_sort_queries(ppm_ctx* c, const double* dpos, int64_t n) {
   if (n >= (1ll << 32)) return fail(c, PPM_ERR_CAPACITY, "at most 2^32-1 gather queries per call");
-  if (filter < PPM_FILTER_NONE || filter > PPM_FILTER_GAUSS) return fail(c, PPM_ERR_ARG, "bad filter");
-  // 1. key the queries by cell and sort them (stable: ties keep query order -> deterministic)
   CK(c, c->q_key.ensure((size_t)n * 4)); CK(c, c->q_key2.ensure((size_t)n * 4));
   CK(c, c->q_idx.ensure((size_t)n * 4)); CK(c, c->q_idx2.ensure((size_t)n * 4));
   k_query_key<<<nblk(n, 256), 256, 0, c->stream>>>(c->grid, dpos, n, c->q_key.as<uint32_t>(), c->q_idx.as<uint32_t>());
@@ -987,21 +1016,79 @@ int launch_gather(ppm_ctx* c, const double* dpos, const double* dnrm, int64_t n,
   CK(c, c->cub_tmp.ensure(tmp));
   CK(c, cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp, c->q_key.as<uint32_t>(), c->q_key2.as<uint32_t>(), c->q_idx.as<uint32_t>(),
                                         c->q_idx2.as<uint32_t>(), n, 0, bits, c->stream));
-  // 2. warp-cooperative gather over the sorted queries
-  if (c->timed) cudaEventRecord(c->ev[ppm_ctx::EV_A4], c->stream);
+  return PPM_OK;
+}
+// warp-cooperative gather over the sorted queries; mode 0 fixed radius, 1 per-query radius, 2 count only
+int gather_launch(ppm_ctx* c, const double* dpos, const double* dnrm, int64_t n, int filter, int mode, const double* r2q,
+                  double* drgb, uint32_t* dcounts, unsigned long long* dsumk) {
   const int B = GATHER_WARPS * 32;
   const uint32_t* cs = c->cell_start.as<uint32_t>();
   const uint32_t* qk = c->q_key2.as<uint32_t>();
   const uint32_t* qx = c->q_idx2.as<uint32_t>();
-#define GATHER_LAUNCH(F, R) k_gather<F, R><<<nblk(n, B), B, 0, c->stream>>>(c->grid, cs, mapsoa(c), qk, qx, dpos, dnrm, n, c->power, c->r2, drgb, dcounts, dsumk)
-  const bool r2x = c->grid.reach == 2;
-  switch (filter) {
-    case PPM_FILTER_NONE: if (r2x) GATHER_LAUNCH(PPM_FILTER_NONE, 2); else GATHER_LAUNCH(PPM_FILTER_NONE, 1); break;
-    case PPM_FILTER_CONE: if (r2x) GATHER_LAUNCH(PPM_FILTER_CONE, 2); else GATHER_LAUNCH(PPM_FILTER_CONE, 1); break;
-    default:              if (r2x) GATHER_LAUNCH(PPM_FILTER_GAUSS, 2); else GATHER_LAUNCH(PPM_FILTER_GAUSS, 1); break;
+#define GATHER_LAUNCH(F, M) k_gather<F, M><<<nblk(n, B), B, 0, c->stream>>>(c->grid, cs, mapsoa(c), qk, qx, dpos, dnrm, n, c->power, c->r2, r2q, drgb, dcounts, dsumk)
+  if (mode == 2) GATHER_LAUNCH(PPM_FILTER_NONE, 2);
+  else if (mode == 1) {
+    switch (filter) {
+      case PPM_FILTER_NONE: GATHER_LAUNCH(PPM_FILTER_NONE, 1); break;
+      case PPM_FILTER_CONE: GATHER_LAUNCH(PPM_FILTER_CONE, 1); break;
+      default:              GATHER_LAUNCH(PPM_FILTER_GAUSS, 1); break;
+    }
+  } else {
+    switch (filter) {
+      case PPM_FILTER_NONE: GATHER_LAUNCH(PPM_FILTER_NONE, 0); break;
+      case PPM_FILTER_CONE: GATHER_LAUNCH(PPM_FILTER_CONE, 0); break;
+      default:              GATHER_LAUNCH(PPM_FILTER_GAUSS, 0); break;
+    }
   }
 #undef GATHER_LAUNCH
   KCHECK(c);
+  return PPM_OK;
+}
+int launch_gather(ppm_ctx* c, const double* dpos, const double* dnrm, int64_t n, int filter, double* drgb, uint32_t* dcounts,
+                  unsigned long long* dsumk) {
+  if (n <= 0) return PPM_OK;
+  if (filter < PPM_FILTER_NONE || filter > PPM_FILTER_GAUSS) return fail(c, PPM_ERR_ARG, "bad filter");
+  int rc = gather_sort_queries(c, dpos, n);
+  if (rc) return rc;
+  if (c->timed) cudaEventRecord(c->ev[ppm_ctx::EV_A4], c->stream);
+  return gather_launch(c, dpos, dnrm, n, filter, 0, nullptr, drgb, dcounts, dsumk);
+}
+// k-NN estimate (no reference implementation exists: n_sample_photon is dead code, photonmap.rs:18,
+// camera.rs:181; semantics defined in SURVEY.md 8c): for every query the k nearest photons within r;
+// if k are found, r_k^2 = the k-th smallest d2 replaces r^2 in the membership test, the filter and the
+// normaliser; otherwise the fixed radius is used.  r_k^2 is found EXACTLY by bisection on the bit
+// pattern of d2 with the count-only gather (<= 63 steps).
+int launch_gather_knn(ppm_ctx* c, const double* dpos, const double* dnrm, int64_t n, uint32_t k, int filter, double* drgb,
+                      double* dr2k, uint32_t* dcounts) {
+  if (n <= 0) return PPM_OK;
+  int rc = gather_sort_queries(c, dpos, n);
+  if (rc) return rc;
+  CK(c, c->knn_lo.ensure((size_t)n * 8)); CK(c, c->knn_hi.ensure((size_t)n * 8)); CK(c, c->knn_thr.ensure((size_t)n * 8));
+  CK(c, c->knn_cnt.ensure((size_t)n * 4)); CK(c, c->counter.ensure(64));
+  unsigned long long* lo = c->knn_lo.as<unsigned long long>();
+  unsigned long long* hi = c->knn_hi.as<unsigned long long>();
+  double* thr = c->knn_thr.as<double>();
+  uint32_t* cnt = c->knn_cnt.as<uint32_t>();
+  unsigned int* nact = c->counter.as<unsigned int>() + 8;
+  // photons within the fixed radius
+  if ((rc = gather_launch(c, dpos, dnrm, n, PPM_FILTER_NONE, 0, nullptr, drgb, cnt, nullptr))) return rc;
+  CK(c, cudaMemsetAsync(nact, 0, 4, c->stream));
+  k_knn_init<<<nblk(n, 256), 256, 0, c->stream>>>(n, c->r2, cnt, k, lo, hi, thr, nact);
+  KCHECK(c);
+  for (int it = 0; it < 70; ++it) {
+    unsigned int active = 0;
+    CK(c, cudaMemcpyAsync(&active, nact, 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    if (!active) break;
+    if ((rc = gather_launch(c, dpos, dnrm, n, PPM_FILTER_NONE, 2, thr, nullptr, cnt, nullptr))) return rc;
+    CK(c, cudaMemsetAsync(nact, 0, 4, c->stream));
+    k_knn_step<<<nblk(n, 256), 256, 0, c->stream>>>(n, cnt, k, lo, hi, thr, nact);
+    KCHECK(c);
+  }
+  k_knn_finish<<<nblk(n, 256), 256, 0, c->stream>>>(n, c->r2, thr);
+  KCHECK(c);
+  if ((rc = gather_launch(c, dpos, dnrm, n, filter, 1, thr, drgb, dcounts, nullptr))) return rc;
+  if (dr2k) CK(c, cudaMemcpyAsync(dr2k, thr, (size_t)n * 8, cudaMemcpyDeviceToDevice, c->stream));
   return PPM_OK;
 }
 
@@ -1115,7 +1202,7 @@ void ppm_destroy(ppm_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   DBuf* all[] = {&c->r_pos, &c->r_dir, &c->r_wl, &c->r_tag, &c->counter, &c->keys, &c->keys2, &c->vals, &c->vals2, &c->cub_tmp,
-                 &c->cell_start, &c->hist, &c->bbox, &c->axis_hist, &c->m_P, &c->m_D, &c->m_orig, &c->q_key, &c->q_key2, &c->q_idx, &c->q_idx2,
+                 &c->cell_start, &c->hist, &c->bbox, &c->axis_hist, &c->m_P, &c->m_D, &c->m_orig, &c->q_key, &c->q_key2, &c->q_idx, &c->q_idx2, &c->knn_lo, &c->knn_hi, &c->knn_thr, &c->knn_cnt,
                  &c->st_in0, &c->st_in1, &c->st_out0, &c->st_out1, &c->st_out2, &c->st_out3, &c->st_out4,
                  &c->e_head, &c->e_prev, &c->e_pos, &c->e_nrm, &c->e_w, &c->e_emit, &c->e_direct, &c->e_photon, &c->e_rays,
                  &c->pass_img, &c->accum, &c->npass, &c->stats, &c->cub_tmp2};
@@ -1312,6 +1399,28 @@ int ppm_gather(ppm_ctx* c, const double* pos3, const double* nrm3, int64_t n, in
   if ((rc = stage_out(c, counts, (size_t)n * 4, c->st_out1, &dc))) return rc;
   if ((rc = launch_gather(c, (const double*)dp, (const double*)dn, n, filter, (double*)dr, (uint32_t*)dc, nullptr))) return rc;
   if ((rc = finish_out(c, rgb3, (size_t)n * 24, dr))) return rc;
+  if ((rc = finish_out(c, counts, (size_t)n * 4, dc))) return rc;
+  CK(c, cudaStreamSynchronize(c->stream));
+  return PPM_OK;
+}
+
+int ppm_gather_knn(ppm_ctx* c, const double* pos3, const double* nrm3, int64_t n, uint32_t k, int filter, double* rgb3,
+                   double* r2k, uint32_t* counts) {
+  if (!c) return PPM_ERR_ARG;
+  if (!c->have_map) return fail(c, PPM_ERR_STATE, "photon map not built");
+  if (n < 0 || k == 0 || (n > 0 && (!pos3 || !nrm3 || !rgb3))) return fail(c, PPM_ERR_ARG, "null argument or k == 0");
+  if (filter < PPM_FILTER_NONE || filter > PPM_FILTER_GAUSS) return fail(c, PPM_ERR_ARG, "bad filter");
+  if (n == 0) return PPM_OK;
+  CK(c, cudaSetDevice(c->device));
+  const void *dp, *dn; void *dr, *dk, *dc; int rc;
+  if ((rc = stage_in(c, pos3, (size_t)n * 24, c->st_in0, &dp))) return rc;
+  if ((rc = stage_in(c, nrm3, (size_t)n * 24, c->st_in1, &dn))) return rc;
+  if ((rc = stage_out(c, rgb3, (size_t)n * 24, c->st_out0, &dr))) return rc;
+  if ((rc = stage_out(c, r2k, (size_t)n * 8, c->st_out1, &dk))) return rc;
+  if ((rc = stage_out(c, counts, (size_t)n * 4, c->st_out2, &dc))) return rc;
+  if ((rc = launch_gather_knn(c, (const double*)dp, (const double*)dn, n, k, filter, (double*)dr, (double*)dk, (uint32_t*)dc))) return rc;
+  if ((rc = finish_out(c, rgb3, (size_t)n * 24, dr))) return rc;
+  if ((rc = finish_out(c, r2k, (size_t)n * 8, dk))) return rc;
   if ((rc = finish_out(c, counts, (size_t)n * 4, dc))) return rc;
   CK(c, cudaStreamSynchronize(c->stream));
   return PPM_OK;

@@ -249,6 +249,14 @@ class Engine:
         self._ck(lib.ppm_gather(self._h, _ptr(pos3), _ptr(nrm3), n, pfilter, _ptr(out), _ptr(counts)))
         return out, counts
 
+    def estimate_radiance_knn(self, pos3, nrm3, k, pfilter=K.FILTER_NONE):
+        """k-NN estimate (no reference implementation; semantics in include/ppm.h)."""
+        pos3 = _f64(pos3, (3,)); nrm3 = _f64(nrm3, (3,))
+        n = pos3.shape[0]
+        out = np.empty((n, 3)); r2k = np.empty(n); counts = np.empty(n, np.uint32)
+        self._ck(lib.ppm_gather_knn(self._h, _ptr(pos3), _ptr(nrm3), n, int(k), pfilter, _ptr(out), _ptr(r2k), _ptr(counts)))
+        return out, r2k, counts
+
     def generate_rays(self, seed, npass):
         out = np.empty((self.npixels, 6))
         self._ck(lib.ppm_generate_rays(self._h, seed, npass, _ptr(out)))

@@ -68,6 +68,7 @@ def load():
         "orc_map_free": (None, [vp]),
         "orc_within": (u32, [vp, D3, C.c_int, vp, vp, u32]),
         "orc_gather": (None, [vp, vp, vp, i64, C.c_int, vp, vp, C.c_int]),
+        "orc_gather_knn": (None, [vp, vp, vp, i64, u32, C.c_int, vp, vp, vp]),
         "orc_generate_rays": (None, [P(K.Camera), u64, u32, vp]),
         "orc_trace_rays": (None, [P(K.Prim), C.c_int, P(K.Material), C.c_int, P(K.Light), C.c_int, vp, C.c_int, vp, i64,
                                   i64, u64, u32, C.c_int, vp, C.c_int, vp]),
@@ -194,6 +195,13 @@ class OracleMap:
         idx = np.zeros(max(cap, 1), np.uint32); d2 = np.zeros(max(cap, 1))
         k = self.L.orc_within(self.h, d3(q), 1 if brute else 0, _p(idx), _p(d2), cap)
         return idx[:min(k, cap)].copy(), d2[:min(k, cap)].copy(), k
+
+    def gather_knn(self, pos3, nrm3, k, pfilter):
+        pos3 = np.ascontiguousarray(pos3, np.float64); nrm3 = np.ascontiguousarray(nrm3, np.float64)
+        n = len(pos3)
+        out = np.empty((n, 3)); r2k = np.empty(n); cnt = np.empty(n, np.uint32)
+        self.L.orc_gather_knn(self.h, _p(pos3), _p(nrm3), n, k, pfilter, _p(out), _p(r2k), _p(cnt))
+        return out, r2k, cnt
 
     def gather(self, pos3, nrm3, pfilter, nthreads=1):
         pos3 = np.ascontiguousarray(pos3, np.float64); nrm3 = np.ascontiguousarray(nrm3, np.float64)

@@ -429,3 +429,51 @@ def test_render_passes_two_lanes_equal_sequential(engine):
     assert np.array_equal(engine.pass_image(), imgs[0])
     engine.iterate(SEED, 10, 0, 20000, [])
     assert engine.accum_read()[1] == 1
+
+
+@pytest.mark.parametrize("pfilter", [K.FILTER_NONE, K.FILTER_CONE, K.FILTER_GAUSS])
+@pytest.mark.parametrize("k", [1, 10, 100, 500])
+def test_gather_knn_matches_bruteforce(engine, oracle, pfilter, k):
+    """k-NN estimate against the brute-force CPU statement (no reference implementation exists):
+    the k-th squared distance is found exactly, counts and radiance agree."""
+    ph, power = wall_photons(100000, seed=21)
+    r = 0.15
+    engine.import_photons(ph, power)
+    engine.build_photonmap(r * r)
+    m = oracle.map_build(ph, power, r * r)
+    q, nrm = query_points(ph, 1500, 22, r / 4)
+    q = np.concatenate([q, [[50.0, 50.0, 50.0]], ph["pos"][:5]])           # no neighbours / d2 == 0 neighbours
+    nrm = np.concatenate([nrm, [[0.0, 1.0, 0.0]] * 6])
+    g, gr, gc = engine.estimate_radiance_knn(q, nrm, k, pfilter)
+    o, orr, oc = m.gather_knn(q, nrm, k, pfilter)
+    assert np.array_equal(gr, orr)                                          # r_k^2 bit-exact
+    assert np.array_equal(gc, oc)
+    assert_rel(g, o, RTOL)
+    full = gc[:1500]
+    assert np.all(full[orr[:1500] < r * r] == k) and gc[1500] == 0 and gr[1500] == r * r
+
+
+def test_gather_knn_config4_sweep(engine):
+    """configs[3]: mirror-ball / coral-ball, fixed radius vs k-NN: with k photons found everywhere the
+    k-NN estimate has the same mean as the fixed-radius estimate to within Monte-Carlo noise, and a
+    huge k reproduces the fixed-radius estimate exactly."""
+    for name in ("mirror-ball", "coral-ball"):
+        sc = load_scene(name)
+        cam = P.read_camera(os.path.join(EX, "camera0.scr"), xreso=64, yreso=64, blur=0, antialias=0, progressive=1)
+        engine.set_scene(sc); engine.set_camera(cam)
+        power, ns = sc.photon_budget(200000)
+        engine.trace_photons(SEED, 0, False, ns, power)
+        rays = engine.generate_rays(SEED, 0)
+        hit, t, pos, nrm, io = engine.calc_intersection(rays)
+        pos, nrm = pos[hit >= 0], nrm[hit >= 0]
+        for r in (0.1, 0.2, 0.3):
+            engine.build_photonmap(r * r)
+            fixed, cnt = engine.estimate_radiance(pos, nrm, K.FILTER_NONE)
+            same, r2k, c2 = engine.estimate_radiance_knn(pos, nrm, 10 ** 7, K.FILTER_NONE)
+            assert np.array_equal(same, fixed) and np.array_equal(c2, cnt) and np.all(r2k == r * r)
+            for k in (100, 500):
+                knn, r2k, ck = engine.estimate_radiance_knn(pos, nrm, k, K.FILTER_NONE)
+                assert np.all(ck <= np.maximum(cnt, k)) and np.all(r2k <= r * r)
+                lit = cnt > 4 * k
+                if lit.sum() > 100:
+                    assert abs(knn[lit].mean() / fixed[lit].mean() - 1.0) < 0.15
