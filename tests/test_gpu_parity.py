@@ -477,3 +477,38 @@ def test_gather_knn_config4_sweep(engine):
                 lit = cnt > 4 * k
                 if lit.sum() > 100:
                     assert abs(knn[lit].mean() / fixed[lit].mean() - 1.0) < 0.15
+
+
+def test_converged_image_statistical_parity(engine, oracle):
+    """Third tier of the parity contract: with DIFFERENT random streams the averaged multi-pass image must
+    agree with the reference estimator statistically.  GPU passes use seed A, oracle passes seed B; the
+    per-pixel standard error comes from the oracle's own pass-to-pass variance (a bare RMSE is dominated by
+    a few firefly pixels -- light edges, caustic spikes -- that only one side happens to sample).
+    Stated bounds at 48x48, 24 passes x 40 k photons:
+      * per-pixel z-scores: mean |z| < 1.25 and fewer than 1 % beyond 5 sigma;
+      * no bias: total energy within 2 %, median per-pixel ratio within 0.5 %;
+      * trimmed relative RMSE (pixels with standard error < 5 % of their mean, largest 1 % of deviations
+        discarded) <= 10 %."""
+    sc = load_scene("ex-glassbox")
+    cam = P.read_camera(os.path.join(EX, "camera0.scr"), xreso=48, yreso=48, pfilter=K.FILTER_NONE, progressive=1)
+    engine.set_scene(sc); engine.set_camera(cam)
+    NP, NPH = 24, 40000
+    radii = P.radius_schedule(0.25, NP)
+    engine.accum_reset()
+    engine.iterate(0xA11CE, 0, NP, NPH, radii ** 2, uc=True)
+    g = engine.image_mean()
+    passes = np.stack([oracle.render_pass(sc, cam, 0xB0B, p, NPH, radii[p] ** 2, True)[0] for p in range(NP)])
+    o = passes.mean(0)
+    se = passes.std(0, ddof=1) / np.sqrt(NP)
+    lum_g, lum_o, lum_se = g.sum(1), o.sum(1), np.sqrt((se ** 2).sum(1))
+    ok = lum_se > 0
+    z = (lum_g[ok] - lum_o[ok]) / (lum_se[ok] * np.sqrt(2.0))      # both means carry the same variance
+    assert np.mean(np.abs(z)) < 1.25 and np.mean(np.abs(z) > 5) < 0.01, (np.mean(np.abs(z)), np.mean(np.abs(z) > 5))
+    assert abs(lum_g.mean() / lum_o.mean() - 1.0) < 0.02
+    smooth = ok & (lum_se < 0.05 * np.maximum(lum_o, 1e-300))
+    assert smooth.mean() > 0.5
+    assert abs(np.median(lum_g[smooth] / lum_o[smooth]) - 1.0) < 0.005
+    dev = np.sort(np.abs(lum_g[smooth] - lum_o[smooth]))
+    dev = dev[: int(len(dev) * 0.99)]
+    trimmed = np.sqrt(np.mean(dev ** 2)) / lum_o[smooth].mean()
+    assert trimmed <= 0.10, trimmed
