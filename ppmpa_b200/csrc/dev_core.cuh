@@ -134,22 +134,8 @@ __device__ __forceinline__ void consider_ratio(double num, double den, int o, do
   consider(num / den, o, best_t, best_o);
 }
 
-// geometry.rs:149-165 (u, v, t are computed before the rejection test)
-__device__ __forceinline__ bool moller(double l, D3 p0, D3 d1, D3 d2, D3 p, D3 d, double& t_out) {
-  D3 re2 = cross(d, d2);
-  double det_a = dot(re2, d1);
-  D3 pp = p - p0;
-  D3 te1 = cross(pp, d1);
-  double u = dot(re2, pp) / det_a;
-  double v = dot(te1, d) / det_a;
-  double t = dot(te1, d2) / det_a;
-  if (det_a == 0.0 || u < 0.0 || u > 1.0 || v < 0.0 || v > 1.0 || u + v > l) return false;
-  t_out = t;
-  return true;
-}
-
-// Polygon / parallelogram candidate for the nearest-hit scan: same decisions and the same t
-// as `if (moller(...)) consider(t)`, but the three divisions are only executed when a
+// Polygon / parallelogram candidate for the nearest-hit scan (method_moller, geometry.rs:149-165: u, v, t
+// are all computed before the rejection test): same decisions and the same t as the reference, but the three divisions are only executed when a
 // guard-banded sign/magnitude test cannot settle u, v, u+v or t (see consider_ratio).
 // Guard-banded classification of fl(x / det) against [0, 1]:
 //   -1 = certainly rejected (u < 0 or u > 1), +1 = certainly inside, 0 = undecided (divide).

@@ -1,18 +1,20 @@
 // engine.cu -- CUDA engine behind include/ppm.h (sm_100a, f64, no FMA).
 //
-// Kernels (one per hot-path computation of SURVEY.md section 8a):
-//   k_intersect        calc_intersection probe                  tracer.rs:306-350
-//   k_emit             Light::generate_photon probe             light.rs:67-91
-//   k_trace_photons    emit + bounce loop + record compaction   tracer.rs:31-125
-//   k_bbox/k_cell_key/k_scatter/k_hist  photon map = uniform grid, radix sorted
-//                      (replaces the kd-tree of photonmap.rs:23-29)
-//   k_gather           estimate_radiance                        tracer.rs:179-216
-//   k_within           kdtree.within probe                      tracer.rs:180
-//   k_gen_rays         Camera::generate_ray                     camera.rs:58-75
-//   k_eye_expand       trace_ray recursion -> gather-node list  tracer.rs:129-177
-//   k_direct_light     get_radiance_from_light / illuminated    tracer.rs:263-290
-//   k_combine          bsdf combination + pass accumulation     surface.rs:135-206, averager2.rb:49-62
+// This file holds the context, the host-side orchestration (streams, lanes, buffers) and the C ABI.
+// The kernels live in headers of the same translation unit (one per hot-path stage of SURVEY.md 8a):
+//   kernels_photon.cuh  k_intersect (calc_intersection probe, tracer.rs:306-350), k_emit (light.rs:67-91),
+//                       k_trace_photons (tracer.rs:31-125), k_import / k_export
+//   kernels_map.cuh     k_bbox, k_axis_hist, k_cell_key, k_scatter: the photon map as a radix-sorted uniform
+//                       grid (replaces the kd-tree of photonmap.rs:23-29)
+//   kernels_gather.cuh  k_query_key, k_gather (estimate_radiance, tracer.rs:179-216), k_knn_*, k_within
+//   kernels_eye.cuh     k_gen_rays (camera.rs:58-75), k_eye_expand (trace_ray, tracer.rs:129-177),
+//                       k_direct_light (tracer.rs:263-290), k_combine (surface.rs:135-206, averager2.rb:49-62)
+//   dev_core.cuh        f64 math in reference order, Philox, nearest_hit, BSDF sampling
 #include "dev_core.cuh"
+#include "kernels_photon.cuh"
+#include "kernels_map.cuh"
+#include "kernels_gather.cuh"
+#include "kernels_eye.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
@@ -26,660 +28,6 @@
 #include <string>
 #include <thread>
 #include <vector>
-
-// ===========================================================================
-// kernels
-// ===========================================================================
-
-__global__ void k_intersect(const __grid_constant__ DevScene sc, const double* __restrict__ rays6, int64_t n,
-                            int32_t* __restrict__ hit, double* __restrict__ t, double* __restrict__ pos3,
-                            double* __restrict__ nrm3, int32_t* __restrict__ io) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  D3 p = ld3(rays6 + i * 6), d = ld3(rays6 + i * 6 + 3);
-  Isect is;
-  bool ok = nearest_hit(sc, p, d, is);
-  hit[i] = ok ? is.obj : -1;
-  if (t) t[i] = ok ? is.t : 0.0;
-  if (pos3) st3(pos3 + i * 3, ok ? is.pos : mk3(0, 0, 0));
-  if (nrm3) st3(nrm3 + i * 3, ok ? is.nvec : mk3(0, 0, 0));
-  if (io) io[i] = ok ? is.io : 0;
-}
-
-struct LightSplit {
-  int64_t first[PPM_MAX_LIGHTS + 1];   // first[l] = global index of light l's first photon
-};
-__device__ __forceinline__ int light_of(const LightSplit& ls, int nlights, int64_t i) {
-  int l = 0;
-  while (l + 1 < nlights && i >= ls.first[l + 1]) ++l;
-  return l;
-}
-
-__global__ void k_emit(const __grid_constant__ DevScene sc, const __grid_constant__ LightSplit ls, uint64_t seed,
-                       uint32_t pass, int64_t n, ppm_photon* __restrict__ out) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  Philox rng(seed, pass, PPM_DOMAIN_PHOTON, (uint64_t)i, 0);
-  int wl; D3 pos, dir;
-  generate_photon(sc.lights[light_of(ls, sc.nlights, i)], rng, wl, pos, dir);
-  st3(out[i].pos, pos); st3(out[i].dir, dir);
-  out[i].wl = wl; out[i]._pad = 0;
-}
-
-// Unsorted photon records as produced by tracing / import.
-struct RecBuf {
-  double* pos3;     // [cap][3]
-  double* dir3;     // [cap][3]
-  uint8_t* wl;      // [cap]
-  uint64_t* tag;    // [cap]  (photon index << 4) | depth
-};
-
-// Persistent photon tracer with path regeneration.  Every photon path is still its own
-// counter-based Philox stream (seed, pass, photon index), so results do not depend on which
-// lane traces it: a lane whose photon is absorbed immediately claims the next photon index
-// from a global ticket counter (one atomic per warp per refill) instead of idling until the
-// longest path of its warp ends.  One loop iteration = (optional) emission + one bounce.
-// Records are appended with one atomic per warp (warp-aggregated compaction).
-__global__ void __launch_bounds__(128)
-k_trace_photons(const __grid_constant__ DevScene sc, const __grid_constant__ LightSplit ls, uint64_t seed, uint32_t pass,
-                int uc, int64_t n, RecBuf rec, unsigned long long* __restrict__ counter, unsigned long long cap,
-                unsigned long long* __restrict__ ticket) {
-  const unsigned FULL = 0xffffffffu;
-  const unsigned lane = threadIdx.x & 31u;
-  const unsigned lt_mask = (1u << lane) - 1u;
-  bool alive = false, exhausted = false;
-  int64_t idx = 0;
-  int wl = 0, medium = -1, depth = 0;
-  D3 pos = mk3(0, 0, 0), dir = mk3(1, 0, 0);
-  Philox rng(seed, pass, PPM_DOMAIN_PHOTON, 0, 0);
-  for (;;) {
-    // ---- refill dead lanes --------------------------------------------------------------
-    const unsigned need = __ballot_sync(FULL, !alive && !exhausted);
-    if (need) {
-      unsigned long long base = 0;
-      const int leader = __ffs(need) - 1;
-      if ((int)lane == leader) base = atomicAdd(ticket, (unsigned long long)__popc(need));
-      base = __shfl_sync(FULL, base, leader);
-      if (!alive && !exhausted) {
-        const int64_t i = (int64_t)(base + __popc(need & lt_mask));
-        if (i < n) {
-          idx = i;
-          rng = Philox(seed, pass, PPM_DOMAIN_PHOTON, (uint64_t)i, 0);
-          generate_photon(sc.lights[light_of(ls, sc.nlights, i)], rng, wl, pos, dir);
-          medium = -1; depth = 0; alive = true;
-        } else {
-          exhausted = true;
-        }
-      }
-    }
-    if (!__any_sync(FULL, alive)) break;
-    // ---- one bounce ----------------------------------------------------------------------
-    Isect is;
-    bool store = false;
-    const D3 in_dir = dir;
-    const int l = depth;
-    if (alive) {
-      if (!nearest_hit(sc, pos, dir, is)) {
-        alive = false;
-      } else {
-        store = (uc == 0 || l > 0) && surf_store_photon(sc.mats[is.mat]);
-        D3 nd;
-        const bool go = photon_bounce(sc, is, wl, dir, rng, medium, nd);
-        pos = is.pos;
-        ++depth;
-        if (go && depth < PPM_MAX_TRACE) dir = nd; else alive = false;   // `if l >= MAX_TRACE { return vec![] }`
-      }
-    }
-    const unsigned m = __ballot_sync(FULL, store);
-    if (m) {
-      unsigned long long base = 0;
-      const int leader = __ffs(m) - 1;
-      if ((int)lane == leader) base = atomicAdd(counter, (unsigned long long)__popc(m));
-      base = __shfl_sync(FULL, base, leader);
-      if (store) {
-        const unsigned long long slot = base + __popc(m & lt_mask);
-        if (slot < cap) {
-          st3(rec.pos3 + slot * 3, is.pos);
-          st3(rec.dir3 + slot * 3, in_dir);
-          rec.wl[slot] = (uint8_t)wl;
-          rec.tag[slot] = ((uint64_t)idx << 4) | (uint64_t)l;
-        }
-      }
-    }
-  }
-}
-
-__global__ void k_import(const ppm_photon* __restrict__ in, uint64_t n, RecBuf rec) {
-  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  for (int k = 0; k < 3; ++k) { rec.pos3[i * 3 + k] = in[i].pos[k]; rec.dir3[i * 3 + k] = in[i].dir[k]; }
-  rec.wl[i] = (uint8_t)in[i].wl;
-  rec.tag[i] = i << 4;
-}
-__global__ void k_export(RecBuf rec, uint64_t n, ppm_photon* __restrict__ out) {
-  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  for (int k = 0; k < 3; ++k) { out[i].pos[k] = rec.pos3[i * 3 + k]; out[i].dir[k] = rec.dir3[i * 3 + k]; }
-  out[i].wl = rec.wl[i]; out[i]._pad = 0;
-}
-
-// ---- photon map: uniform grid, cell edge >= r, cells linearised x-fastest ----
-struct Grid {
-  double org[3];
-  double inv_cell;
-  int32_t nx, ny, nz;
-  uint32_t ncells;
-};
-__device__ __forceinline__ unsigned long long enc_ord(double v) {
-  unsigned long long b = (unsigned long long)__double_as_longlong(v);
-  return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
-}
-static inline double dec_ord(unsigned long long e) {
-  unsigned long long b = (e & 0x8000000000000000ull) ? (e & 0x7fffffffffffffffull) : ~e;
-  double v;
-  std::memcpy(&v, &b, 8);
-  return v;
-}
-// mm[0..2] = min xyz, mm[3..5] = max xyz (order-preserving encoding)
-__global__ void k_bbox(const double* __restrict__ pos3, uint64_t n, unsigned long long* __restrict__ mm) {
-  unsigned long long lo[3] = {~0ull, ~0ull, ~0ull}, hi[3] = {0ull, 0ull, 0ull};
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
-    for (int k = 0; k < 3; ++k) {
-      unsigned long long e = enc_ord(pos3[i * 3 + k]);
-      lo[k] = e < lo[k] ? e : lo[k];
-      hi[k] = e > hi[k] ? e : hi[k];
-    }
-  for (int k = 0; k < 3; ++k) {
-    for (int o = 16; o > 0; o >>= 1) {
-      unsigned long long a = __shfl_xor_sync(0xffffffffu, lo[k], o), b = __shfl_xor_sync(0xffffffffu, hi[k], o);
-      lo[k] = a < lo[k] ? a : lo[k];
-      hi[k] = b > hi[k] ? b : hi[k];
-    }
-    if ((threadIdx.x & 31) == 0) { atomicMin(&mm[k], lo[k]); atomicMax(&mm[3 + k], hi[k]); }
-  }
-}
-// Per-axis histograms (AXIS_BINS bins over [lo, lo + AXIS_BINS*w)) for the trimmed grid region.
-#define AXIS_BINS 1024
-struct AxisRange { double lo[3], inv_w[3]; };
-__global__ void __launch_bounds__(256)
-k_axis_hist(const double* __restrict__ pos3, uint64_t n, AxisRange ar, uint32_t* __restrict__ hist) {
-  __shared__ uint32_t sh[3 * AXIS_BINS];
-  for (int i = threadIdx.x; i < 3 * AXIS_BINS; i += blockDim.x) sh[i] = 0;
-  __syncthreads();
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
-    for (int k = 0; k < 3; ++k) {
-      double b = floor((pos3[i * 3 + k] - ar.lo[k]) * ar.inv_w[k]);
-      int bi = b < 0.0 ? 0 : (b > (double)(AXIS_BINS - 1) ? AXIS_BINS - 1 : (int)b);
-      atomicAdd(&sh[k * AXIS_BINS + bi], 1u);
-    }
-  __syncthreads();
-  for (int i = threadIdx.x; i < 3 * AXIS_BINS; i += blockDim.x)
-    if (sh[i]) atomicAdd(&hist[i], sh[i]);
-}
-// cell coordinate, clamped into the grid (see the note on the trimmed region in do_map_build)
-__device__ __forceinline__ int cell_coord(const Grid& g, double p, int ax) {
-  const int nmax = (ax == 0 ? g.nx : (ax == 1 ? g.ny : g.nz)) - 1;
-  double f = floor((p - g.org[ax]) * g.inv_cell);
-  return f < 0.0 ? 0 : (f > (double)nmax ? nmax : (int)f);   // NaN -> 0
-}
-// sort key = (cell << 38) | (tag & (2^38-1)): photons ordered by cell, then by
-// (photon index, depth) -> the map is bit-reproducible whatever order the
-// tracing atomics produced.
-__global__ void k_cell_key(Grid g, const double* __restrict__ pos3, const uint64_t* __restrict__ tag, uint64_t n,
-                           uint64_t* __restrict__ keys, uint32_t* __restrict__ vals, uint32_t* __restrict__ hist) {
-  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  int cx = cell_coord(g, pos3[i * 3], 0), cy = cell_coord(g, pos3[i * 3 + 1], 1), cz = cell_coord(g, pos3[i * 3 + 2], 2);
-  uint32_t c = ((uint32_t)cz * (uint32_t)g.ny + (uint32_t)cy) * (uint32_t)g.nx + (uint32_t)cx;
-  keys[i] = ((uint64_t)c << 38) | (tag[i] & ((1ull << 38) - 1ull));
-  vals[i] = (uint32_t)i;
-  atomicAdd(&hist[c], 1u);
-}
-// Sorted photon map, laid out for 16-byte vector loads: per photon two double2
-// for (px, py | pz, wavelength-bits) and two for (dx, dy | dz, 0).  64 B physical
-// per photon (49 B of information).
-struct MapSoA {
-  double2* P;       // [n][2]
-  double2* D;       // [n][2]
-  uint32_t* orig;   // index in the unsorted (import/export) order
-};
-__global__ void k_scatter(RecBuf rec, const uint32_t* __restrict__ vals, uint64_t n, MapSoA m) {
-  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  uint32_t s = vals[i];
-  const double* p = rec.pos3 + (uint64_t)s * 3;
-  const double* d = rec.dir3 + (uint64_t)s * 3;
-  m.P[i * 2] = make_double2(p[0], p[1]);
-  m.P[i * 2 + 1] = make_double2(p[2], __longlong_as_double((long long)rec.wl[s]));
-  m.D[i * 2] = make_double2(d[0], d[1]);
-  m.D[i * 2 + 1] = make_double2(d[2], 0.0);
-  m.orig[i] = s;
-}
-
-// ---- gather -------------------------------------------------------------------
-// tracer.rs:198-216
-__device__ __forceinline__ double filter_cone(double d, double rmax) {
-  const double K_CONE = 1.1;
-  const double FAC_K = 1.0 - 2.0 / (3.0 * K_CONE);
-  double d2 = sqrt(d / rmax) / K_CONE;
-  return d2 > 1.0 ? 0.0 : (1.0 - d2) / FAC_K;
-}
-__device__ __forceinline__ double filter_gauss(double d, double rmax) {
-  const double ALPHA = 0.918, BETA = 1.953, E_BETA = 1.0 - 0.14184788965323, CORR = 0.5;
-  double e_r = 1.0 - exp(-BETA * d / (rmax * 2.0));
-  return e_r > E_BETA ? 0.0 : ALPHA * (1.0 - e_r / E_BETA) + CORR;
-}
-
-// Queries are keyed by their (padded) grid cell and radix sorted, so that the 32
-// lanes of a warp hold queries of the same cell (or of a few cells).
-__global__ void k_query_key(Grid g, const double* __restrict__ qpos3, int64_t n, uint32_t* __restrict__ keys,
-                            uint32_t* __restrict__ vals) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  int cx = cell_coord(g, qpos3[i * 3], 0), cy = cell_coord(g, qpos3[i * 3 + 1], 1), cz = cell_coord(g, qpos3[i * 3 + 2], 2);
-  uint32_t key = ((uint32_t)cz * (uint32_t)g.ny + (uint32_t)cy) * (uint32_t)g.nx + (uint32_t)cx;
-  keys[i] = key;
-  vals[i] = (uint32_t)i;
-}
-
-// v2: warp-cooperative gather.  A warp owns 32 cell-sorted queries (one per lane).
-// For each distinct cell among them, the photons of the (2R+1)^3 neighbourhood -- (2R+1)^2
-// x-contiguous runs of the sorted map, R = 1 (cell edge r: 9 runs of 3 cells) or R = 2 (cell
-// edge r/2: 25 runs of 5 cells, 30 % fewer candidates) -- form one virtual candidate stream;
-// 32 candidates at a time are fetched with coalesced 16-byte loads, staged in shared memory,
-// and every lane tests the SAME photon (broadcast LDS.128) against its own query -- no
-// per-lane loop lengths, no scattered global loads.
-#define GATHER_WARPS 4
-#define GATHER_SPAN 3        // a group may span cells cx .. cx+3 of one row
-// MODE 0: fixed radius r2 (estimate_radiance).  MODE 1: per-query squared radius r2q[] (k-NN estimate:
-// membership, filter rmax and normaliser all use the query's own radius).  MODE 2: count only,
-// members are d2 <= r2q[] (the bisection steps of the k-NN radius search).
-template <int FILTER, int MODE>
-__global__ void __launch_bounds__(GATHER_WARPS * 32)
-k_gather(Grid g, const uint32_t* __restrict__ cell_start, MapSoA m, const uint32_t* __restrict__ qkey,
-         const uint32_t* __restrict__ qidx, const double* __restrict__ qpos3, const double* __restrict__ qnrm3, int64_t n,
-         double power, double r2_fixed, const double* __restrict__ r2q, double* __restrict__ rgb3, uint32_t* __restrict__ counts,
-         unsigned long long* __restrict__ sum_k) {
-  constexpr int REACH = 1;
-  __shared__ double2 sP[GATHER_WARPS][32][2];
-  __shared__ double2 sD[GATHER_WARPS][32][2];
-  __shared__ uint32_t sEnd[GATHER_WARPS][32], sOff[GATHER_WARPS][32];   // per run: cumulative end, start - exclusive prefix
-  constexpr int W = 2 * REACH + 1, ROWS = W * W;
-  static_assert(ROWS <= 32, "one lane per run");
-  const unsigned FULL = 0xffffffffu;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t s = ((int64_t)blockIdx.x * GATHER_WARPS + warp) * 32 + lane;
-  const bool valid = s < n;
-  const uint32_t key = valid ? qkey[s] : 0xFFFFFFFFu;
-  const uint32_t qi = valid ? qidx[s] : 0u;
-  double qx = 0.0, qy = 0.0, qz = 0.0;
-  D3 nv = mk3(0.0, 0.0, 0.0);
-  double r2 = r2_fixed;
-  if (valid) {
-    qx = qpos3[(uint64_t)qi * 3]; qy = qpos3[(uint64_t)qi * 3 + 1]; qz = qpos3[(uint64_t)qi * 3 + 2];
-    if (MODE != 2) nv = ld3(qnrm3 + (uint64_t)qi * 3);
-    if (MODE != 0) r2 = r2q[qi];
-  }
-  double rr = 0.0, rg = 0.0, rb = 0.0;
-  uint32_t cnt = 0;
-  const uint32_t nxp = (uint32_t)g.nx, nyp = (uint32_t)g.ny;
-  unsigned pending = __ballot_sync(FULL, valid);
-  while (pending) {
-    const int leader = __ffs(pending) - 1;
-    const uint32_t ck = __shfl_sync(FULL, key, leader);
-    // Group = the pending lanes whose cell lies in the leader's row (same cy, cz) at most
-    // GATHER_SPAN cells to the right of the leader's cell (keys are sorted, x fastest).  They
-    // share ONE candidate stream covering [cx_leader - R, cx_last + R]: a superset of every
-    // lane's own neighbourhood, so the extra candidates simply fail the distance test.
-    const bool act = valid && key >= ck && key - ck <= (uint32_t)GATHER_SPAN && key / nxp == ck / nxp;
-    const unsigned grp = __ballot_sync(FULL, act);
-    pending &= ~grp;
-    const uint32_t klast = __shfl_sync(FULL, key, 31 - __clz((int)grp));
-    const int cx = (int)(ck % nxp), cy = (int)((ck / nxp) % nyp), cz = (int)(ck / (nxp * nyp));
-    const int x0 = max(cx - REACH, 0), x1 = min((int)(klast % nxp) + REACH, g.nx - 1);
-    // lane l < ROWS looks up run l = (dz, dy) of the neighbourhood
-    uint32_t rbeg = 0, rlen = 0;
-    if (lane < ROWS && x0 <= x1) {
-      const int z = cz + lane / W - REACH, y = cy + lane % W - REACH;
-      if (z >= 0 && z < g.nz && y >= 0 && y < g.ny) {
-        const uint32_t row = ((uint32_t)z * (uint32_t)g.ny + (uint32_t)y) * (uint32_t)g.nx;
-        rbeg = cell_start[row + x0];
-        rlen = cell_start[row + x1 + 1] - rbeg;
-      }
-    }
-    uint32_t pre = rlen;                               // inclusive prefix of the run lengths
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      uint32_t t = __shfl_up_sync(FULL, pre, o);
-      if (lane >= o) pre += t;
-    }
-    const uint32_t total = __shfl_sync(FULL, pre, 31);
-    __syncwarp();
-    sEnd[warp][lane] = pre;
-    sOff[warp][lane] = rbeg - (pre - rlen);
-    __syncwarp();
-    for (uint32_t base = 0; base < total; base += 32) {
-      const uint32_t v = base + lane;
-      if (v < total) {
-        int run = 0;                                   // number of runs that end at or before v (binary search)
-#pragma unroll
-        for (int step = 16; step > 0; step >>= 1)
-          if (sEnd[warp][run + step - 1] <= v) run += step;
-        const uint32_t o = sOff[warp][run];
-        const uint64_t j = (uint64_t)(v + o) * 2;
-        sP[warp][lane][0] = m.P[j]; sP[warp][lane][1] = m.P[j + 1];
-        if (MODE != 2) { sD[warp][lane][0] = m.D[j]; sD[warp][lane][1] = m.D[j + 1]; }
-      }
-      __syncwarp();
-      const int mcount = (int)min(32u, total - base);
-      if (act) {
-        for (int t = 0; t < mcount; ++t) {
-          const double2 a = sP[warp][t][0], b = sP[warp][t][1];
-          // squared_euclidean: ((qx-px)^2 + (qy-py)^2) + (qz-pz)^2, member iff d2 <= r2
-          const double ax = qx - a.x, ay = qy - a.y, az = qz - b.x;
-          const double d2 = (ax * ax + ay * ay) + az * az;
-          if (d2 <= r2) {
-            ++cnt;
-            if (MODE == 2) continue;
-            const double wt = FILTER == PPM_FILTER_NONE ? 1.0 : (FILTER == PPM_FILTER_CONE ? filter_cone(d2, r2) : filter_gauss(d2, r2));
-            const double2 c = sD[warp][t][0], d = sD[warp][t][1];
-            // photon_to_radiance, optics.rs:224-233
-            const double cos0 = (nv.x * c.x + nv.y * c.y) + nv.z * d.x;
-            const double pw2 = cos0 < 0.0 ? (wt * power) * -cos0 : 0.0;
-            const int w = (int)__double_as_longlong(b.y);
-            if (w == 0) rr = rr + pw2; else if (w == 1) rg = rg + pw2; else rb = rb + pw2;
-          }
-        }
-      }
-      __syncwarp();
-    }
-  }
-  if (valid) {
-    if (MODE != 2) {
-      const double sc = (1.0 / PPM_PI) / r2;          // rad * (ONE_PI / radius), tracer.rs:193
-      rgb3[(uint64_t)qi * 3] = rr * sc; rgb3[(uint64_t)qi * 3 + 1] = rg * sc; rgb3[(uint64_t)qi * 3 + 2] = rb * sc;
-    }
-    if (counts) counts[qi] = cnt;
-  }
-  if (sum_k) {
-    unsigned long long c = cnt;
-    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(FULL, c, o);
-    if (lane == 0 && c) atomicAdd(sum_k, c);
-  }
-}
-
-// ---- k-NN radius search: exact k-th smallest d2 per query by bisection on the bit pattern of d2 --------
-// (non-negative doubles order like their bit patterns).  State per query: [lo, hi] as uint64 bits,
-// hi always satisfies count(d2 <= hi) >= k.  done[] = 1 when fewer than k photons lie within r (fixed radius).
-__global__ void k_knn_init(int64_t n, double r2, const uint32_t* __restrict__ cnt, uint32_t k, unsigned long long* __restrict__ lo,
-                           unsigned long long* __restrict__ hi, double* __restrict__ thr, unsigned int* __restrict__ n_active) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const unsigned long long rb = (unsigned long long)__double_as_longlong(r2);
-  if (cnt[i] < k) { lo[i] = hi[i] = rb; thr[i] = r2; return; }        // fewer than k within r: fixed radius
-  lo[i] = 0ull; hi[i] = rb;
-  thr[i] = __longlong_as_double((long long)(rb >> 1));
-  atomicAdd(n_active, 1u);
-}
-__global__ void k_knn_step(int64_t n, const uint32_t* __restrict__ cnt, uint32_t k, unsigned long long* __restrict__ lo,
-                           unsigned long long* __restrict__ hi, double* __restrict__ thr, unsigned int* __restrict__ n_active) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  unsigned long long l = lo[i], h = hi[i];
-  if (l >= h) return;
-  const unsigned long long mid = l + ((h - l) >> 1);                   // thr[i] was asdouble(mid)
-  if (cnt[i] >= k) h = mid; else l = mid + 1;
-  lo[i] = l; hi[i] = h;
-  if (l < h) { thr[i] = __longlong_as_double((long long)(l + ((h - l) >> 1))); atomicAdd(n_active, 1u); }
-  else thr[i] = __longlong_as_double((long long)h);
-}
-// a k-th distance of exactly zero (k coincident photons at the query) cannot normalise: fall back to r2
-__global__ void k_knn_finish(int64_t n, double r2, double* __restrict__ thr) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n && !(thr[i] > 0.0)) thr[i] = r2;
-}
-
-__global__ void k_within(Grid g, const uint32_t* __restrict__ cell_start, MapSoA m, const double* __restrict__ qpos3,
-                         int64_t n, double r2, uint32_t* __restrict__ idx, uint32_t* __restrict__ counts, uint32_t cap) {
-  int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= n) return;
-  const double qx = qpos3[q * 3], qy = qpos3[q * 3 + 1], qz = qpos3[q * 3 + 2];
-  uint32_t cnt = 0;
-  int cx = cell_coord(g, qx, 0), cy = cell_coord(g, qy, 1), cz = cell_coord(g, qz, 2);
-  const int R = 1;
-  int x0 = max(cx - R, 0), x1 = min(cx + R, g.nx - 1);
-  if (x0 <= x1)
-    for (int z = max(cz - R, 0); z <= min(cz + R, g.nz - 1); ++z)
-      for (int y = max(cy - R, 0); y <= min(cy + R, g.ny - 1); ++y) {
-        uint32_t row = ((uint32_t)z * (uint32_t)g.ny + (uint32_t)y) * (uint32_t)g.nx;
-        uint32_t b = cell_start[row + x0], e = cell_start[row + x1 + 1];
-        for (uint32_t j = b; j < e; ++j) {
-          const double2 a = m.P[(uint64_t)j * 2], b = m.P[(uint64_t)j * 2 + 1];
-          double ax = qx - a.x, ay = qy - a.y, az = qz - b.x;
-          double d2 = (ax * ax + ay * ay) + az * az;
-          if (d2 <= r2) {
-            if (cnt < cap) idx[(uint64_t)q * cap + cnt] = m.orig[j];
-            ++cnt;
-          }
-        }
-      }
-  counts[q] = cnt;
-}
-
-// ---- camera ---------------------------------------------------------------------
-__device__ __forceinline__ void camera_ray(const ppm_camera& cam, int64_t pix, uint64_t seed, uint32_t pass, D3& pos, D3& dir) {
-  Philox rng(seed, pass, PPM_DOMAIN_EYE, (uint64_t)pix, 0);
-  double y = (double)(pix / cam.xreso), x = (double)(pix % cam.xreso);
-  D3 blur = mk3(0.0, 0.0, 0.0);
-  if (cam.blur) {
-    double r1 = rng.range(-0.5, 0.5);
-    double r2 = rng.range(-0.5, 0.5);
-    blur = r1 * ld3(cam.eex) + r2 * ld3(cam.eey);
-  }
-  double r3 = 0.0, r4 = 0.0;
-  if (cam.progressive && cam.antialias) { r3 = rng.range(-0.5, 0.5); r4 = rng.range(-0.5, 0.5); }
-  pos = ld3(cam.eye_pos) + blur;
-  D3 ed = ((ld3(cam.origin) + (x + r3) * ld3(cam.esx)) + (y + r4) * ld3(cam.esy)) - blur;
-  dir = mk3(1.0, 0.0, 0.0);
-  normalize(ed, dir);
-}
-__global__ void k_gen_rays(const __grid_constant__ ppm_camera cam, uint64_t seed, uint32_t pass, int64_t n,
-                           double* __restrict__ rays6) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  D3 p, d;
-  camera_ray(cam, i, seed, pass, p, d);
-  st3(rays6 + i * 6, p); st3(rays6 + i * 6 + 3, d);
-}
-
-// ---- eye path expansion ------------------------------------------------------------
-// The binary recursion of trace_ray becomes a per-pixel depth-first walk with an explicit
-// stack and a top-down RGB throughput W.  Each visited node that has a non-zero diffuse
-// coefficient becomes one "gather node" (hit point, normal, W (.) kd) in a global pool.
-// Single pass: slots are claimed with one atomic per warp (opportunistic warp aggregation);
-// every node stores the slot of the previous node of its pixel, and the pixel stores the last
-// one, so k_combine can walk a pixel's nodes in a fixed order (reverse creation order) --
-// the image does not depend on where the atomics placed the nodes.
-struct EyeNodes {
-  double* pos3;     // [cap][3] hit position     (gather / direct-light query)
-  double* nrm3;     // [cap][3] facing normal
-  double* w3;       // [cap][3] W (.) kd
-  uint32_t* prev;   // [cap]    previous node of the same pixel, EYE_NONE = first
-};
-#define EYE_NONE 0xFFFFFFFFu
-struct EyeStack {
-  D3 pos, dir, W;
-  int medium, depth;
-  uint32_t node;
-};
-__global__ void __launch_bounds__(128)
-k_eye_expand(const __grid_constant__ DevScene sc, const __grid_constant__ ppm_camera cam, const double* __restrict__ rays6,
-             int64_t n, int64_t first_pixel, uint64_t seed, uint32_t pass, EyeNodes nodes, uint32_t cap,
-             uint32_t* __restrict__ head, double* __restrict__ emit3, unsigned long long* __restrict__ pool_counter,
-             unsigned long long* __restrict__ n_visited, int classic) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const unsigned lane = threadIdx.x & 31u;
-  const unsigned lt_mask = (1u << lane) - 1u;
-  const int64_t pix = first_pixel + i;
-  EyeStack st[PPM_MAX_TRACE + 2];
-  int sp = 0;
-  if (rays6) { st[0].pos = ld3(rays6 + i * 6); st[0].dir = ld3(rays6 + i * 6 + 3); }
-  else camera_ray(cam, pix, seed, pass, st[0].pos, st[0].dir);
-  st[0].W = mk3(1.0, 1.0, 1.0); st[0].medium = -1; st[0].depth = 0; st[0].node = 1;
-  sp = 1;
-  D3 emit = mk3(0.0, 0.0, 0.0);
-  uint32_t last = EYE_NONE, visited = 0;
-  const double SR_HALF = 1.0 / (2.0 * PPM_PI);
-  while (sp > 0) {
-    EyeStack e = st[--sp];
-    if (e.depth >= PPM_MAX_TRACE) continue;
-    Isect is;
-    if (!nearest_hit(sc, e.pos, e.dir, is)) continue;
-    ++visited;
-    Philox rng(seed, pass, PPM_DOMAIN_EYE, (uint64_t)pix, e.node);
-    EyeNode nd;
-    eye_node(sc, is, e.dir, e.medium, rng, nd, classic != 0);
-    const ppm_material& m = sc.mats[is.mat];
-    emit = emit + cmul(e.W, ld3(m.emittance) * SR_HALF);
-    const D3 wd = cmul(e.W, nd.kd);
-    {
-      const bool create = any_nz(wd);
-      const unsigned conv = __activemask();                 // lanes that reached this point together
-      const unsigned cm = __ballot_sync(conv, create);
-      if (cm) {
-        unsigned long long base = 0;
-        const int leader = __ffs(cm) - 1;
-        if ((int)lane == leader) base = atomicAdd(pool_counter, (unsigned long long)__popc(cm));
-        base = __shfl_sync(conv, base, leader);
-        if (create) {
-          const unsigned long long s = base + __popc(cm & lt_mask);
-          if (s < cap) {
-            st3(nodes.pos3 + s * 3, is.pos); st3(nodes.nrm3 + s * 3, is.nvec); st3(nodes.w3 + s * 3, wd);
-            nodes.prev[s] = last;
-            last = (uint32_t)s;
-          }                                                 // else: pool overflow, the host grows it and re-runs
-        }
-      }
-    }
-    // push the refract child first so that the reflect subtree is walked first
-    // (reference order: si is evaluated before ti, tracer.rs:152-171)
-    if (nd.refract) {
-      D3 wt = cmul(e.W, nd.kt);
-      if (any_nz(wt) && sp < PPM_MAX_TRACE + 2) {
-        EyeStack& c = st[sp++];
-        c.pos = is.pos; c.dir = nd.tdir; c.W = wt; c.medium = nd.t_medium; c.depth = e.depth + 1; c.node = e.node * 2 + 1;
-      }
-    }
-    if (nd.reflect) {
-      D3 ws = cmul(e.W, nd.ks);
-      if (any_nz(ws) && sp < PPM_MAX_TRACE + 2) {
-        EyeStack& c = st[sp++];
-        c.pos = is.pos; c.dir = nd.rdir; c.W = ws; c.medium = e.medium; c.depth = e.depth + 1; c.node = e.node * 2;
-      }
-    }
-  }
-  head[i] = last;
-  st3(emit3 + i * 3, emit);
-  if (n_visited) {
-    const unsigned conv = __activemask();
-    unsigned long long v = visited;
-    for (int o = 16; o > 0; o >>= 1) {
-      unsigned long long t = __shfl_down_sync(conv, v, o);
-      if (lane + o < 32 && ((conv >> (lane + o)) & 1u)) v += t;
-    }
-    if (lane == (unsigned)(__ffs(conv) - 1)) atomicAdd(n_visited, v);
-  }
-}
-
-// ---- direct light: one thread per gather node, samples walked sequentially ----------
-// get_radiance_from_light (tracer.rs:263-270) pairs [0, L(d0), L(d1), ...] with
-// [c0, c1, c2, ...] (the RADIANCE0 seed of light.rs:132): the i-th surviving sample is
-// weighted with the radiance of the (i-1)-th.  Walking the 25 samples in order inside one
-// thread turns that pairing into a register recurrence and reproduces the reference's
-// summation order.  Point and sun lights have a single sample, which is paired with the
-// zero -> they contribute nothing and are skipped.
-__device__ __forceinline__ double ts5(unsigned i) {   // the literals 0.1, 0.3, 0.5, 0.7, 0.9 (light.rs:164-170)
-  return i == 0 ? 0.1 : (i == 1 ? 0.3 : (i == 2 ? 0.5 : (i == 3 ? 0.7 : 0.9)));
-}
-__global__ void __launch_bounds__(128)
-k_direct_light(const __grid_constant__ DevScene sc, const double* __restrict__ pos3, const double* __restrict__ nrm3,
-               int64_t n, double* __restrict__ out3) {
-  const int64_t node = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (node >= n) return;
-  const D3 p = ld3(pos3 + node * 3), nv = ld3(nrm3 + node * 3);
-  D3 total = mk3(0.0, 0.0, 0.0);
-  for (int li = 0; li < sc.nlights; ++li) {
-    const ppm_light& l = sc.lights[li];
-    if (l.type != PPM_LIGHT_PARALLELOGRAM) continue;
-    const D3 lpos = ld3(l.pos), ldir1 = ld3(l.dir1), ldir2 = ld3(l.dir2), lnv = ld3(l.nvec);
-    const double PI4 = PPM_PI * 4.0;
-    const double lnum = 2.0 * l.flux * 0.2 * 0.2;           // 2 * flux * PARA_DIV * PARA_DIV, light.rs:142
-    D3 rad = mk3(0.0, 0.0, 0.0);
-    bool have_prev = false;
-    double dprev = 0.0;
-    for (unsigned s = 0; s < 25; ++s) {
-      const D3 gp = (lpos + ts5(s / 5) * ldir1) + ts5(s % 5) * ldir2;   // gen_pos, light.rs:152-154
-      const D3 d = gp - p;
-      if (!(dot(lnv, d) < 0.0)) continue;                   // light.rs:112
-      D3 ld;
-      if (!normalize(d, ld)) continue;                      // tracer.rs:275-276
-      const double cos0 = dot(nv, ld);
-      if (cos0 < 0.0) continue;
-      Isect is;
-      if (!nearest_hit(sc, p, ld, is)) continue;            // no hit counts as occluded, tracer.rs:282
-      const double sq_ldist = dot(d, d);
-      const D3 po = is.pos - p;
-      if (sq_ldist - dot(po, po) > 0.002) continue;
-      if (have_prev) {
-        const double l0 = lnum / (PI4 * dprev);
-        const double cc = cos0 * cos0;
-        rad = rad + mk3((l.color[0] * l0) * cc, (l.color[1] * l0) * cc, (l.color[2] * l0) * cc);
-      }
-      have_prev = true;
-      dprev = sq_ldist;
-    }
-    total = total + rad;
-  }
-  st3(out3 + node * 3, total);
-}
-
-// ---- combine + accumulate ------------------------------------------------------------
-// pixel = sum_nodes W(.)kd (.) (direct + photon estimate) + sum emittance terms;
-// then the pass image is added to the running sum (util/averager2.rb:49-62).
-__global__ void k_combine(const uint32_t* __restrict__ head, const uint32_t* __restrict__ prev, const double* __restrict__ w3,
-                          const double* __restrict__ direct3, const double* __restrict__ photon3,
-                          const double* __restrict__ emit3, int64_t n, double* __restrict__ out3,
-                          double* __restrict__ accum3, int64_t accum_first, D3 ambient) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  D3 rad = ld3(emit3 + i * 3);
-  for (uint32_t s = head[i]; s != EYE_NONE; s = prev[s]) {
-    D3 di;
-    if (photon3) {
-      di = ld3(photon3 + (uint64_t)s * 3);
-      if (direct3) di = ld3(direct3 + (uint64_t)s * 3) + di;   // di = direct + estimate, tracer.rs:136-145
-    } else {
-      di = ld3(direct3 + (uint64_t)s * 3) + ambient;           // classic: di = direct + cam.ambient, tracer.rs:234-238
-    }
-    rad = rad + cmul(ld3(w3 + (uint64_t)s * 3), di);
-  }
-  st3(out3 + i * 3, rad);
-  if (accum3) {
-    double* a = accum3 + (accum_first + i) * 3;
-    a[0] += rad.x; a[1] += rad.y; a[2] += rad.z;
-  }
-}
-__global__ void k_bump(double* npass) { npass[0] += 1.0; }
-// acc += other; other = 0   (merging the twin lane's accumulator, incl. the pass counter)
-__global__ void k_accum_merge(double* __restrict__ acc, double* __restrict__ other, int64_t n) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) { acc[i] += other[i]; other[i] = 0.0; }
-}
-__global__ void k_scale(const double* __restrict__ in, const double* __restrict__ npass, int64_t n, double* __restrict__ out) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = in[i] / npass[0];
-}
 
 // ===========================================================================
 // context

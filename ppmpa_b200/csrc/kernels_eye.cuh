@@ -1,0 +1,223 @@
+// kernels_eye.cuh -- camera rays, eye-path expansion, classic direct light, combine + accumulate
+// Part of the single translation unit engine.cu (compiled -fmad=false, sm_100a); see DESIGN.md section 6.
+#ifndef PPM_KERNELS_EYE_CUH_
+#define PPM_KERNELS_EYE_CUH_
+
+#include "dev_core.cuh"
+
+// ---- camera ---------------------------------------------------------------------
+__device__ __forceinline__ void camera_ray(const ppm_camera& cam, int64_t pix, uint64_t seed, uint32_t pass, D3& pos, D3& dir) {
+  Philox rng(seed, pass, PPM_DOMAIN_EYE, (uint64_t)pix, 0);
+  double y = (double)(pix / cam.xreso), x = (double)(pix % cam.xreso);
+  D3 blur = mk3(0.0, 0.0, 0.0);
+  if (cam.blur) {
+    double r1 = rng.range(-0.5, 0.5);
+    double r2 = rng.range(-0.5, 0.5);
+    blur = r1 * ld3(cam.eex) + r2 * ld3(cam.eey);
+  }
+  double r3 = 0.0, r4 = 0.0;
+  if (cam.progressive && cam.antialias) { r3 = rng.range(-0.5, 0.5); r4 = rng.range(-0.5, 0.5); }
+  pos = ld3(cam.eye_pos) + blur;
+  D3 ed = ((ld3(cam.origin) + (x + r3) * ld3(cam.esx)) + (y + r4) * ld3(cam.esy)) - blur;
+  dir = mk3(1.0, 0.0, 0.0);
+  normalize(ed, dir);
+}
+__global__ void k_gen_rays(const __grid_constant__ ppm_camera cam, uint64_t seed, uint32_t pass, int64_t n,
+                           double* __restrict__ rays6) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  D3 p, d;
+  camera_ray(cam, i, seed, pass, p, d);
+  st3(rays6 + i * 6, p); st3(rays6 + i * 6 + 3, d);
+}
+
+// ---- eye path expansion ------------------------------------------------------------
+// The binary recursion of trace_ray becomes a per-pixel depth-first walk with an explicit
+// stack and a top-down RGB throughput W.  Each visited node that has a non-zero diffuse
+// coefficient becomes one "gather node" (hit point, normal, W (.) kd) in a global pool.
+// Single pass: slots are claimed with one atomic per warp (opportunistic warp aggregation);
+// every node stores the slot of the previous node of its pixel, and the pixel stores the last
+// one, so k_combine can walk a pixel's nodes in a fixed order (reverse creation order) --
+// the image does not depend on where the atomics placed the nodes.
+struct EyeNodes {
+  double* pos3;     // [cap][3] hit position     (gather / direct-light query)
+  double* nrm3;     // [cap][3] facing normal
+  double* w3;       // [cap][3] W (.) kd
+  uint32_t* prev;   // [cap]    previous node of the same pixel, EYE_NONE = first
+};
+#define EYE_NONE 0xFFFFFFFFu
+struct EyeStack {
+  D3 pos, dir, W;
+  int medium, depth;
+  uint32_t node;
+};
+__global__ void __launch_bounds__(128)
+k_eye_expand(const __grid_constant__ DevScene sc, const __grid_constant__ ppm_camera cam, const double* __restrict__ rays6,
+             int64_t n, int64_t first_pixel, uint64_t seed, uint32_t pass, EyeNodes nodes, uint32_t cap,
+             uint32_t* __restrict__ head, double* __restrict__ emit3, unsigned long long* __restrict__ pool_counter,
+             unsigned long long* __restrict__ n_visited, int classic) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const int64_t pix = first_pixel + i;
+  EyeStack st[PPM_MAX_TRACE + 2];
+  int sp = 0;
+  if (rays6) { st[0].pos = ld3(rays6 + i * 6); st[0].dir = ld3(rays6 + i * 6 + 3); }
+  else camera_ray(cam, pix, seed, pass, st[0].pos, st[0].dir);
+  st[0].W = mk3(1.0, 1.0, 1.0); st[0].medium = -1; st[0].depth = 0; st[0].node = 1;
+  sp = 1;
+  D3 emit = mk3(0.0, 0.0, 0.0);
+  uint32_t last = EYE_NONE, visited = 0;
+  const double SR_HALF = 1.0 / (2.0 * PPM_PI);
+  while (sp > 0) {
+    EyeStack e = st[--sp];
+    if (e.depth >= PPM_MAX_TRACE) continue;
+    Isect is;
+    if (!nearest_hit(sc, e.pos, e.dir, is)) continue;
+    ++visited;
+    Philox rng(seed, pass, PPM_DOMAIN_EYE, (uint64_t)pix, e.node);
+    EyeNode nd;
+    eye_node(sc, is, e.dir, e.medium, rng, nd, classic != 0);
+    const ppm_material& m = sc.mats[is.mat];
+    emit = emit + cmul(e.W, ld3(m.emittance) * SR_HALF);
+    const D3 wd = cmul(e.W, nd.kd);
+    {
+      const bool create = any_nz(wd);
+      const unsigned conv = __activemask();                 // lanes that reached this point together
+      const unsigned cm = __ballot_sync(conv, create);
+      if (cm) {
+        unsigned long long base = 0;
+        const int leader = __ffs(cm) - 1;
+        if ((int)lane == leader) base = atomicAdd(pool_counter, (unsigned long long)__popc(cm));
+        base = __shfl_sync(conv, base, leader);
+        if (create) {
+          const unsigned long long s = base + __popc(cm & lt_mask);
+          if (s < cap) {
+            st3(nodes.pos3 + s * 3, is.pos); st3(nodes.nrm3 + s * 3, is.nvec); st3(nodes.w3 + s * 3, wd);
+            nodes.prev[s] = last;
+            last = (uint32_t)s;
+          }                                                 // else: pool overflow, the host grows it and re-runs
+        }
+      }
+    }
+    // push the refract child first so that the reflect subtree is walked first
+    // (reference order: si is evaluated before ti, tracer.rs:152-171)
+    if (nd.refract) {
+      D3 wt = cmul(e.W, nd.kt);
+      if (any_nz(wt) && sp < PPM_MAX_TRACE + 2) {
+        EyeStack& c = st[sp++];
+        c.pos = is.pos; c.dir = nd.tdir; c.W = wt; c.medium = nd.t_medium; c.depth = e.depth + 1; c.node = e.node * 2 + 1;
+      }
+    }
+    if (nd.reflect) {
+      D3 ws = cmul(e.W, nd.ks);
+      if (any_nz(ws) && sp < PPM_MAX_TRACE + 2) {
+        EyeStack& c = st[sp++];
+        c.pos = is.pos; c.dir = nd.rdir; c.W = ws; c.medium = e.medium; c.depth = e.depth + 1; c.node = e.node * 2;
+      }
+    }
+  }
+  head[i] = last;
+  st3(emit3 + i * 3, emit);
+  if (n_visited) {
+    const unsigned conv = __activemask();
+    unsigned long long v = visited;
+    for (int o = 16; o > 0; o >>= 1) {
+      unsigned long long t = __shfl_down_sync(conv, v, o);
+      if (lane + o < 32 && ((conv >> (lane + o)) & 1u)) v += t;
+    }
+    if (lane == (unsigned)(__ffs(conv) - 1)) atomicAdd(n_visited, v);
+  }
+}
+
+// ---- direct light: one thread per gather node, samples walked sequentially ----------
+// get_radiance_from_light (tracer.rs:263-270) pairs [0, L(d0), L(d1), ...] with
+// [c0, c1, c2, ...] (the RADIANCE0 seed of light.rs:132): the i-th surviving sample is
+// weighted with the radiance of the (i-1)-th.  Walking the 25 samples in order inside one
+// thread turns that pairing into a register recurrence and reproduces the reference's
+// summation order.  Point and sun lights have a single sample, which is paired with the
+// zero -> they contribute nothing and are skipped.
+__device__ __forceinline__ double ts5(unsigned i) {   // the literals 0.1, 0.3, 0.5, 0.7, 0.9 (light.rs:164-170)
+  return i == 0 ? 0.1 : (i == 1 ? 0.3 : (i == 2 ? 0.5 : (i == 3 ? 0.7 : 0.9)));
+}
+__global__ void __launch_bounds__(128)
+k_direct_light(const __grid_constant__ DevScene sc, const double* __restrict__ pos3, const double* __restrict__ nrm3,
+               int64_t n, double* __restrict__ out3) {
+  const int64_t node = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (node >= n) return;
+  const D3 p = ld3(pos3 + node * 3), nv = ld3(nrm3 + node * 3);
+  D3 total = mk3(0.0, 0.0, 0.0);
+  for (int li = 0; li < sc.nlights; ++li) {
+    const ppm_light& l = sc.lights[li];
+    if (l.type != PPM_LIGHT_PARALLELOGRAM) continue;
+    const D3 lpos = ld3(l.pos), ldir1 = ld3(l.dir1), ldir2 = ld3(l.dir2), lnv = ld3(l.nvec);
+    const double PI4 = PPM_PI * 4.0;
+    const double lnum = 2.0 * l.flux * 0.2 * 0.2;           // 2 * flux * PARA_DIV * PARA_DIV, light.rs:142
+    D3 rad = mk3(0.0, 0.0, 0.0);
+    bool have_prev = false;
+    double dprev = 0.0;
+    for (unsigned s = 0; s < 25; ++s) {
+      const D3 gp = (lpos + ts5(s / 5) * ldir1) + ts5(s % 5) * ldir2;   // gen_pos, light.rs:152-154
+      const D3 d = gp - p;
+      if (!(dot(lnv, d) < 0.0)) continue;                   // light.rs:112
+      D3 ld;
+      if (!normalize(d, ld)) continue;                      // tracer.rs:275-276
+      const double cos0 = dot(nv, ld);
+      if (cos0 < 0.0) continue;
+      Isect is;
+      if (!nearest_hit(sc, p, ld, is)) continue;            // no hit counts as occluded, tracer.rs:282
+      const double sq_ldist = dot(d, d);
+      const D3 po = is.pos - p;
+      if (sq_ldist - dot(po, po) > 0.002) continue;
+      if (have_prev) {
+        const double l0 = lnum / (PI4 * dprev);
+        const double cc = cos0 * cos0;
+        rad = rad + mk3((l.color[0] * l0) * cc, (l.color[1] * l0) * cc, (l.color[2] * l0) * cc);
+      }
+      have_prev = true;
+      dprev = sq_ldist;
+    }
+    total = total + rad;
+  }
+  st3(out3 + node * 3, total);
+}
+
+// ---- combine + accumulate ------------------------------------------------------------
+// pixel = sum_nodes W(.)kd (.) (direct + photon estimate) + sum emittance terms;
+// then the pass image is added to the running sum (util/averager2.rb:49-62).
+__global__ void k_combine(const uint32_t* __restrict__ head, const uint32_t* __restrict__ prev, const double* __restrict__ w3,
+                          const double* __restrict__ direct3, const double* __restrict__ photon3,
+                          const double* __restrict__ emit3, int64_t n, double* __restrict__ out3,
+                          double* __restrict__ accum3, int64_t accum_first, D3 ambient) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  D3 rad = ld3(emit3 + i * 3);
+  for (uint32_t s = head[i]; s != EYE_NONE; s = prev[s]) {
+    D3 di;
+    if (photon3) {
+      di = ld3(photon3 + (uint64_t)s * 3);
+      if (direct3) di = ld3(direct3 + (uint64_t)s * 3) + di;   // di = direct + estimate, tracer.rs:136-145
+    } else {
+      di = ld3(direct3 + (uint64_t)s * 3) + ambient;           // classic: di = direct + cam.ambient, tracer.rs:234-238
+    }
+    rad = rad + cmul(ld3(w3 + (uint64_t)s * 3), di);
+  }
+  st3(out3 + i * 3, rad);
+  if (accum3) {
+    double* a = accum3 + (accum_first + i) * 3;
+    a[0] += rad.x; a[1] += rad.y; a[2] += rad.z;
+  }
+}
+__global__ void k_bump(double* npass) { npass[0] += 1.0; }
+// acc += other; other = 0   (merging the twin lane's accumulator, incl. the pass counter)
+__global__ void k_accum_merge(double* __restrict__ acc, double* __restrict__ other, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { acc[i] += other[i]; other[i] = 0.0; }
+}
+__global__ void k_scale(const double* __restrict__ in, const double* __restrict__ npass, int64_t n, double* __restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[i] / npass[0];
+}
+
+#endif

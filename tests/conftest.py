@@ -8,7 +8,18 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
-REF_EXAMPLES = os.path.join(ROOT, "tests", "golden", "scenes")   # committed copies of the *data* files used by tests
+
+
+def _ensure_built():
+    """The CPU suite needs libppm_b200.so (host functions + ABI surface) and the oracle: build them if absent."""
+    import subprocess
+    if not os.path.exists(os.path.join(ROOT, "ppmpa_b200", "libppm_b200.so")):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "ppmpa_b200", "csrc"), "-s", "all"])
+    if not os.path.exists(os.path.join(ROOT, "oracle", "libppm_oracle.so")):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "-s"])
+
+
+_ensure_built()
 
 
 def pytest_configure(config):
