@@ -711,6 +711,7 @@ int ppm_within(ppm_ctx* c, const double* q3, int64_t nq, uint32_t* idx, uint32_t
   if ((rc = stage_in(c, q3, (size_t)nq * 24, c->st_in0, &dq))) return rc;
   CK(c, c->st_out0.ensure(ib));
   di = c->st_out0.p;
+  CK(c, cudaMemsetAsync(di, 0, ib, c->stream));      // slots beyond a query's count stay 0
   if ((rc = stage_out(c, count, (size_t)nq * 4, c->st_out1, &dc))) return rc;
   k_within<<<nblk(nq, 128), 128, 0, c->stream>>>(c->grid, c->cell_start.as<uint32_t>(), mapsoa(c), (const double*)dq, nq, c->r2,
                                                 (uint32_t*)di, (uint32_t*)dc, cap);

@@ -1,0 +1,29 @@
+"""Small end-to-end run for compute-sanitizer: every kernel once (pass, batch with two lanes, probes, k-NN, classic)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, ppmpa_b200 as P
+from ppmpa_b200 import _capi as K
+from ppmpa_b200.synth import wall_photons
+EX = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples")
+eng = P.Engine(0)
+for scene in (None, os.path.join(EX, "ex-glassbox.scene")):
+    sc = P.read_scene(scene)
+    cam = P.read_camera(None, xreso=24, yreso=24)
+    eng.set_scene(sc); eng.set_camera(cam)
+    eng.accum_reset()
+    eng.iteration(1, 0, 3000, 0.3 ** 2, True)
+    eng.iterate(1, 1, 3, 3000, [0.09, 0.08, 0.07], uc=False)
+    img = eng.image_mean()
+    rays = eng.generate_rays(1, 0)
+    eng.calc_intersection(rays)
+    eng.trace_rays_classic(rays, 1, 0)
+ph, power = wall_photons(3000, seed=1)
+eng.import_photons(ph, power); eng.build_photonmap(0.04)
+q = ph["pos"][:200] + 0.01
+nrm = np.tile([0.0, 1.0, 0.0], (200, 1))
+for f in (0, 1, 2):
+    eng.estimate_radiance(q, nrm, f)
+eng.estimate_radiance_knn(q, nrm, 20, 1)
+eng.within(q, 64)
+print("sanitize run ok", float(img.sum()))
+eng.close()
