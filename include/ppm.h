@@ -267,6 +267,12 @@ int  ppm_trace_rays(ppm_ctx* ctx, const double* rays6_h_or_d, int64_t n,
                     int64_t first_pixel, uint64_t seed, uint32_t pass, int uc,
                     double* rgb3_h_or_d);
 
+/* -- parity probe: get_radiance_from_light summed over the lights, tracer.rs:136-141,
+ *    263-290 (`illuminated`, Light::get_direction light.rs:93-129, get_radiance :131-150):
+ *    classic direct light at n surface points (position, facing normal). */
+int  ppm_direct_light(ppm_ctx* ctx, const double* pos3_h_or_d, const double* nrm3_h_or_d,
+                      int64_t n, double* rgb3_h_or_d);
+
 /* -- trace_ray_classic, tracer.rs:221-259 (the `rtc` binary, rtc.rs:17-38): Whitted-style
  *    tracing without a photon map: di = classic direct light + camera ambient; mirror
  *    direction without the glossy lobe; Fresnel from cos1. */

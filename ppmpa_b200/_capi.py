@@ -113,6 +113,7 @@ SIGNATURES = {
     "ppm_generate_rays": (C.c_int, [vp, u64, u32, vp]),
     "ppm_trace_rays": (C.c_int, [vp, vp, i64, i64, u64, u32, C.c_int, vp]),
     "ppm_trace_rays_classic": (C.c_int, [vp, vp, i64, i64, u64, u32, vp]),
+    "ppm_direct_light": (C.c_int, [vp, vp, vp, i64, vp]),
     "ppm_render_pass": (C.c_int, [vp, u64, u32, i64, dbl, C.c_int]),
     "ppm_render_passes": (C.c_int, [vp, u64, u32, u32, i32, i64, P(dbl), C.c_int]),
     "ppm_pass_image_read": (C.c_int, [vp, vp]),

@@ -55,6 +55,8 @@ struct ppm_ctx {
   std::string err;
   bool have_scene = false, have_camera = false, have_map = false;
   DevScene scene;
+  DBuf cull;                      // DevCull: per-scene table for the shadow-ray culling of k_direct_light
+  PrimMasks types;                // primitives by shape
   ppm_camera cam;
   // unsorted records
   DBuf r_pos, r_dir, r_wl, r_tag, counter;
@@ -164,6 +166,103 @@ int light_split(ppm_ctx* c, const int64_t* n_per_light, LightSplit* ls, int64_t*
   for (int i = c->scene.nlights; i <= PPM_MAX_LIGHTS; ++i) ls->first[i] = acc;
   *total = acc;
   return PPM_OK;
+}
+
+// Per-scene table for the conservative shadow-ray culling of k_direct_light (kernels_eye.cuh).
+// Everything here is a bound with a 1e-6 safety margin, never a quantity that enters a result.
+void build_cull(const DevScene& sc, DevCull& cu) {
+  std::memset(&cu, 0, sizeof cu);
+  auto len3 = [](const double* a) { return std::sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]); };
+  auto quad_sphere = [&](const double* p0, const double* d1, const double* d2, double* c, double* r) {
+    double s[3], d[3];
+    for (int k = 0; k < 3; ++k) { s[k] = d1[k] + d2[k]; d[k] = d1[k] - d2[k]; c[k] = p0[k] + 0.5 * s[k]; }
+    double rr = 0.5 * std::max(len3(s), len3(d));
+    *r = rr * (1.0 + 1e-6) + 1e-6 * (1.0 + len3(c));
+  };
+  for (int o = 0; o < sc.nprims; ++o) {
+    const ppm_prim& s = sc.prims[o];
+    CullPrim& cp = cu.prim[o];
+    if (s.type == PPM_SHAPE_PLAIN) {
+      cp.kind = 1;
+      double nl = std::max(1.0, len3(s.nvec));
+      double scale = nl * (1.0 + std::fabs(s.scalar));
+      cp.c[0] = 1e-6 * scale;    // D: sign margin on dist + n.p
+      cp.c[1] = 1e-2 * scale;    // gap: the light must be closer to the plane than the node by this much
+    } else if (s.type == PPM_SHAPE_SPHERE) {
+      cp.kind = 2;
+      for (int k = 0; k < 3; ++k) cp.c[k] = s.position[k];
+      cp.r = std::fabs(s.scalar) * (1.0 + 1e-6) + 1e-6 * (1.0 + len3(s.position));
+    } else if (s.type == PPM_SHAPE_POLYGON || s.type == PPM_SHAPE_PARALLELOGRAM) {
+      cp.kind = 2;               // the triangle u + v <= 1 is a subset of its parallelogram
+      quad_sphere(s.position, s.dir1, s.dir2, cp.c, &cp.r);
+    } else {
+      cp.kind = 0;               // Point: calc_distance never yields a root
+    }
+    if (cp.kind == 2 && !(cp.r < 1e150)) cp.kind = 3;   // non-finite geometry: always tested
+    const unsigned long long bit = 1ull << o;
+    if (s.type == PPM_SHAPE_PLAIN) cu.types.plain |= bit;
+    else if (s.type == PPM_SHAPE_SPHERE) cu.types.sphere |= bit;
+    else if (s.type == PPM_SHAPE_POLYGON) cu.types.poly |= bit;
+    else if (s.type == PPM_SHAPE_PARALLELOGRAM) cu.types.para |= bit;
+  }
+  for (int li = 0; li < sc.nlights; ++li) {
+    const ppm_light& l = sc.lights[li];
+    CullLight& cl = cu.light[li];
+    if (l.type != PPM_LIGHT_PARALLELOGRAM) continue;
+    quad_sphere(l.pos, l.dir1, l.dir2, cl.c, &cl.r);
+    if (!(cl.r < 1e150)) { cl.r = 1e300; }              // r^2 overflows -> the cone test is off, planes below stay valid or NaN
+    // unit normal of the light's plane and the polygons / parallelograms lying in it (the emitter's own
+    // geometry): every vertex within 1e-12 (relative to the scene scale) of the plane through the quad
+    {
+      const double cx[3] = {l.dir1[1] * l.dir2[2] - l.dir2[1] * l.dir1[2], l.dir1[2] * l.dir2[0] - l.dir2[2] * l.dir1[0],
+                            l.dir1[0] * l.dir2[1] - l.dir2[0] * l.dir1[1]};
+      const double cn = len3(cx);
+      if (cn > 0.0 && cn < 1e150) {
+        for (int k = 0; k < 3; ++k) cl.nl[k] = cx[k] / cn;
+        for (int o = 0; o < sc.nprims; ++o) {
+          const ppm_prim& s = sc.prims[o];
+          if (s.type != PPM_SHAPE_POLYGON && s.type != PPM_SHAPE_PARALLELOGRAM) continue;
+          bool in_plane = true;
+          double scale = 1.0 + len3(l.pos) + len3(s.position) + len3(s.dir1) + len3(s.dir2);
+          for (int j = 0; j < 4 && in_plane; ++j) {
+            double h = 0.0;
+            for (int k = 0; k < 3; ++k)
+              h += cl.nl[k] * ((s.position[k] + ((j & 1) ? s.dir1[k] : 0.0) + ((j & 2) ? s.dir2[k] : 0.0)) - l.pos[k]);
+            if (!(std::fabs(h) <= 1e-12 * scale)) in_plane = false;
+          }
+          if (in_plane) cl.coplanar |= 1ull << o;
+        }
+      }
+    }
+    for (int o = 0; o < sc.nprims; ++o) {
+      const ppm_prim& s = sc.prims[o];
+      if (s.type != PPM_SHAPE_PLAIN) continue;
+      double hmin = 0.0, hmax = 0.0;
+      for (int j = 0; j < 4; ++j) {
+        double h = s.scalar;
+        for (int k = 0; k < 3; ++k) h += s.nvec[k] * (l.pos[k] + ((j & 1) ? l.dir1[k] : 0.0) + ((j & 2) ? l.dir2[k] : 0.0));
+        if (j == 0 || h < hmin) hmin = h;
+        if (j == 0 || h > hmax) hmax = h;
+        if (!(h == h)) { hmin = -1e300; hmax = 1e300; break; }   // NaN: the plane is always tested
+      }
+      cl.hmin[o] = hmin; cl.hmax[o] = hmax;
+    }
+  }
+}
+int upload_cull(ppm_ctx* c) {
+  static_assert(sizeof(DevCull) < (1 << 16), "cull table");
+  DevCull cu;
+  build_cull(c->scene, cu);
+  CK(c, c->cull.ensure(sizeof cu));
+  CK(c, cudaMemcpy(c->cull.p, &cu, sizeof cu, cudaMemcpyHostToDevice));
+  c->types = cu.types;
+  return PPM_OK;
+}
+// PPM_DL_CULL=0 switches the culling off (parity tests compare both settings bit for bit)
+const DevCull* cull_arg(ppm_ctx* c) {
+  const char* e = std::getenv("PPM_DL_CULL");
+  if (e && e[0] == '0') return nullptr;
+  return c->cull.as<DevCull>();
 }
 
 // -- internal (device-resident) building blocks shared by the probes and render_pass --
@@ -472,7 +571,7 @@ int eye_front(ppm_ctx* c, cudaStream_t st, DBuf& tmpbuf, const double* drays, in
   EyeNodes nodes = {c->e_pos.as<double>(), c->e_nrm.as<double>(), c->e_w.as<double>(), c->e_prev.as<uint32_t>()};
   cudaEventRecord(c->ev[ppm_ctx::EV_B1], st);
   if (uc && nn) {
-    k_direct_light<<<nblk((int64_t)nn, 128), 128, 0, st>>>(c->scene, nodes.pos3, nodes.nrm3, nn, c->e_direct.as<double>());
+    k_direct_light<<<nblk((int64_t)nn, 128), 128, 0, st>>>(c->scene, c->types, cull_arg(c), nodes.pos3, nodes.nrm3, nn, c->e_direct.as<double>());
     KCHECK(c);
   }
   cudaEventRecord(c->ev[ppm_ctx::EV_B2], st);
@@ -553,7 +652,7 @@ void ppm_destroy(ppm_ctx* c) {
                  &c->cell_start, &c->hist, &c->bbox, &c->axis_hist, &c->m_P, &c->m_D, &c->m_orig, &c->q_key, &c->q_key2, &c->q_idx, &c->q_idx2, &c->knn_lo, &c->knn_hi, &c->knn_thr, &c->knn_cnt,
                  &c->st_in0, &c->st_in1, &c->st_out0, &c->st_out1, &c->st_out2, &c->st_out3, &c->st_out4,
                  &c->e_head, &c->e_prev, &c->e_pos, &c->e_nrm, &c->e_w, &c->e_emit, &c->e_direct, &c->e_photon, &c->e_rays,
-                 &c->pass_img, &c->accum, &c->npass, &c->stats, &c->cub_tmp2};
+                 &c->pass_img, &c->accum, &c->npass, &c->stats, &c->cub_tmp2, &c->cull};
   for (DBuf* b : all) b->release();
   for (int i = 0; i < ppm_ctx::EV_COUNT; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   cudaStreamSynchronize(c->stream2);
@@ -581,6 +680,9 @@ int ppm_scene_set(ppm_ctx* c, const ppm_prim* prims, int32_t nprims, const ppm_m
   std::memcpy(c->scene.prims, prims, sizeof(ppm_prim) * nprims);
   std::memcpy(c->scene.mats, mats, sizeof(ppm_material) * nmats);
   if (nlights) std::memcpy(c->scene.lights, lights, sizeof(ppm_light) * nlights);
+  CK(c, cudaSetDevice(c->device));
+  int rc = upload_cull(c);
+  if (rc) return rc;
   c->have_scene = true;
   return PPM_OK;
 }
@@ -775,6 +877,23 @@ int ppm_gather_knn(ppm_ctx* c, const double* pos3, const double* nrm3, int64_t n
   return PPM_OK;
 }
 
+int ppm_direct_light(ppm_ctx* c, const double* pos3, const double* nrm3, int64_t n, double* rgb3) {
+  if (!c) return PPM_ERR_ARG;
+  if (!c->have_scene) return fail(c, PPM_ERR_STATE, "scene not set");
+  if (n < 0 || (n > 0 && (!pos3 || !nrm3 || !rgb3))) return fail(c, PPM_ERR_ARG, "null argument");
+  if (n == 0) return PPM_OK;
+  CK(c, cudaSetDevice(c->device));
+  const void *dp, *dn; void* dr; int rc;
+  if ((rc = stage_in(c, pos3, (size_t)n * 24, c->st_in0, &dp))) return rc;
+  if ((rc = stage_in(c, nrm3, (size_t)n * 24, c->st_in1, &dn))) return rc;
+  if ((rc = stage_out(c, rgb3, (size_t)n * 24, c->st_out0, &dr))) return rc;
+  k_direct_light<<<nblk(n, 128), 128, 0, c->stream>>>(c->scene, c->types, cull_arg(c), (const double*)dp, (const double*)dn, n, (double*)dr);
+  KCHECK(c);
+  if ((rc = finish_out(c, rgb3, (size_t)n * 24, dr))) return rc;
+  CK(c, cudaStreamSynchronize(c->stream));
+  return PPM_OK;
+}
+
 int ppm_generate_rays(ppm_ctx* c, uint64_t seed, uint32_t pass, double* rays6) {
   if (!c) return PPM_ERR_ARG;
   if (!c->have_camera) return fail(c, PPM_ERR_STATE, "camera not set");
@@ -923,7 +1042,9 @@ int ppm_render_passes(ppm_ctx* c, uint64_t seed, uint32_t first_pass, uint32_t p
       if (rc) return fail(c, rc, "cannot create the second lane");
     }
     ppm_ctx* t = c->twin;
-    t->scene = c->scene; t->have_scene = true; t->cam = c->cam; t->have_camera = true;
+    t->scene = c->scene; t->cam = c->cam; t->have_camera = true;
+    { int rc = upload_cull(t); if (rc) return fail(c, rc, "second lane: " + t->err); }
+    t->have_scene = true;
     int rc_twin = PPM_OK, rc_main = PPM_OK;
     double tms[8] = {0}; uint64_t tct[8] = {0};
     std::thread worker([&]() {

@@ -138,38 +138,157 @@ k_eye_expand(const __grid_constant__ DevScene sc, const __grid_constant__ ppm_ca
 // thread turns that pairing into a register recurrence and reproduces the reference's
 // summation order.  Point and sun lights have a single sample, which is paired with the
 // zero -> they contribute nothing and are skipped.
+//
+// Conservative per-node culling (cull_classify).  All 25 shadow rays of a node start at the node
+// and end inside the light's quad, so most primitives can be ruled out ONCE per node instead of
+// being tested 25 times.  `illuminated` (tracer.rs:272-290) only uses the nearest hit through
+// "is there one" and "sq_ldist - |hit - p|^2 > 0.002", so a primitive may be skipped for a node
+// when, for EVERY ray from the node to a point of the light quad, one of these is certain:
+//  (a) it yields no candidate at all:
+//      - bounded primitive whose bounding sphere (radius inflated by 1e-6) lies outside the cone
+//        apex = node, through the light's bounding sphere, with a 2e-7 margin on the cosine -- ten
+//        orders above the rounding of the tests;
+//      - the plane the node itself lies on: with h = dist + n.p (the very value calc_distance
+//        computes, identical for all 25 rays) and h_g the same at the sample, den = (h - h_g)/ldist
+//        +- 1e-15, so |t| <= |h| ldist / (|h_g| - |h|) < NEARLY0 / 2 when the light is well off
+//        the plane: the root is always discarded by `t < NEARLY0`;
+//  (b) its root can never be an occluder, i.e. never makes sq_ldist - |po|^2 exceed 0.002:
+//      - a plane with the node and all four corners of the light quad on the same side by more than
+//        D = 1e-6: the computed t is < 0, or > ldist (1 + 1e-8), or > 1e8;
+//      - a polygon / parallelogram lying IN the light's plane (the emitter's own geometry): its root
+//        is t = ldist (1 +- 1e-7/(1+L)) as long as the node is off that plane by 1e-6 (1+L).
+// Primitives of class (b) can still be what makes calc_intersection return Some, so they are only
+// skipped when some plane is a CERTIFICATE: node and light strictly on one side, the light closer by
+// more than `gap` => every ray has a valid root (t > ldist >= NEARLY0) on it.  Then "no candidate
+// among the tested primitives" means "nearest hit is at or beyond the light" = lit.  Without a
+// certificate class (b) is tested like everything else.  Masks are OR-ed across the warp (testing
+// extra primitives never changes a result), so the primitive loops stay warp-uniform.
+// tests/test_gpu_parity.py::test_direct_light_cull_is_exact compares culled and unculled bit for bit.
+struct CullPrim {
+  double c[3];      // bounded: bounding-sphere centre | plane: c[0] = D, c[1] = gap
+  double r;         // bounded: inflated radius
+  int32_t kind;     // 0 = can never be hit (Point), 1 = plane, 2 = bounded (sphere, polygon, parallelogram), 3 = always tested
+  int32_t _pad;
+};
+struct CullLight {
+  double c[3], r;                                   // bounding sphere of the light quad (inflated)
+  double nl[3];                                     // unit normal of the light's plane (through c)
+  unsigned long long coplanar;                      // polygons / parallelograms lying in that plane
+  double hmin[PPM_MAX_PRIMS], hmax[PPM_MAX_PRIMS];  // planes: min / max of dist + n.corner over the quad's corners
+};
+struct DevCull {
+  PrimMasks types;                                  // primitives by shape
+  CullPrim prim[PPM_MAX_PRIMS];
+  CullLight light[PPM_MAX_LIGHTS];
+};
+__device__ __forceinline__ unsigned long long cull_classify(const DevScene& sc, const DevCull* __restrict__ cull, int li, D3 p,
+                                                            unsigned long long all, bool& cert) {
+  cert = false;
+  const CullLight& cl = cull->light[li];
+  const D3 u = ld3(cl.c) - p;
+  const double uu = dot(u, u);
+  if (!(uu < 1e6)) return all;                      // absurd scale or NaN: no culling
+  const double rl = cl.r;
+  const double ucone = uu - rl * rl;
+  const bool cone = ucone > 0.0;                    // the node is outside the light's bounding sphere
+  const double L = sqrt(uu) + rl;                   // every ldist is below this
+  const bool off_light_plane = fabs(dot(ld3(cl.nl), u)) > 1e-6 * (1.0 + L);
+  unsigned long long mask = 0, harmless = 0;
+  const int np = sc.nprims;
+  for (int o = 0; o < np; ++o) {
+    const CullPrim& cp = cull->prim[o];
+    const unsigned long long bit = 1ull << o;
+    if (cp.kind == 1) {
+      const ppm_prim& s = sc.prims[o];
+      const double num = s.scalar + dot(ld3(s.nvec), p);
+      const double D = cp.c[0], gap = cp.c[1];
+      const double hmin = cl.hmin[o], hmax = cl.hmax[o];
+      if (num > D && hmin > D) { harmless |= bit; if (hmax < num - gap) cert = true; }
+      else if (num < -D && hmax < -D) { harmless |= bit; if (hmin > num + gap) cert = true; }
+      else {
+        const double habs = hmin > D ? hmin : (hmax < -D ? -hmax : 0.0);   // light quad's distance from the plane
+        const double an = fabs(num);
+        if (!(habs > 0.0 && an * L < 0.4999e-4 * (habs - an))) mask |= bit;  // else: |t| < NEARLY0/2 for every ray
+      }
+    } else if (cp.kind == 2) {
+      if (off_light_plane && ((cl.coplanar >> o) & 1ull)) { harmless |= bit; continue; }
+      bool keep = true;
+      if (cone) {
+        const D3 v = ld3(cp.c) - p;
+        const double vv = dot(v, v);
+        const double vcone = vv - cp.r * cp.r;
+        if (vcone > 0.0 && vv < 1e12) {             // the node is outside the primitive's bounding sphere
+          // angle(u, v) > asin(rl/|u|) + asin(r/|v|)  <=>  u.v < sqrt((uu - rl^2)(vv - r^2)) - rl r
+          const double rhs = (sqrt(ucone * vcone) - rl * cp.r) - 1e-7 * (uu + vv);
+          keep = !(dot(u, v) < rhs);
+        }
+      }
+      if (keep) mask |= bit;
+    } else if (cp.kind == 3) {
+      mask |= bit;
+    }
+  }
+  if (!cert) mask |= harmless;
+  return mask;
+}
+
 __device__ __forceinline__ double ts5(unsigned i) {   // the literals 0.1, 0.3, 0.5, 0.7, 0.9 (light.rs:164-170)
   return i == 0 ? 0.1 : (i == 1 ? 0.3 : (i == 2 ? 0.5 : (i == 3 ? 0.7 : 0.9)));
 }
 __global__ void __launch_bounds__(128)
-k_direct_light(const __grid_constant__ DevScene sc, const double* __restrict__ pos3, const double* __restrict__ nrm3,
-               int64_t n, double* __restrict__ out3) {
-  const int64_t node = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (node >= n) return;
+k_direct_light(const __grid_constant__ DevScene sc, const PrimMasks types, const DevCull* __restrict__ cull,
+               const double* __restrict__ pos3, const double* __restrict__ nrm3, int64_t n, double* __restrict__ out3) {
+  __shared__ double s_gp[25][3];
+  const int64_t node0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = node0 < n;
+  const int64_t node = live ? node0 : n - 1;          // idle lanes of the last block shadow the last node (no store)
   const D3 p = ld3(pos3 + node * 3), nv = ld3(nrm3 + node * 3);
+  const unsigned long long all = sc.nprims >= 64 ? ~0ull : ((1ull << sc.nprims) - 1ull);
+  const PrimMasks tmask = types;
   D3 total = mk3(0.0, 0.0, 0.0);
   for (int li = 0; li < sc.nlights; ++li) {
     const ppm_light& l = sc.lights[li];
     if (l.type != PPM_LIGHT_PARALLELOGRAM) continue;
-    const D3 lpos = ld3(l.pos), ldir1 = ld3(l.dir1), ldir2 = ld3(l.dir2), lnv = ld3(l.nvec);
+    const D3 lnv = ld3(l.nvec);
+    __syncthreads();
+    if (threadIdx.x < 25) {
+      const unsigned s = threadIdx.x;
+      const D3 gp = (ld3(l.pos) + ts5(s / 5) * ld3(l.dir1)) + ts5(s % 5) * ld3(l.dir2);   // gen_pos, light.rs:152-154
+      s_gp[s][0] = gp.x; s_gp[s][1] = gp.y; s_gp[s][2] = gp.z;
+    }
+    __syncthreads();
+    bool cert = false;
+    unsigned long long mask = all;
+    if (cull) {
+      mask = cull_classify(sc, cull, li, p, all, cert);
+      const unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)mask);
+      const unsigned hi = __reduce_or_sync(0xffffffffu, (unsigned)(mask >> 32));
+      mask = ((unsigned long long)hi << 32) | lo;
+    }
+    PrimMasks pm;
+    pm.plain = mask & tmask.plain; pm.sphere = mask & tmask.sphere; pm.poly = mask & tmask.poly; pm.para = mask & tmask.para;
     const double PI4 = PPM_PI * 4.0;
     const double lnum = 2.0 * l.flux * 0.2 * 0.2;           // 2 * flux * PARA_DIV * PARA_DIV, light.rs:142
     D3 rad = mk3(0.0, 0.0, 0.0);
     bool have_prev = false;
     double dprev = 0.0;
     for (unsigned s = 0; s < 25; ++s) {
-      const D3 gp = (lpos + ts5(s / 5) * ldir1) + ts5(s % 5) * ldir2;   // gen_pos, light.rs:152-154
+      const D3 gp = mk3(s_gp[s][0], s_gp[s][1], s_gp[s][2]);
       const D3 d = gp - p;
       if (!(dot(lnv, d) < 0.0)) continue;                   // light.rs:112
       D3 ld;
       if (!normalize(d, ld)) continue;                      // tracer.rs:275-276
       const double cos0 = dot(nv, ld);
       if (cos0 < 0.0) continue;
-      Isect is;
-      if (!nearest_hit(sc, p, ld, is)) continue;            // no hit counts as occluded, tracer.rs:282
       const double sq_ldist = dot(d, d);
-      const D3 po = is.pos - p;
-      if (sq_ldist - dot(po, po) > 0.002) continue;
+      D3 hp;
+      const int hit = nearest_hit_masked(sc, p, ld, pm, hp);
+      if (hit == 1) {
+        const D3 po = hp - p;
+        if (sq_ldist - dot(po, po) > 0.002) continue;
+      } else if (hit == 2 || !cert) {
+        continue;                                           // no hit counts as occluded, tracer.rs:282
+      }                                                     // hit == 0 with a certificate: nearest hit beyond the light
       if (have_prev) {
         const double l0 = lnum / (PI4 * dprev);
         const double cc = cos0 * cos0;
@@ -180,7 +299,7 @@ k_direct_light(const __grid_constant__ DevScene sc, const double* __restrict__ p
     }
     total = total + rad;
   }
-  st3(out3 + node * 3, total);
+  if (live) st3(out3 + node * 3, total);
 }
 
 // ---- combine + accumulate ------------------------------------------------------------

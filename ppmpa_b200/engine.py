@@ -277,6 +277,14 @@ class Engine:
         self._ck(lib.ppm_trace_rays_classic(self._h, _ptr(rays6), n, first_pixel, seed, npass, _ptr(out)))
         return out
 
+    def direct_light(self, pos3, nrm3):
+        """get_radiance_from_light summed over the lights (tracer.rs:136-141, 263-290) at surface points."""
+        pos3 = _f64(pos3, (3,)); nrm3 = _f64(nrm3, (3,))
+        n = pos3.shape[0]
+        out = np.empty((n, 3))
+        self._ck(lib.ppm_direct_light(self._h, _ptr(pos3), _ptr(nrm3), n, _ptr(out)))
+        return out
+
     # ---- whole pass --------------------------------------------------------------
     def iteration(self, seed, npass, nphoton, radius2, uc=True):
         """One PPM-PA pass (ppmpa.rs:74-84), accumulated on the device."""

@@ -356,6 +356,121 @@ def test_direct_light_matches_oracle(engine, oracle, name):
     assert np.mean(np.any(err > RTOL, axis=1)) <= 2e-3
 
 
+ADVERSARIAL_SCENE = """
+# open scene (no enclosing room), tilted planes with un-normalised normals, a triangle, spheres,
+# two area lights (one tilted, one tiny): stresses every branch of the shadow-ray culling
+light:
+  - type: parallelogram
+    color: [ 1.0, 0.8, 0.6 ]
+    flux: 5.0
+    position: [ -0.5, 3.0, 2.5 ]
+    dir1: [ 1.0, 0.2, 0.0 ]
+    dir2: [ 0.0, 0.3, 1.0 ]
+  - type: parallelogram
+    color: [ 0.2, 0.3, 1.0 ]
+    flux: 2.0
+    position: [ 1.5, 1.0, 0.0 ]
+    dir1: [ 0.0, 0.05, 0.0 ]
+    dir2: [ 0.0, 0.0, 0.05 ]
+material:
+  - type: solid
+    name: m
+    emittance: [ 0.0, 0.0, 0.0 ]
+    reflectance: [ 0.5, 0.5, 0.5 ]
+    transmittance: [ 0.0, 0.0, 0.0 ]
+    specularrefl: [ 0.0, 0.0, 0.0 ]
+    ior: [ 0.0, 0.0, 0.0 ]
+    diffuseness: 1.0
+    metalness: 0.0
+    smoothness: 0.0
+object:
+  - type: plain
+    name: floor
+    normal: [ 0.0, 1.0, 0.0 ]
+    position: [ 0.0, 0.0, 0.0 ]
+    material: m
+  - type: plain
+    name: tilted
+    normal: [ 3.0, 1.0, 0.5 ]
+    position: [ -2.0, 0.0, 0.0 ]
+    material: m
+  - type: plain
+    name: above_the_light
+    normal: [ 0.0, -2.0, 0.1 ]
+    position: [ 0.0, 3.6, 0.0 ]
+    material: m
+  - type: sphere
+    name: ball
+    center: [ 0.2, 1.0, 2.8 ]
+    radius: 0.7
+    material: m
+  - type: sphere
+    name: small_ball
+    center: [ 1.0, 1.0, 0.3 ]
+    radius: 0.2
+    material: m
+  - type: polygon
+    name: tri
+    pos1: [ -1.0, 1.5, 2.0 ]
+    pos2: [ 1.0, 2.0, 2.2 ]
+    pos3: [ -0.5, 1.8, 4.0 ]
+    material: m
+  - type: parallelogram
+    name: card
+    pos1: [ -1.5, 0.0, 1.0 ]
+    pos2: [ -1.5, 1.0, 1.0 ]
+    pos3: [ -1.2, 0.0, 2.0 ]
+    material: m
+"""
+
+
+def _cull_probe_nodes(engine, seed):
+    """Surface points as the eye paths produce them (hits of random rays) plus free points with
+    arbitrary normals, points a hair above/below every kind of surface and points around the lights."""
+    rays = random_rays(30000, seed)
+    hit, t, pos, nrm, io = engine.calc_intersection(rays)
+    ok = hit >= 0
+    pos, nrm = pos[ok], nrm[ok]
+    rng = np.random.default_rng(seed + 1)
+    free = rng.uniform([-2.5, -0.5, -6.5], [2.5, 4.5, 5.5], size=(15000, 3))
+    fn = rng.normal(size=(15000, 3)); fn /= np.linalg.norm(fn, axis=1, keepdims=True)
+    # offsets straddling the culling margins (1e-6 sign margin, 1e-2 certificate gap, NEARLY0)
+    k = min(len(pos), 12000)
+    off = rng.choice([0.0, 1e-12, -1e-12, 1e-7, -1e-7, 9e-7, 1.1e-6, -1.1e-6, 1e-4, -1e-4, 5e-3, 1.1e-2, -1.1e-2], size=(k, 1))
+    near = pos[:k] + off * nrm[:k]
+    lights = rng.uniform([-1.2, 2.8, 2.3], [1.2, 4.2, 3.7], size=(6000, 3))
+    ln = rng.normal(size=(6000, 3)); ln /= np.linalg.norm(ln, axis=1, keepdims=True)
+    P3 = np.concatenate([pos, free, near, lights])
+    N3 = np.concatenate([nrm, fn, nrm[:k], ln])
+    return np.ascontiguousarray(P3), np.ascontiguousarray(N3)
+
+
+@pytest.mark.parametrize("name", SCENES + ["adversarial"])
+def test_direct_light_cull_is_exact(engine, oracle, name, tmp_path, monkeypatch):
+    """k_direct_light's conservative per-node culling must not change a single bit: compare with the
+    culling switched off (PPM_DL_CULL=0) and with the oracle's get_radiance_from_light."""
+    if name == "adversarial":
+        f = tmp_path / "adversarial.scene"
+        f.write_text(ADVERSARIAL_SCENE)
+        sc = P.read_scene(str(f))
+    else:
+        sc = load_scene(name)
+    engine.set_scene(sc)
+    pos, nrm = _cull_probe_nodes(engine, 77)
+    monkeypatch.setenv("PPM_DL_CULL", "1")
+    a = engine.direct_light(pos, nrm)
+    monkeypatch.setenv("PPM_DL_CULL", "0")
+    b = engine.direct_light(pos, nrm)
+    monkeypatch.delenv("PPM_DL_CULL")
+    assert np.array_equal(a, b), f"{np.sum(np.any(a != b, axis=1))} of {len(a)} nodes differ between culled and unculled"
+    sub = np.random.default_rng(5).choice(len(pos), 12000, replace=False)
+    o = oracle.direct_light(sc, pos[sub], nrm[sub])
+    if name not in ("ex-sunwindow",):
+        assert o.max() > 0 and np.count_nonzero(np.any(o > 0, axis=1)) > 500
+    assert np.array_equal(a[sub] > 0, o > 0)           # same lit/occluded decisions
+    assert_rel(a[sub], o, 1e-12)
+
+
 @pytest.mark.parametrize("name", [None, "ex-glassbox", "sample1", "mirror-ball", "ex-sunwindow"])
 def test_trace_rays_classic_parity(engine, oracle, name):
     """trace_ray_classic (tracer.rs:221-259, the `rtc` renderer): deterministic given the rays."""
