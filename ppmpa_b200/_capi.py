@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libppm_b200.so")
+# PPM_B200_LIB selects another build of the same library (kernel tuning experiments)
+LIB_PATH = os.environ.get("PPM_B200_LIB") or os.path.join(_HERE, "libppm_b200.so")
 
 PPM_OK = 0
 ERR_NAMES = {0: "PPM_OK", -1: "PPM_ERR_ARG", -2: "PPM_ERR_STATE", -3: "PPM_ERR_CUDA", -4: "PPM_ERR_CAPACITY",

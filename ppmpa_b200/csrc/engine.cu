@@ -20,6 +20,7 @@
 #include <cub/device/device_scan.cuh>
 
 #include <algorithm>
+#include <array>
 #include <chrono>
 #include <cmath>
 #include <cstdlib>
@@ -55,6 +56,7 @@ struct ppm_ctx {
   std::string err;
   bool have_scene = false, have_camera = false, have_map = false;
   DevScene scene;
+  DBuf dl_dbg;
   DBuf cull;                      // DevCull: per-scene table for the shadow-ray culling of k_direct_light
   PrimMasks types;                // primitives by shape
   ppm_camera cam;
@@ -87,8 +89,11 @@ struct ppm_ctx {
   cudaEvent_t ev[EV_COUNT] = {nullptr};
   bool timed = false;             // record the phase events (render_pass only)
   uint64_t launches = 0;
-  ppm_ctx* twin = nullptr;        // second lane on the same GPU (ppm_render_passes), owned
+  std::vector<ppm_ctx*> twins;    // further lanes on the same GPU (ppm_render_passes), owned
 };
+
+#define PPM_DEFAULT_LANES 2
+#define PPM_MAX_LANES 8
 
 namespace {
 
@@ -263,6 +268,26 @@ const DevCull* cull_arg(ppm_ctx* c) {
   const char* e = std::getenv("PPM_DL_CULL");
   if (e && e[0] == '0') return nullptr;
   return c->cull.as<DevCull>();
+}
+
+int launch_direct_light(ppm_ctx* c, cudaStream_t st, const double* dpos, const double* dnrm, int64_t n, double* dout) {
+  unsigned long long* dbg = nullptr;
+  const bool stats = std::getenv("PPM_DL_STATS") != nullptr;
+  if (stats) {
+    CK(c, c->dl_dbg.ensure(32));
+    CK(c, cudaMemsetAsync(c->dl_dbg.p, 0, 32, st));
+    dbg = c->dl_dbg.as<unsigned long long>();
+  }
+  k_direct_light<<<nblk(n, 128), 128, 0, st>>>(c->scene, c->types, cull_arg(c), dpos, dnrm, n, dout, dbg);
+  KCHECK(c);
+  if (stats) {
+    unsigned long long h[4];
+    CK(c, cudaMemcpyAsync(h, dbg, 32, cudaMemcpyDeviceToHost, st));
+    CK(c, cudaStreamSynchronize(st));
+    if (h[0]) std::fprintf(stderr, "[ppm direct light] nodes=%llu tested prims/node: own %.3f, warp union %.3f; certificate %.1f%%\n", h[0],
+                           (double)h[1] / h[0], (double)h[2] / h[0], 100.0 * h[3] / h[0]);
+  }
+  return PPM_OK;
 }
 
 // -- internal (device-resident) building blocks shared by the probes and render_pass --
@@ -571,8 +596,8 @@ int eye_front(ppm_ctx* c, cudaStream_t st, DBuf& tmpbuf, const double* drays, in
   EyeNodes nodes = {c->e_pos.as<double>(), c->e_nrm.as<double>(), c->e_w.as<double>(), c->e_prev.as<uint32_t>()};
   cudaEventRecord(c->ev[ppm_ctx::EV_B1], st);
   if (uc && nn) {
-    k_direct_light<<<nblk((int64_t)nn, 128), 128, 0, st>>>(c->scene, c->types, cull_arg(c), nodes.pos3, nodes.nrm3, nn, c->e_direct.as<double>());
-    KCHECK(c);
+    int rc = launch_direct_light(c, st, nodes.pos3, nodes.nrm3, nn, c->e_direct.as<double>());
+    if (rc) return rc;
   }
   cudaEventRecord(c->ev[ppm_ctx::EV_B2], st);
   *nn_out = nn;
@@ -645,14 +670,15 @@ int ppm_create(int device, ppm_ctx** out) {
 
 void ppm_destroy(ppm_ctx* c) {
   if (!c) return;
-  if (c->twin) { ppm_destroy(c->twin); c->twin = nullptr; }
+  for (ppm_ctx* t : c->twins) ppm_destroy(t);
+  c->twins.clear();
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   DBuf* all[] = {&c->r_pos, &c->r_dir, &c->r_wl, &c->r_tag, &c->counter, &c->keys, &c->keys2, &c->vals, &c->vals2, &c->cub_tmp,
                  &c->cell_start, &c->hist, &c->bbox, &c->axis_hist, &c->m_P, &c->m_D, &c->m_orig, &c->q_key, &c->q_key2, &c->q_idx, &c->q_idx2, &c->knn_lo, &c->knn_hi, &c->knn_thr, &c->knn_cnt,
                  &c->st_in0, &c->st_in1, &c->st_out0, &c->st_out1, &c->st_out2, &c->st_out3, &c->st_out4,
                  &c->e_head, &c->e_prev, &c->e_pos, &c->e_nrm, &c->e_w, &c->e_emit, &c->e_direct, &c->e_photon, &c->e_rays,
-                 &c->pass_img, &c->accum, &c->npass, &c->stats, &c->cub_tmp2, &c->cull};
+                 &c->pass_img, &c->accum, &c->npass, &c->stats, &c->cub_tmp2, &c->cull, &c->dl_dbg};
   for (DBuf* b : all) b->release();
   for (int i = 0; i < ppm_ctx::EV_COUNT; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   cudaStreamSynchronize(c->stream2);
@@ -887,8 +913,7 @@ int ppm_direct_light(ppm_ctx* c, const double* pos3, const double* nrm3, int64_t
   if ((rc = stage_in(c, pos3, (size_t)n * 24, c->st_in0, &dp))) return rc;
   if ((rc = stage_in(c, nrm3, (size_t)n * 24, c->st_in1, &dn))) return rc;
   if ((rc = stage_out(c, rgb3, (size_t)n * 24, c->st_out0, &dr))) return rc;
-  k_direct_light<<<nblk(n, 128), 128, 0, c->stream>>>(c->scene, c->types, cull_arg(c), (const double*)dp, (const double*)dn, n, (double*)dr);
-  KCHECK(c);
+  if ((rc = launch_direct_light(c, c->stream, (const double*)dp, (const double*)dn, n, (double*)dr))) return rc;
   if ((rc = finish_out(c, rgb3, (size_t)n * 24, dr))) return rc;
   CK(c, cudaStreamSynchronize(c->stream));
   return PPM_OK;
@@ -1026,55 +1051,70 @@ int ppm_render_passes(ppm_ctx* c, uint64_t seed, uint32_t first_pass, uint32_t p
   if (npass < 0 || (npass > 0 && !radius2)) return fail(c, PPM_ERR_ARG, "bad pass batch");
   if (npass == 0) return PPM_OK;
   if (!c->have_scene || !c->have_camera) return fail(c, PPM_ERR_STATE, "scene and camera must be set");
-  const char* lanes_env = std::getenv("PPM_LANES");
-  const bool two = npass >= 2 && !(lanes_env && lanes_env[0] == '1');
+  // lanes: this context plus (lanes - 1) internal twins on the same GPU; PPM_LANES overrides the default
+  int lanes = PPM_DEFAULT_LANES;
+  if (const char* e = std::getenv("PPM_LANES")) lanes = std::atoi(e);
+  lanes = std::max(1, std::min(lanes, (int)PPM_MAX_LANES));
+  lanes = std::min<int>(lanes, npass);
   double ms_sum[8] = {0}; uint64_t ct_sum[8] = {0};
-  auto add_stats = [&](ppm_ctx* x) { for (int k = 0; k < 8; ++k) { ms_sum[k] += x->ms[k]; ct_sum[k] += x->counters[k]; } };
-  if (!two) {
+  if (lanes == 1) {
     for (int32_t i = 0; i < npass; ++i) {
       int rc = ppm_render_pass(c, seed, first_pass + (uint32_t)i * pass_stride, nphoton, radius2[i], uc);
       if (rc) return rc;
-      add_stats(c);
+      for (int k = 0; k < 8; ++k) { ms_sum[k] += c->ms[k]; ct_sum[k] += c->counters[k]; }
     }
   } else {
-    if (!c->twin) {
-      int rc = ppm_create(c->device, &c->twin);
-      if (rc) return fail(c, rc, "cannot create the second lane");
-    }
-    ppm_ctx* t = c->twin;
-    t->scene = c->scene; t->cam = c->cam; t->have_camera = true;
-    { int rc = upload_cull(t); if (rc) return fail(c, rc, "second lane: " + t->err); }
-    t->have_scene = true;
-    int rc_twin = PPM_OK, rc_main = PPM_OK;
-    double tms[8] = {0}; uint64_t tct[8] = {0};
-    std::thread worker([&]() {
-      cudaSetDevice(t->device);
-      for (int32_t i = 1; i < npass; i += 2) {
-        rc_twin = ppm_render_pass(t, seed, first_pass + (uint32_t)i * pass_stride, nphoton, radius2[i], uc);
-        if (rc_twin) return;
-        for (int k = 0; k < 8; ++k) { tms[k] += t->ms[k]; tct[k] += t->counters[k]; }
+    std::vector<ppm_ctx*> lane(lanes, nullptr);
+    lane[0] = c;
+    for (int j = 1; j < lanes; ++j) {
+      if ((int)c->twins.size() < j) {
+        ppm_ctx* t = nullptr;
+        int rc = ppm_create(c->device, &t);
+        if (rc) return fail(c, rc, "cannot create another lane");
+        c->twins.push_back(t);
       }
-    });
-    for (int32_t i = 0; i < npass; i += 2) {
-      rc_main = ppm_render_pass(c, seed, first_pass + (uint32_t)i * pass_stride, nphoton, radius2[i], uc);
-      if (rc_main) break;
-      add_stats(c);
+      ppm_ctx* t = c->twins[j - 1];
+      t->scene = c->scene; t->cam = c->cam; t->have_camera = true;
+      { int rc = upload_cull(t); if (rc) return fail(c, rc, "lane: " + t->err); }
+      t->have_scene = true;
+      lane[j] = t;
     }
-    worker.join();
-    if (rc_main) return rc_main;
-    if (rc_twin) return fail(c, rc_twin, std::string("second lane: ") + t->err);
-    for (int k = 0; k < 8; ++k) { ms_sum[k] += tms[k]; ct_sum[k] += tct[k]; }
-    // merge the twin's accumulator (and pass counter) into ours; last pass image follows the last pass
+    std::vector<int> rcs(lanes, PPM_OK);
+    std::vector<std::array<double, 8>> lms(lanes);
+    std::vector<std::array<uint64_t, 8>> lct(lanes);
+    auto run_lane = [&](int j) {
+      ppm_ctx* x = lane[j];
+      cudaSetDevice(x->device);
+      lms[j].fill(0.0); lct[j].fill(0);
+      for (int32_t i = j; i < npass; i += lanes) {
+        rcs[j] = ppm_render_pass(x, seed, first_pass + (uint32_t)i * pass_stride, nphoton, radius2[i], uc);
+        if (rcs[j]) return;
+        for (int k = 0; k < 8; ++k) { lms[j][k] += x->ms[k]; lct[j][k] += x->counters[k]; }
+      }
+    };
+    std::vector<std::thread> workers;
+    for (int j = 1; j < lanes; ++j) workers.emplace_back(run_lane, j);
+    run_lane(0);
+    for (auto& w : workers) w.join();
+    if (rcs[0]) return rcs[0];
+    for (int j = 1; j < lanes; ++j)
+      if (rcs[j]) return fail(c, rcs[j], std::string("lane: ") + lane[j]->err);
+    for (int j = 0; j < lanes; ++j)
+      for (int k = 0; k < 8; ++k) { ms_sum[k] += lms[j][k]; ct_sum[k] += lct[j][k]; }
+    // merge the twins' accumulators (and pass counters) into ours; last pass image follows the last pass
     CK(c, cudaSetDevice(c->device));
     const int64_t nacc = (int64_t)c->accum_pixels * 3 + 1;
-    CK(c, cudaStreamSynchronize(t->stream));
-    k_accum_merge<<<nblk(nacc, 256), 256, 0, c->stream>>>(c->accum.as<double>(), t->accum.as<double>(), nacc);
-    KCHECK(c);
-    if (((npass - 1) & 1) == 1)
-      CK(c, cudaMemcpyAsync(c->pass_img.p, t->pass_img.p, (size_t)c->accum_pixels * 24, cudaMemcpyDeviceToDevice, c->stream));
+    for (int j = 1; j < lanes; ++j) {
+      CK(c, cudaStreamSynchronize(lane[j]->stream));
+      k_accum_merge<<<nblk(nacc, 256), 256, 0, c->stream>>>(c->accum.as<double>(), lane[j]->accum.as<double>(), nacc);
+      KCHECK(c);
+    }
+    const int last_lane = (npass - 1) % lanes;
+    if (last_lane != 0)
+      CK(c, cudaMemcpyAsync(c->pass_img.p, lane[last_lane]->pass_img.p, (size_t)c->accum_pixels * 24, cudaMemcpyDeviceToDevice, c->stream));
     CK(c, cudaStreamSynchronize(c->stream));
   }
-  std::memcpy(c->ms, ms_sum, sizeof ms_sum);          // batch totals (sum over the passes of both lanes)
+  std::memcpy(c->ms, ms_sum, sizeof ms_sum);          // batch totals (sum over the passes of all lanes)
   std::memcpy(c->counters, ct_sum, sizeof ct_sum);
   return PPM_OK;
 }

@@ -51,7 +51,10 @@ struct EyeStack {
   int medium, depth;
   uint32_t node;
 };
-__global__ void __launch_bounds__(128)
+#ifndef PPM_EYE_MINB
+#define PPM_EYE_MINB 6
+#endif
+__global__ void __launch_bounds__(128, PPM_EYE_MINB)
 k_eye_expand(const __grid_constant__ DevScene sc, const __grid_constant__ ppm_camera cam, const double* __restrict__ rays6,
              int64_t n, int64_t first_pixel, uint64_t seed, uint32_t pass, EyeNodes nodes, uint32_t cap,
              uint32_t* __restrict__ head, double* __restrict__ emit3, unsigned long long* __restrict__ pool_counter,
@@ -235,9 +238,12 @@ __device__ __forceinline__ unsigned long long cull_classify(const DevScene& sc, 
 __device__ __forceinline__ double ts5(unsigned i) {   // the literals 0.1, 0.3, 0.5, 0.7, 0.9 (light.rs:164-170)
   return i == 0 ? 0.1 : (i == 1 ? 0.3 : (i == 2 ? 0.5 : (i == 3 ? 0.7 : 0.9)));
 }
-__global__ void __launch_bounds__(128)
+// 64 registers (8 CTAs per SM): the kernel is latency bound, so occupancy beats the ~100 bytes of spills
+// (96 registers / 5 CTAs: 2.1 ms, 64 / 8: 1.35 ms on config 2).
+__global__ void __launch_bounds__(128, 8)
 k_direct_light(const __grid_constant__ DevScene sc, const PrimMasks types, const DevCull* __restrict__ cull,
-               const double* __restrict__ pos3, const double* __restrict__ nrm3, int64_t n, double* __restrict__ out3) {
+               const double* __restrict__ pos3, const double* __restrict__ nrm3, int64_t n, double* __restrict__ out3,
+               unsigned long long* __restrict__ dbg) {
   __shared__ double s_gp[25][3];
   const int64_t node0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = node0 < n;
@@ -261,9 +267,14 @@ k_direct_light(const __grid_constant__ DevScene sc, const PrimMasks types, const
     unsigned long long mask = all;
     if (cull) {
       mask = cull_classify(sc, cull, li, p, all, cert);
+      const unsigned long long own = mask;
       const unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)mask);
       const unsigned hi = __reduce_or_sync(0xffffffffu, (unsigned)(mask >> 32));
       mask = ((unsigned long long)hi << 32) | lo;
+      if (dbg && live) {                                      // diagnostic (PPM_DL_STATS): primitives tested per node
+        atomicAdd(dbg, 1ull); atomicAdd(dbg + 1, (unsigned long long)__popcll(own));
+        atomicAdd(dbg + 2, (unsigned long long)__popcll(mask)); atomicAdd(dbg + 3, cert ? 1ull : 0ull);
+      }
     }
     PrimMasks pm;
     pm.plain = mask & tmask.plain; pm.sphere = mask & tmask.sphere; pm.poly = mask & tmask.poly; pm.para = mask & tmask.para;

@@ -55,7 +55,10 @@ struct RecBuf {
 // from a global ticket counter (one atomic per warp per refill) instead of idling until the
 // longest path of its warp ends.  One loop iteration = (optional) emission + one bounce.
 // Records are appended with one atomic per warp (warp-aggregated compaction).
-__global__ void __launch_bounds__(128)
+#ifndef PPM_TRACE_MINB
+#define PPM_TRACE_MINB 6
+#endif
+__global__ void __launch_bounds__(128, PPM_TRACE_MINB)
 k_trace_photons(const __grid_constant__ DevScene sc, const __grid_constant__ LightSplit ls, uint64_t seed, uint32_t pass,
                 int uc, int64_t n, RecBuf rec, unsigned long long* __restrict__ counter, unsigned long long cap,
                 unsigned long long* __restrict__ ticket) {
