@@ -234,7 +234,7 @@ __device__ __forceinline__ bool nearest_hit(const DevScene& sc, D3 pos, D3 dir, 
 // conservative per-node classification in kernels_eye.cuh (cull_classify).  The loops run type by type
 // instead of in object order, so the reference's tie rule (stable sort: equal t -> earliest candidate)
 // is kept explicitly by consider_tie; with all primitives in the masks this is exactly nearest_hit.
-struct PrimMasks { unsigned long long plain, sphere, poly, para; };
+struct PrimMasks { unsigned long long plain, sphere, poly, para; int nwords, _pad; };   // nwords: 1 if the scene has <= 32 primitives
 __device__ __forceinline__ void consider_tie(double t, int o, double& best_t, int& best_o) {
   if (t < PPM_NEARLY0) return;
   if (best_o < 0 || t < best_t || (t == best_t && o < best_o)) { best_t = t; best_o = o; }
@@ -287,7 +287,7 @@ __device__ __forceinline__ void consider_polygon_tie(double l, D3 p0, D3 d1, D3 
 // Returns 0 = no candidate among the masked primitives, 1 = hit (hit_pos set), 2 = calc_intersection is None
 // because get_normal failed.
 #define PPM_FOR_EACH_BIT(mask64, o)                                                        \
-  _Pragma("unroll 1") for (int w__ = 0; w__ < 2; ++w__)                                    \
+  if (mask64) _Pragma("unroll 1") for (int w__ = 0; w__ < pm.nwords; ++w__)                \
     for (unsigned m__ = (unsigned)((mask64) >> (32 * w__)), o = 0; m__ && ((o = __ffs(m__) - 1 + 32 * w__), true); m__ &= m__ - 1)
 __device__ __forceinline__ int nearest_hit_masked(const DevScene& sc, D3 pos, D3 dir, const PrimMasks& pm, D3& hit_pos) {
   double best_t = 0.0;

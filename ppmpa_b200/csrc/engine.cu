@@ -210,6 +210,7 @@ void build_cull(const DevScene& sc, DevCull& cu) {
     else if (s.type == PPM_SHAPE_POLYGON) cu.types.poly |= bit;
     else if (s.type == PPM_SHAPE_PARALLELOGRAM) cu.types.para |= bit;
   }
+  cu.types.nwords = sc.nprims > 32 ? 2 : 1;
   for (int li = 0; li < sc.nlights; ++li) {
     const ppm_light& l = sc.lights[li];
     CullLight& cl = cu.light[li];

@@ -278,6 +278,7 @@ k_direct_light(const __grid_constant__ DevScene sc, const PrimMasks types, const
     }
     PrimMasks pm;
     pm.plain = mask & tmask.plain; pm.sphere = mask & tmask.sphere; pm.poly = mask & tmask.poly; pm.para = mask & tmask.para;
+    pm.nwords = tmask.nwords; pm._pad = 0;
     const double PI4 = PPM_PI * 4.0;
     const double lnum = 2.0 * l.flux * 0.2 * 0.2;           // 2 * flux * PARA_DIV * PARA_DIV, light.rs:142
     D3 rad = mk3(0.0, 0.0, 0.0);

@@ -506,6 +506,31 @@ def test_render_pass_matches_oracle_and_accumulates(engine, oracle):
     assert np.array_equal(engine.image_mean(), acc / 2.0)
 
 
+@pytest.mark.parametrize("xres,yres,rows", [(1024, 1024, (640, 644)), (1920, 1080, (700, 703))])
+def test_full_size_pass_rows_match_oracle(engine, oracle, xres, yres, rows):
+    """BASELINE configs 2 and 5 at FULL size (1 M photons, 1024^2 / 1920x1080): the oracle traces the same
+    1 M photon paths and the image rows that cross the glass box; the rest of the image is covered by
+    size-independent properties (finite, non-negative, accumulator == pass image, record count)."""
+    sc = load_scene("ex-glassbox")
+    cam = P.read_camera(os.path.join(EX, "camera0.scr"), xreso=xres, yreso=yres, pfilter=K.FILTER_NONE, progressive=1)
+    engine.set_scene(sc); engine.set_camera(cam)
+    engine.accum_reset()
+    r2 = 0.06 ** 2
+    engine.iteration(SEED, 5, 1_000_000, r2, uc=True)
+    img = engine.pass_image()
+    ms, ct = engine.last_pass_stats()
+    o, _, ostats = oracle.render_pass(sc, cam, SEED, 5, 1_000_000, r2, True, rows[0], rows[1])
+    assert ct["emitted"] == 1_000_000 and ct["stored"] == int(ostats[0])
+    assert int(ostats[2]) > 1.5 * (rows[1] - rows[0]) * xres            # the rows do cross the glass box (eye-path trees)
+    g = img.reshape(yres, xres, 3)[rows[0]:rows[1]].reshape(-1, 3)
+    err = np.abs(g - o) / np.maximum(np.maximum(np.abs(o), np.abs(g)), 1e-300)
+    assert np.mean(np.any(err > 1e-6, axis=1)) <= 5e-3
+    assert np.median(err) < 1e-12
+    assert np.isfinite(img).all() and img.min() >= 0.0 and img.max() > 0.0
+    acc, n = engine.accum_read()
+    assert n == 1 and np.array_equal(acc, img)
+
+
 def test_two_contexts_are_independent():
     a, b = P.Engine(0), P.Engine(0)
     try:
