@@ -23,11 +23,14 @@
 
 // The whole scene travels as a __grid_constant__ kernel parameter (<32 KB):
 // primitive loops are warp-uniform, so every read is a constant-cache broadcast.
+// primitives by shape (bit o = primitive o); nwords = 1 if the scene has <= 32 primitives
+struct PrimMasks { unsigned long long plain, sphere, poly, para; int nwords, _pad; };
 struct DevScene {
   int32_t nprims, nmats, nlights, _pad;
   ppm_prim prims[PPM_MAX_PRIMS];
   ppm_material mats[PPM_MAX_MATS];
   ppm_light lights[PPM_MAX_LIGHTS];
+  PrimMasks types;                 // filled by ppm_scene_set
 };
 static_assert(sizeof(DevScene) < 32000, "scene must fit the kernel parameter space");
 
@@ -102,8 +105,12 @@ struct Philox {
 // ---------------------------------------------------------------------------
 // Nearest hit: calc_intersection, tracer.rs:306-350.
 // Every object is tested; roots with t >= NEARLY0 are kept in (object, root)
-// order and the reference stable-sorts by t and takes the first, i.e. the
-// minimum t with ties going to the earliest candidate -> strict '<' scan.
+// order and the reference stable-sorts by t and takes the first (:335-336), i.e.
+// the minimum t with ties going to the earliest candidate.  The scan below runs
+// shape by shape (bit loops over the scene's per-shape masks, no per-primitive
+// dispatch) instead of in object order, so consider() keeps the tie rule
+// explicitly: equal t -> lower object index (within one object the roots come
+// in order, and the later equal root does not replace the earlier one).
 // ---------------------------------------------------------------------------
 struct Isect {
   D3 pos, nvec;
@@ -113,7 +120,7 @@ struct Isect {
 
 __device__ __forceinline__ void consider(double t, int o, double& best_t, int& best_o) {
   if (t < PPM_NEARLY0) return;          // `if i.0 < NEARLY0 { continue; }`
-  if (best_o < 0 || t < best_t) { best_t = t; best_o = o; }
+  if (best_o < 0 || t < best_t || (t == best_t && o < best_o)) { best_t = t; best_o = o; }
 }
 
 // consider(num / den) without the IEEE division whenever the outcome is certain.
@@ -185,34 +192,47 @@ __device__ __forceinline__ void consider_polygon(double l, D3 p0, D3 d1, D3 d2, 
   consider_ratio(c, det, o, best_t, best_o);
 }
 
+#define PPM_FOR_EACH_BIT(mask64, o)                                                        \
+  if (mask64) _Pragma("unroll 1") for (int w__ = 0; w__ < pm.nwords; ++w__)                \
+    for (unsigned m__ = (unsigned)((mask64) >> (32 * w__)), o = 0; m__ && ((o = __ffs(m__) - 1 + 32 * w__), true); m__ &= m__ - 1)
+__device__ __forceinline__ void scan_prims(const DevScene& sc, const PrimMasks& pm, D3 pos, D3 dir, double& best_t, int& best_o) {
+  PPM_FOR_EACH_BIT(pm.plain, o) {
+    // geometry.rs:170-177: t = (dist + n.pos) / -cos0
+    const ppm_prim& s = sc.prims[o];
+    D3 n = ld3(s.nvec);
+    double cos0 = dot(n, dir);
+    if (cos0 != 0.0) consider_ratio(s.scalar + dot(n, pos), -cos0, (int)o, best_t, best_o);
+  }
+  PPM_FOR_EACH_BIT(pm.para, o) {
+    // geometry.rs:195-202, l = 2 (parallelogram), :141-143
+    const ppm_prim& s = sc.prims[o];
+    consider_polygon(2.0, ld3(s.position), ld3(s.dir1), ld3(s.dir2), pos, dir, (int)o, best_t, best_o);
+  }
+  PPM_FOR_EACH_BIT(pm.poly, o) {
+    const ppm_prim& s = sc.prims[o];
+    consider_polygon(1.0, ld3(s.position), ld3(s.dir1), ld3(s.dir2), pos, dir, (int)o, best_t, best_o);
+  }
+  PPM_FOR_EACH_BIT(pm.sphere, o) {
+    // geometry.rs:179-193
+    const ppm_prim& s = sc.prims[o];
+    D3 oc = ld3(s.position) - pos;
+    double t0 = dot(oc, dir);
+    double rad = s.scalar;
+    double t1 = rad * rad - (dot(oc, oc) - (t0 * t0));
+    if (t1 > 0.0) {
+      double t2 = sqrt(t1);
+      if (t2 == 0.0) consider(t0, (int)o, best_t, best_o);
+      else { consider(t0 - t2, (int)o, best_t, best_o); consider(t0 + t2, (int)o, best_t, best_o); }
+    }
+  }
+}
+
+// Nearest hit: calc_intersection, tracer.rs:306-350.  Every object is tested; roots with t >= NEARLY0
+// are kept and the reference stable-sorts by t and takes the first.
 __device__ __forceinline__ bool nearest_hit(const DevScene& sc, D3 pos, D3 dir, Isect& is) {
   double best_t = 0.0;
   int best_o = -1;
-  const int np = sc.nprims;
-  for (int o = 0; o < np; ++o) {
-    const ppm_prim& s = sc.prims[o];
-    const int type = s.type;
-    if (type == PPM_SHAPE_PLAIN) {
-      // geometry.rs:170-177: t = (dist + n.pos) / -cos0
-      D3 n = ld3(s.nvec);
-      double cos0 = dot(n, dir);
-      if (cos0 != 0.0) consider_ratio(s.scalar + dot(n, pos), -cos0, o, best_t, best_o);
-    } else if (type == PPM_SHAPE_SPHERE) {
-      // geometry.rs:179-193
-      D3 oc = ld3(s.position) - pos;
-      double t0 = dot(oc, dir);
-      double rad = s.scalar;
-      double t1 = rad * rad - (dot(oc, oc) - (t0 * t0));
-      if (t1 > 0.0) {
-        double t2 = sqrt(t1);
-        if (t2 == 0.0) consider(t0, o, best_t, best_o);
-        else { consider(t0 - t2, o, best_t, best_o); consider(t0 + t2, o, best_t, best_o); }
-      }
-    } else if (type == PPM_SHAPE_POLYGON || type == PPM_SHAPE_PARALLELOGRAM) {
-      // geometry.rs:195-202, l = 1 (triangle) / 2 (parallelogram), :141-143
-      consider_polygon(type == PPM_SHAPE_POLYGON ? 1.0 : 2.0, ld3(s.position), ld3(s.dir1), ld3(s.dir2), pos, dir, o, best_t, best_o);
-    }
-  }
+  scan_prims(sc, sc.types, pos, dir, best_t, best_o);
   if (best_o < 0) return false;
   const ppm_prim& s = sc.prims[best_o];
   D3 p = pos + dir * best_t;            // Ray::target, geometry.rs:56-58
@@ -228,96 +248,15 @@ __device__ __forceinline__ bool nearest_hit(const DevScene& sc, D3 pos, D3 dir, 
   return true;
 }
 
-// Shadow-ray variant of nearest_hit for k_direct_light: the same candidate tests, but only over the
-// primitives whose bit is set in the per-type masks, and only the data `illuminated` (tracer.rs:272-290)
-// consumes: whether calc_intersection returns Some, and the hit position.  The masks come from the
-// conservative per-node classification in kernels_eye.cuh (cull_classify).  The loops run type by type
-// instead of in object order, so the reference's tie rule (stable sort: equal t -> earliest candidate)
-// is kept explicitly by consider_tie; with all primitives in the masks this is exactly nearest_hit.
-struct PrimMasks { unsigned long long plain, sphere, poly, para; int nwords, _pad; };   // nwords: 1 if the scene has <= 32 primitives
-__device__ __forceinline__ void consider_tie(double t, int o, double& best_t, int& best_o) {
-  if (t < PPM_NEARLY0) return;
-  if (best_o < 0 || t < best_t || (t == best_t && o < best_o)) { best_t = t; best_o = o; }
-}
-__device__ __forceinline__ void consider_ratio_tie(double num, double den, int o, double& best_t, int& best_o) {
-  const double an = fabs(num), ad = fabs(den);
-  if (num == 0.0 && ad > 0.0 && ad < 1e300) return;
-  if (an > 0.0 && ad > 0.0 && an < 1e300 && ad < 1e300) {
-    if ((num < 0.0) != (den < 0.0)) return;
-    if (an < ad * (PPM_NEARLY0 * (1.0 - PPM_GUARD))) return;
-    if (best_o >= 0 && best_t < 1e300 && an > (ad * best_t) * (1.0 + PPM_GUARD)) return;
-  }
-  consider_tie(num / den, o, best_t, best_o);
-}
-__device__ __forceinline__ void consider_polygon_tie(double l, D3 p0, D3 d1, D3 d2, D3 p, D3 d, int o, double& best_t, int& best_o) {
-  const D3 re2 = cross(d, d2);
-  const double det = dot(re2, d1);
-  if (det == 0.0) return;
-  const D3 pp = p - p0;
-  const double a = dot(re2, pp);
-  const double ad = fabs(det);
-  const double ad_hi = ad * (1.0 + PPM_GUARD), ad_lo = ad * (1.0 - PPM_GUARD);
-  bool exact = !(ad < 1e300 && ad > 1e-300);
-  if (!exact) {
-    const int cu = classify01(a, det, ad, ad_hi, ad_lo);
-    if (cu < 0) return;
-    exact = cu == 0;
-  }
-  const D3 te1 = cross(pp, d1);
-  const double b = dot(te1, d);
-  if (!exact) {
-    const int cv = classify01(b, det, ad, ad_hi, ad_lo);
-    if (cv < 0) return;
-    exact = cv == 0;
-    if (!exact) {
-      const double sum = fabs(a) + fabs(b);
-      if (sum > ad_hi * l) return;
-      exact = !(sum < ad_lo * l);
-    }
-  }
-  const double c = dot(te1, d2);
-  if (exact) {
-    const double u = a / det, v = b / det, t = c / det;
-    if (u < 0.0 || u > 1.0 || v < 0.0 || v > 1.0 || u + v > l) return;
-    consider_tie(t, o, best_t, best_o);
-    return;
-  }
-  consider_ratio_tie(c, det, o, best_t, best_o);
-}
+// Shadow-ray variant for k_direct_light: only the primitives in `pm` (the conservative per-node
+// classification of kernels_eye.cuh, cull_classify) and only the data `illuminated` (tracer.rs:272-290)
+// consumes: whether calc_intersection returns Some, and the hit position.
 // Returns 0 = no candidate among the masked primitives, 1 = hit (hit_pos set), 2 = calc_intersection is None
 // because get_normal failed.
-#define PPM_FOR_EACH_BIT(mask64, o)                                                        \
-  if (mask64) _Pragma("unroll 1") for (int w__ = 0; w__ < pm.nwords; ++w__)                \
-    for (unsigned m__ = (unsigned)((mask64) >> (32 * w__)), o = 0; m__ && ((o = __ffs(m__) - 1 + 32 * w__), true); m__ &= m__ - 1)
 __device__ __forceinline__ int nearest_hit_masked(const DevScene& sc, D3 pos, D3 dir, const PrimMasks& pm, D3& hit_pos) {
   double best_t = 0.0;
   int best_o = -1;
-  PPM_FOR_EACH_BIT(pm.plain, o) {
-    const ppm_prim& s = sc.prims[o];
-    D3 n = ld3(s.nvec);
-    double cos0 = dot(n, dir);
-    if (cos0 != 0.0) consider_ratio_tie(s.scalar + dot(n, pos), -cos0, (int)o, best_t, best_o);
-  }
-  PPM_FOR_EACH_BIT(pm.para, o) {
-    const ppm_prim& s = sc.prims[o];
-    consider_polygon_tie(2.0, ld3(s.position), ld3(s.dir1), ld3(s.dir2), pos, dir, (int)o, best_t, best_o);
-  }
-  PPM_FOR_EACH_BIT(pm.poly, o) {
-    const ppm_prim& s = sc.prims[o];
-    consider_polygon_tie(1.0, ld3(s.position), ld3(s.dir1), ld3(s.dir2), pos, dir, (int)o, best_t, best_o);
-  }
-  PPM_FOR_EACH_BIT(pm.sphere, o) {
-    const ppm_prim& s = sc.prims[o];
-    D3 oc = ld3(s.position) - pos;
-    double t0 = dot(oc, dir);
-    double rad = s.scalar;
-    double t1 = rad * rad - (dot(oc, oc) - (t0 * t0));
-    if (t1 > 0.0) {
-      double t2 = sqrt(t1);
-      if (t2 == 0.0) consider_tie(t0, (int)o, best_t, best_o);
-      else { consider_tie(t0 - t2, (int)o, best_t, best_o); consider_tie(t0 + t2, (int)o, best_t, best_o); }
-    }
-  }
+  scan_prims(sc, pm, pos, dir, best_t, best_o);
   if (best_o < 0) return 0;
   hit_pos = pos + dir * best_t;
   const ppm_prim& s = sc.prims[best_o];

@@ -58,7 +58,6 @@ struct ppm_ctx {
   DevScene scene;
   DBuf dl_dbg;
   DBuf cull;                      // DevCull: per-scene table for the shadow-ray culling of k_direct_light
-  PrimMasks types;                // primitives by shape
   ppm_camera cam;
   // unsorted records
   DBuf r_pos, r_dir, r_wl, r_tag, counter;
@@ -204,13 +203,7 @@ void build_cull(const DevScene& sc, DevCull& cu) {
       cp.kind = 0;               // Point: calc_distance never yields a root
     }
     if (cp.kind == 2 && !(cp.r < 1e150)) cp.kind = 3;   // non-finite geometry: always tested
-    const unsigned long long bit = 1ull << o;
-    if (s.type == PPM_SHAPE_PLAIN) cu.types.plain |= bit;
-    else if (s.type == PPM_SHAPE_SPHERE) cu.types.sphere |= bit;
-    else if (s.type == PPM_SHAPE_POLYGON) cu.types.poly |= bit;
-    else if (s.type == PPM_SHAPE_PARALLELOGRAM) cu.types.para |= bit;
   }
-  cu.types.nwords = sc.nprims > 32 ? 2 : 1;
   for (int li = 0; li < sc.nlights; ++li) {
     const ppm_light& l = sc.lights[li];
     CullLight& cl = cu.light[li];
@@ -261,7 +254,6 @@ int upload_cull(ppm_ctx* c) {
   build_cull(c->scene, cu);
   CK(c, c->cull.ensure(sizeof cu));
   CK(c, cudaMemcpy(c->cull.p, &cu, sizeof cu, cudaMemcpyHostToDevice));
-  c->types = cu.types;
   return PPM_OK;
 }
 // PPM_DL_CULL=0 switches the culling off (parity tests compare both settings bit for bit)
@@ -279,7 +271,7 @@ int launch_direct_light(ppm_ctx* c, cudaStream_t st, const double* dpos, const d
     CK(c, cudaMemsetAsync(c->dl_dbg.p, 0, 32, st));
     dbg = c->dl_dbg.as<unsigned long long>();
   }
-  k_direct_light<<<nblk(n, 128), 128, 0, st>>>(c->scene, c->types, cull_arg(c), dpos, dnrm, n, dout, dbg);
+  k_direct_light<<<nblk(n, 128), 128, 0, st>>>(c->scene, cull_arg(c), dpos, dnrm, n, dout, dbg);
   KCHECK(c);
   if (stats) {
     unsigned long long h[4];
@@ -707,6 +699,14 @@ int ppm_scene_set(ppm_ctx* c, const ppm_prim* prims, int32_t nprims, const ppm_m
   std::memcpy(c->scene.prims, prims, sizeof(ppm_prim) * nprims);
   std::memcpy(c->scene.mats, mats, sizeof(ppm_material) * nmats);
   if (nlights) std::memcpy(c->scene.lights, lights, sizeof(ppm_light) * nlights);
+  c->scene.types.nwords = nprims > 32 ? 2 : 1;
+  for (int o = 0; o < nprims; ++o) {
+    const unsigned long long bit = 1ull << o;
+    if (prims[o].type == PPM_SHAPE_PLAIN) c->scene.types.plain |= bit;
+    else if (prims[o].type == PPM_SHAPE_SPHERE) c->scene.types.sphere |= bit;
+    else if (prims[o].type == PPM_SHAPE_POLYGON) c->scene.types.poly |= bit;
+    else if (prims[o].type == PPM_SHAPE_PARALLELOGRAM) c->scene.types.para |= bit;
+  }
   CK(c, cudaSetDevice(c->device));
   int rc = upload_cull(c);
   if (rc) return rc;

@@ -180,7 +180,6 @@ struct CullLight {
   double hmin[PPM_MAX_PRIMS], hmax[PPM_MAX_PRIMS];  // planes: min / max of dist + n.corner over the quad's corners
 };
 struct DevCull {
-  PrimMasks types;                                  // primitives by shape
   CullPrim prim[PPM_MAX_PRIMS];
   CullLight light[PPM_MAX_LIGHTS];
 };
@@ -241,7 +240,7 @@ __device__ __forceinline__ double ts5(unsigned i) {   // the literals 0.1, 0.3, 
 // 64 registers (8 CTAs per SM): the kernel is latency bound, so occupancy beats the ~100 bytes of spills
 // (96 registers / 5 CTAs: 2.1 ms, 64 / 8: 1.35 ms on config 2).
 __global__ void __launch_bounds__(128, 8)
-k_direct_light(const __grid_constant__ DevScene sc, const PrimMasks types, const DevCull* __restrict__ cull,
+k_direct_light(const __grid_constant__ DevScene sc, const DevCull* __restrict__ cull,
                const double* __restrict__ pos3, const double* __restrict__ nrm3, int64_t n, double* __restrict__ out3,
                unsigned long long* __restrict__ dbg) {
   __shared__ double s_gp[25][3];
@@ -250,7 +249,7 @@ k_direct_light(const __grid_constant__ DevScene sc, const PrimMasks types, const
   const int64_t node = live ? node0 : n - 1;          // idle lanes of the last block shadow the last node (no store)
   const D3 p = ld3(pos3 + node * 3), nv = ld3(nrm3 + node * 3);
   const unsigned long long all = sc.nprims >= 64 ? ~0ull : ((1ull << sc.nprims) - 1ull);
-  const PrimMasks tmask = types;
+  const PrimMasks tmask = sc.types;
   D3 total = mk3(0.0, 0.0, 0.0);
   for (int li = 0; li < sc.nlights; ++li) {
     const ppm_light& l = sc.lights[li];
