@@ -459,6 +459,18 @@ struct EyeNode {
 __device__ __forceinline__ void eye_node(const DevScene& sc, const Isect& is, D3 in_dir, int medium, Philox& rng, EyeNode& nd,
                                          bool classic = false) {
   const ppm_material& m = sc.mats[is.mat];
+  if (m.surface == PPM_SURF_SIMPLE && m.p0 == 1.0) {
+    // Purely diffuse Simple surface: ks = (1 - p0) f = 0 and kt = (1 - p0)(1 - metalness) f2 = 0 whatever the
+    // Fresnel term, so neither child is ever traced (tracer.rs:152-171 multiply their radiance by zero) and
+    // kd does not depend on the directions: skip the glossy lobe, the refraction and both pow() calls.  The
+    // node's random draws come from its own Philox stream, so not drawing them changes nothing else.
+    nd.kd = m.p0 * (ld3(m.color_a) * (1.0 / PPM_PI));
+    nd.ks = nd.kt = mk3(0.0, 0.0, 0.0);
+    nd.rdir = nd.tdir = mk3(1.0, 0.0, 0.0);
+    nd.reflect = nd.refract = false;
+    nd.t_medium = -1;
+    return;
+  }
   D3 rdir0; double cos1;
   specular_reflection(is.nvec, in_dir, rdir0, cos1);
   nd.rdir = classic ? rdir0 : reflection_glossy(is.nvec, rdir0, surf_power_glossy(m), rng);
