@@ -279,7 +279,7 @@ def run_gpu(args):
     # reference's NPARA processes -- two engine contexts per GPU are driven by two host threads, each doing
     # whole steps through the public API.
     import threading
-    E2E_LANES = max(1, env_int("PPM_E2E_LANES", 2))
+    E2E_LANES = max(1, env_int("PPM_E2E_LANES", 4))
     engs = [eng] + [P.Engine(local) for _ in range(E2E_LANES - 1)]
     bufs = [torch.empty((npix, 3), dtype=torch.float64).pin_memory().numpy() for _ in range(E2E_LANES)]
     h2d = (C.sizeof(P._capi.Prim) * sc.nprims + C.sizeof(P._capi.Material) * sc.nmats + C.sizeof(P._capi.Light) * sc.nlights

@@ -267,18 +267,25 @@ int launch_direct_light(ppm_ctx* c, cudaStream_t st, const double* dpos, const d
   unsigned long long* dbg = nullptr;
   const bool stats = std::getenv("PPM_DL_STATS") != nullptr;
   if (stats) {
-    CK(c, c->dl_dbg.ensure(32));
-    CK(c, cudaMemsetAsync(c->dl_dbg.p, 0, 32, st));
+    CK(c, c->dl_dbg.ensure(160));
+    CK(c, cudaMemsetAsync(c->dl_dbg.p, 0, 160, st));
     dbg = c->dl_dbg.as<unsigned long long>();
   }
   k_direct_light<<<nblk(n, 128), 128, 0, st>>>(c->scene, cull_arg(c), dpos, dnrm, n, dout, dbg);
   KCHECK(c);
   if (stats) {
-    unsigned long long h[4];
-    CK(c, cudaMemcpyAsync(h, dbg, 32, cudaMemcpyDeviceToHost, st));
+    unsigned long long h[20];
+    CK(c, cudaMemcpyAsync(h, dbg, 160, cudaMemcpyDeviceToHost, st));
     CK(c, cudaStreamSynchronize(st));
     if (h[0]) std::fprintf(stderr, "[ppm direct light] nodes=%llu tested prims/node: own %.3f, warp union %.3f; certificate %.1f%%\n", h[0],
                            (double)h[1] / h[0], (double)h[2] / h[0], 100.0 * h[3] / h[0]);
+    if (h[0]) {
+      std::fprintf(stderr, "[ppm direct light] nodes by tested prims 0..7+: own");
+      for (int k = 0; k < 8; ++k) std::fprintf(stderr, " %.1f%%", 100.0 * h[4 + k] / h[0]);
+      std::fprintf(stderr, " | warp union");
+      for (int k = 0; k < 8; ++k) std::fprintf(stderr, " %.1f%%", 100.0 * h[12 + k] / h[0]);
+      std::fprintf(stderr, "\n");
+    }
   }
   return PPM_OK;
 }

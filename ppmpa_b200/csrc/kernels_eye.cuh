@@ -273,6 +273,7 @@ k_direct_light(const __grid_constant__ DevScene sc, const DevCull* __restrict__ 
       if (dbg && live) {                                      // diagnostic (PPM_DL_STATS): primitives tested per node
         atomicAdd(dbg, 1ull); atomicAdd(dbg + 1, (unsigned long long)__popcll(own));
         atomicAdd(dbg + 2, (unsigned long long)__popcll(mask)); atomicAdd(dbg + 3, cert ? 1ull : 0ull);
+        atomicAdd(dbg + 4 + min(__popcll(own), 7), 1ull); atomicAdd(dbg + 12 + min(__popcll(mask), 7), 1ull);
       }
     }
     PrimMasks pm;
