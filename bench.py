@@ -56,7 +56,7 @@ def load_workload():
 
 def base_config(n_gpus):
     return {"workload": WORKLOAD, "pixels_per_pass": XRES * YRES, "photons_per_pass": NPHOTON,
-            "passes_per_step": 1, "parallelism": f"pass-sharded x{n_gpus}; within a GPU alternate passes run on two lanes (ppm_render_passes)",
+            "passes_per_step": 1, "parallelism": f"pass-sharded x{n_gpus}; within a GPU passes run round-robin on two lanes (ppm_render_passes)",
             "radius": "iterator.rb schedule indexed by the per-rank step, so per-GPU work is identical at every N",
             "l2": "per-pass working set (~280 MB of records, sorted map, node lists, images; regenerated every pass) "
                   "exceeds the 126 MB L2; nothing is reused between timed passes"}
@@ -276,8 +276,8 @@ def run_gpu(args):
     # ---- end-to-end through the C ABI with host buffers --------------------------------
     # Every step: ppm_scene_set + ppm_camera_set (host structs -> device), one whole pass, and the pass
     # image read back into pinned host memory (what `ppmpa` prints).  Passes are independent, so -- like the
-    # reference's NPARA processes -- two engine contexts per GPU are driven by two host threads, each doing
-    # whole steps through the public API.
+    # reference's NPARA = 4 processes (util/iterator.rb:18) -- E2E_LANES engine contexts per GPU are driven by as
+    # many host threads, each doing whole steps through the public API (PPM_E2E_LANES, default 4).
     import threading
     E2E_LANES = max(1, env_int("PPM_E2E_LANES", 4))
     engs = [eng] + [P.Engine(local) for _ in range(E2E_LANES - 1)]
