@@ -366,7 +366,10 @@ __device__ __forceinline__ int decide_wavelength(const double c[3], double p) { 
   if (p < c[0] + c[1]) return PPM_WL_GREEN;
   return PPM_WL_BLUE;
 }
-__device__ __forceinline__ void generate_photon(const ppm_light& l, Philox& rng, int& wl, D3& pos, D3& dir) {
+// defer = true: for an area light the direction (the LAST draws of the emission) is not sampled here;
+// the function returns true and the caller samples diffuse_reflection(l.nvec) from the same stream.
+template <bool DEFER>
+__device__ __forceinline__ bool generate_photon_t(const ppm_light& l, Philox& rng, int& wl, D3& pos, D3& dir) {
   wl = decide_wavelength(l.color, rng.range(0.0, 1.0));       // select_wavelength, light.rs:157-160
   if (l.type == PPM_LIGHT_POINT) {
     pos = ld3(l.pos);
@@ -379,10 +382,18 @@ __device__ __forceinline__ void generate_photon(const ppm_light& l, Philox& rng,
   } else {
     double t1 = rng.range(0.0, 1.0);
     double t2 = rng.range(0.0, 1.0);
-    if (l.type == PPM_LIGHT_PARALLELOGRAM) dir = diffuse_reflection(ld3(l.nvec), rng);
-    else dir = ld3(l.dir);
     pos = (ld3(l.pos) + t1 * ld3(l.dir1)) + t2 * ld3(l.dir2);
+    if (l.type == PPM_LIGHT_PARALLELOGRAM) {
+      if (DEFER) { dir = ld3(l.nvec); return true; }
+      dir = diffuse_reflection(ld3(l.nvec), rng);
+    } else {
+      dir = ld3(l.dir);
+    }
   }
+  return false;
+}
+__device__ __forceinline__ void generate_photon(const ppm_light& l, Philox& rng, int& wl, D3& pos, D3& dir) {
+  generate_photon_t<false>(l, rng, wl, pos, dir);
 }
 
 // ---------------------------------------------------------------------------
@@ -393,15 +404,19 @@ __device__ __forceinline__ void generate_photon(const ppm_light& l, Philox& rng,
 __device__ __forceinline__ double medium_ior(const DevScene& sc, int medium, int wl) {
   return medium < 0 ? 1.0 : sc.mats[medium].ior[wl];
 }
+// need_diffuse: set when the photon goes on diffusely; the direction -- diffuse_reflection(is.nvec), always the
+// LAST draws of the bounce -- is then left to the caller (k_trace_photons samples it together with the emission
+// directions of freshly regenerated lanes, so the expensive sincos/sqrt/normalize runs on full warps).
 __device__ __forceinline__ bool photon_bounce(const DevScene& sc, const Isect& is, int wl, D3 in_dir, Philox& rng,
-                                              int& medium, D3& out_dir) {
+                                              int& medium, D3& out_dir, bool& need_diffuse) {
+  need_diffuse = false;
   const ppm_material& m = sc.mats[is.mat];
   if (m.surface == PPM_SURF_SIMPLE) {
     // roughness() of a Simple surface is its *diffuseness* (surface.rs:358-367)
     if (roulette(m.p0, rng) == 0) {
       // reflect_diff, tracer.rs:83-92
       if (roulette(m.color_a[wl], rng) != 0) return false;
-      out_dir = diffuse_reflection(is.nvec, rng);
+      need_diffuse = true;
       return true;
     }
     // reflect_spec, tracer.rs:94-109
@@ -432,7 +447,7 @@ __device__ __forceinline__ bool photon_bounce(const DevScene& sc, const Isect& i
     double f = schlick(m.color_b[wl], c);
     if (roulette(f, rng) == 0) { out_dir = rdir; return true; }
     if (roulette(m.color_a[wl], rng) == 1) return false;
-    if (roulette(m.p0, rng) == 0) { out_dir = diffuse_reflection(is.nvec, rng); return true; }
+    if (roulette(m.p0, rng) == 0) { need_diffuse = true; return true; }
     if (!has_t) return false;
     medium = is.mat;              // `if m == true { m0 } else { &is1.mate }`, tracer.rs:68
     out_dir = tdir;

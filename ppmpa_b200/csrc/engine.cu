@@ -62,6 +62,7 @@ struct ppm_ctx {
   // unsorted records
   DBuf r_pos, r_dir, r_wl, r_tag, counter;
   uint64_t n_rec = 0;
+  int tag_bits = 38;              // bits of the largest record tag (photon << 4 | depth) of the current photon set
   double power = 0.0;
   // map
   DBuf keys, keys2, vals, vals2, cub_tmp, cell_start, hist, bbox, axis_hist;
@@ -160,6 +161,12 @@ MapSoA mapsoa(ppm_ctx* c) {
   MapSoA m;
   m.P = c->m_P.as<double2>(); m.D = c->m_D.as<double2>(); m.orig = c->m_orig.as<uint32_t>();
   return m;
+}
+// bits needed for the tags (index << 4 | depth) of `count` photons; cell bits go above them in the sort key
+int tag_bits_for(uint64_t count) {
+  int b = 1;
+  while (b < 38 && (1ull << b) < count) ++b;
+  return std::min(38, b + 4);
 }
 int light_split(ppm_ctx* c, const int64_t* n_per_light, LightSplit* ls, int64_t* total) {
   int64_t acc = 0;
@@ -298,6 +305,7 @@ int trace_photons_launch(ppm_ctx* c, uint64_t seed, uint32_t pass, int uc, const
   if (rc) return rc;
   uint64_t cap = (uint64_t)total * PPM_MAX_TRACE;
   if (cap == 0) cap = 1;
+  c->tag_bits = tag_bits_for((uint64_t)total);
   rc = ensure_records(c, cap);
   if (rc) return rc;
   CK(c, cudaMemsetAsync(c->counter.p, 0, 16, c->stream));     // [0] record counter, [1] photon ticket
@@ -443,12 +451,12 @@ int do_map_build(ppm_ctx* c, double radius2) {
   CK(c, c->m_P.ensure(nn * 32)); CK(c, c->m_D.ensure(nn * 32)); CK(c, c->m_orig.ensure(nn * 4));
   tr.mark("alloc_map");
   if (n > 0) {
-    k_cell_key<<<nblk((int64_t)n, 256), 256, 0, c->stream>>>(g, c->r_pos.as<double>(), c->r_tag.as<uint64_t>(), n,
+    k_cell_key<<<nblk((int64_t)n, 256), 256, 0, c->stream>>>(g, c->r_pos.as<double>(), c->r_tag.as<uint64_t>(), n, c->tag_bits,
                                                             c->keys.as<uint64_t>(), c->vals.as<uint32_t>(), c->hist.as<uint32_t>());
     KCHECK(c);
     int cell_bits = 1;
     while ((1ull << cell_bits) < (unsigned long long)g.ncells) ++cell_bits;
-    int end_bit = std::min(64, 38 + cell_bits);
+    int end_bit = std::min(64, c->tag_bits + cell_bits);
     size_t tmp = 0;
     CK(c, cub::DeviceRadixSort::SortPairs(nullptr, tmp, c->keys.as<uint64_t>(), c->keys2.as<uint64_t>(), c->vals.as<uint32_t>(),
                                           c->vals2.as<uint32_t>(), (int64_t)n, 0, end_bit, c->stream));
@@ -824,6 +832,7 @@ int ppm_photons_import(ppm_ctx* c, const ppm_photon* in, uint64_t n, double powe
     CK(c, cudaStreamSynchronize(c->stream));
   }
   c->n_rec = n; c->power = power; c->have_map = false;
+  c->tag_bits = tag_bits_for(n);
   return PPM_OK;
 }
 

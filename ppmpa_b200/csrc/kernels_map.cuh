@@ -67,16 +67,16 @@ __device__ __forceinline__ int cell_coord(const Grid& g, double p, int ax) {
   double f = floor((p - g.org[ax]) * g.inv_cell);
   return f < 0.0 ? 0 : (f > (double)nmax ? nmax : (int)f);   // NaN -> 0
 }
-// sort key = (cell << 38) | (tag & (2^38-1)): photons ordered by cell, then by
-// (photon index, depth) -> the map is bit-reproducible whatever order the
-// tracing atomics produced.
-__global__ void k_cell_key(Grid g, const double* __restrict__ pos3, const uint64_t* __restrict__ tag, uint64_t n,
+// sort key = (cell << tag_bits) | tag: photons ordered by cell, then by (photon index, depth) -> the map
+// is bit-reproducible whatever order the tracing atomics produced.  tag_bits = bits of the largest tag
+// of this photon set (24 for 1 M photons), so the radix sort runs over tag_bits + cell bits only.
+__global__ void k_cell_key(Grid g, const double* __restrict__ pos3, const uint64_t* __restrict__ tag, uint64_t n, int tag_bits,
                            uint64_t* __restrict__ keys, uint32_t* __restrict__ vals, uint32_t* __restrict__ hist) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   int cx = cell_coord(g, pos3[i * 3], 0), cy = cell_coord(g, pos3[i * 3 + 1], 1), cz = cell_coord(g, pos3[i * 3 + 2], 2);
   uint32_t c = ((uint32_t)cz * (uint32_t)g.ny + (uint32_t)cy) * (uint32_t)g.nx + (uint32_t)cx;
-  keys[i] = ((uint64_t)c << 38) | (tag[i] & ((1ull << 38) - 1ull));
+  keys[i] = ((uint64_t)c << tag_bits) | (tag[i] & ((1ull << tag_bits) - 1ull));
   vals[i] = (uint32_t)i;
   atomicAdd(&hist[c], 1u);
 }

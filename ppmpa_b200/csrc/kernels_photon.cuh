@@ -65,7 +65,7 @@ k_trace_photons(const __grid_constant__ DevScene sc, const __grid_constant__ Lig
   const unsigned FULL = 0xffffffffu;
   const unsigned lane = threadIdx.x & 31u;
   const unsigned lt_mask = (1u << lane) - 1u;
-  bool alive = false, exhausted = false;
+  bool alive = false, exhausted = false, need_dir = false;
   int64_t idx = 0;
   int wl = 0, medium = -1, depth = 0;
   D3 pos = mk3(0, 0, 0), dir = mk3(1, 0, 0);
@@ -83,7 +83,7 @@ k_trace_photons(const __grid_constant__ DevScene sc, const __grid_constant__ Lig
         if (i < n) {
           idx = i;
           rng = Philox(seed, pass, PPM_DOMAIN_PHOTON, (uint64_t)i, 0);
-          generate_photon(sc.lights[light_of(ls, sc.nlights, i)], rng, wl, pos, dir);
+          need_dir = generate_photon_t<true>(sc.lights[light_of(ls, sc.nlights, i)], rng, wl, pos, dir);   // dir = normal if deferred
           medium = -1; depth = 0; alive = true;
         } else {
           exhausted = true;
@@ -91,6 +91,9 @@ k_trace_photons(const __grid_constant__ DevScene sc, const __grid_constant__ Lig
       }
     }
     if (!__any_sync(FULL, alive)) break;
+    // ---- deferred diffuse directions: emission of the lanes regenerated above and the diffuse bounces of
+    //      the previous iteration (`dir` holds the normal to sample about) --------------------------------------
+    if (need_dir) { dir = diffuse_reflection(dir, rng); need_dir = false; }
     // ---- one bounce ----------------------------------------------------------------------
     Isect is;
     bool store = false;
@@ -102,10 +105,12 @@ k_trace_photons(const __grid_constant__ DevScene sc, const __grid_constant__ Lig
       } else {
         store = (uc == 0 || l > 0) && surf_store_photon(sc.mats[is.mat]);
         D3 nd;
-        const bool go = photon_bounce(sc, is, wl, dir, rng, medium, nd);
+        bool diffuse;
+        const bool go = photon_bounce(sc, is, wl, dir, rng, medium, nd, diffuse);
         pos = is.pos;
         ++depth;
-        if (go && depth < PPM_MAX_TRACE) dir = nd; else alive = false;   // `if l >= MAX_TRACE { return vec![] }`
+        if (go && depth < PPM_MAX_TRACE) { dir = diffuse ? is.nvec : nd; need_dir = diffuse; }
+        else alive = false;                                              // `if l >= MAX_TRACE { return vec![] }`
       }
     }
     const unsigned m = __ballot_sync(FULL, store);
