@@ -67,7 +67,7 @@ struct ppm_ctx {
   // map
   DBuf keys, keys2, vals, vals2, cub_tmp, cell_start, hist, bbox, axis_hist;
   DBuf m_P, m_D, m_orig;
-  DBuf q_key, q_key2, q_idx, q_idx2;
+  DBuf q_key, q_key2, q_idx, q_idx2, heavy;
   DBuf knn_lo, knn_hi, knn_thr, knn_cnt;
   Grid grid;
   double r2 = 0.0;
@@ -505,7 +505,19 @@ int gather_launch(ppm_ctx* c, const double* dpos, const double* dnrm, int64_t n,
   const uint32_t* cs = c->cell_start.as<uint32_t>();
   const uint32_t* qk = c->q_key2.as<uint32_t>();
   const uint32_t* qx = c->q_idx2.as<uint32_t>();
-#define GATHER_LAUNCH(F, M) k_gather<F, M><<<nblk(n, B), B, 0, c->stream>>>(c->grid, cs, mapsoa(c), qk, qx, dpos, dnrm, n, c->power, c->r2, r2q, drgb, dcounts, dsumk)
+  // heavy groups: the light kernel hands them over through a device-side list, the persistent
+  // heavy kernel (a no-op when the list is empty) splits each over 8 warps
+  HeavyGroup* hv = nullptr;
+  unsigned int* nhv = nullptr;
+  const uint32_t hcap = 1u << 16;
+  if (!(std::getenv("PPM_GATHER_HEAVY") && std::getenv("PPM_GATHER_HEAVY")[0] == '0')) {
+    CK(c, c->heavy.ensure((size_t)hcap * sizeof(HeavyGroup) + 16));
+    nhv = c->heavy.as<unsigned int>();
+    hv = (HeavyGroup*)(c->heavy.as<char>() + 16);
+    CK(c, cudaMemsetAsync(nhv, 0, 4, c->stream));
+  }
+#define GATHER_LAUNCH(F, M) k_gather<F, M><<<nblk(n, B), B, 0, c->stream>>>(c->grid, cs, mapsoa(c), qk, qx, dpos, dnrm, n, c->power, c->r2, r2q, drgb, dcounts, dsumk, hv, nhv, hcap)
+#define HEAVY_LAUNCH(F, M) k_gather_heavy<F, M><<<c->sm_count * 2, GATHER_HEAVY_WARPS * 32, 0, c->stream>>>(c->grid, cs, mapsoa(c), qx, dpos, dnrm, n, c->power, c->r2, r2q, drgb, dcounts, dsumk, hv, nhv, hcap)
   if (mode == 2) GATHER_LAUNCH(PPM_FILTER_NONE, 2);
   else if (mode == 1) {
     switch (filter) {
@@ -522,6 +534,24 @@ int gather_launch(ppm_ctx* c, const double* dpos, const double* dnrm, int64_t n,
   }
 #undef GATHER_LAUNCH
   KCHECK(c);
+  if (hv) {
+    if (mode == 2) HEAVY_LAUNCH(PPM_FILTER_NONE, 2);
+    else if (mode == 1) {
+      switch (filter) {
+        case PPM_FILTER_NONE: HEAVY_LAUNCH(PPM_FILTER_NONE, 1); break;
+        case PPM_FILTER_CONE: HEAVY_LAUNCH(PPM_FILTER_CONE, 1); break;
+        default:              HEAVY_LAUNCH(PPM_FILTER_GAUSS, 1); break;
+      }
+    } else {
+      switch (filter) {
+        case PPM_FILTER_NONE: HEAVY_LAUNCH(PPM_FILTER_NONE, 0); break;
+        case PPM_FILTER_CONE: HEAVY_LAUNCH(PPM_FILTER_CONE, 0); break;
+        default:              HEAVY_LAUNCH(PPM_FILTER_GAUSS, 0); break;
+      }
+    }
+    KCHECK(c);
+  }
+#undef HEAVY_LAUNCH
   return PPM_OK;
 }
 int launch_gather(ppm_ctx* c, const double* dpos, const double* dnrm, int64_t n, int filter, double* drgb, uint32_t* dcounts,
@@ -686,7 +716,7 @@ void ppm_destroy(ppm_ctx* c) {
                  &c->cell_start, &c->hist, &c->bbox, &c->axis_hist, &c->m_P, &c->m_D, &c->m_orig, &c->q_key, &c->q_key2, &c->q_idx, &c->q_idx2, &c->knn_lo, &c->knn_hi, &c->knn_thr, &c->knn_cnt,
                  &c->st_in0, &c->st_in1, &c->st_out0, &c->st_out1, &c->st_out2, &c->st_out3, &c->st_out4,
                  &c->e_head, &c->e_prev, &c->e_pos, &c->e_nrm, &c->e_w, &c->e_emit, &c->e_direct, &c->e_photon, &c->e_rays,
-                 &c->pass_img, &c->accum, &c->npass, &c->stats, &c->cub_tmp2, &c->cull, &c->dl_dbg};
+                 &c->pass_img, &c->accum, &c->npass, &c->stats, &c->cub_tmp2, &c->cull, &c->dl_dbg, &c->heavy};
   for (DBuf* b : all) b->release();
   for (int i = 0; i < ppm_ctx::EV_COUNT; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   cudaStreamSynchronize(c->stream2);

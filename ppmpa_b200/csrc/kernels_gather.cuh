@@ -33,14 +33,94 @@ __global__ void k_query_key(Grid g, const double* __restrict__ qpos3, int64_t n,
 }
 
 // v2: warp-cooperative gather.  A warp owns 32 cell-sorted queries (one per lane).
-// For each distinct cell among them, the photons of the (2R+1)^3 neighbourhood -- (2R+1)^2
-// x-contiguous runs of the sorted map, R = 1 (cell edge r: 9 runs of 3 cells) or R = 2 (cell
-// edge r/2: 25 runs of 5 cells, 30 % fewer candidates) -- form one virtual candidate stream;
+// For each distinct cell among them, the photons of the 3x3x3 neighbourhood -- nine
+// x-contiguous runs of the sorted map (cell edge >= r) -- form one virtual candidate stream;
 // 32 candidates at a time are fetched with coalesced 16-byte loads, staged in shared memory,
 // and every lane tests the SAME photon (broadcast LDS.128) against its own query -- no
 // per-lane loop lengths, no scattered global loads.
 #define GATHER_WARPS 4
 #define GATHER_SPAN 3        // a group may span cells cx .. cx+3 of one row
+#define GATHER_HEAVY_WARPS 8 // warps that share one heavy group (k_gather_heavy)
+// A group whose candidate stream is longer than this is not processed by its warp but handed to
+// k_gather_heavy, where 8 warps split the stream.  Work concentrated in few queries (a sunlit patch that
+// holds most photons: 10^4..10^5 neighbours for ~1 % of the queries, BASELINE config 3) otherwise leaves
+// ~1000 long-running warps for 592 schedulers.
+#define GATHER_HEAVY_MIN 4096u
+struct HeavyGroup { uint32_t s_base, grp, ck, klast; };   // warp's first sorted query, lane mask, leader / last cell key
+
+// lanes 0..8 look up the nine runs of the group's neighbourhood; returns the length of the candidate stream and
+// leaves, per run, its cumulative end (sEnd) and start minus exclusive prefix (sOff) in the warp's shared arrays
+__device__ __forceinline__ uint32_t gather_group_runs(const Grid& g, const uint32_t* __restrict__ cell_start, uint32_t ck, uint32_t klast,
+                                                      int lane, uint32_t* sEnd, uint32_t* sOff) {
+  constexpr int REACH = 1, W = 2 * REACH + 1, ROWS = W * W;
+  const unsigned FULL = 0xffffffffu;
+  const uint32_t nxp = (uint32_t)g.nx, nyp = (uint32_t)g.ny;
+  const int cx = (int)(ck % nxp), cy = (int)((ck / nxp) % nyp), cz = (int)(ck / (nxp * nyp));
+  const int x0 = max(cx - REACH, 0), x1 = min((int)(klast % nxp) + REACH, g.nx - 1);
+  uint32_t rbeg = 0, rlen = 0;
+  if (lane < ROWS && x0 <= x1) {
+    const int z = cz + lane / W - REACH, y = cy + lane % W - REACH;
+    if (z >= 0 && z < g.nz && y >= 0 && y < g.ny) {
+      const uint32_t row = ((uint32_t)z * (uint32_t)g.ny + (uint32_t)y) * (uint32_t)g.nx;
+      rbeg = cell_start[row + x0];
+      rlen = cell_start[row + x1 + 1] - rbeg;
+    }
+  }
+  uint32_t pre = rlen;                               // inclusive prefix of the run lengths
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t t = __shfl_up_sync(FULL, pre, o);
+    if (lane >= o) pre += t;
+  }
+  const uint32_t total = __shfl_sync(FULL, pre, 31);
+  __syncwarp();
+  sEnd[lane] = pre;
+  sOff[lane] = rbeg - (pre - rlen);
+  __syncwarp();
+  return total;
+}
+// chunks base = first, first + stride, ... of the candidate stream: stage 32 candidates, test them against the lane's query
+template <int FILTER, int MODE>
+__device__ __forceinline__ void gather_chunks(const MapSoA& m, uint32_t total, uint32_t first, uint32_t stride, int lane, bool act,
+                                              const uint32_t* sEnd, const uint32_t* sOff, double2 (*sP)[2], double2 (*sD)[2],
+                                              double qx, double qy, double qz, D3 nv, double r2, double power,
+                                              double& rr, double& rg, double& rb, uint32_t& cnt) {
+  for (uint32_t base = first; base < total; base += stride) {
+    const uint32_t v = base + lane;
+    if (v < total) {
+      int run = 0;                                   // number of runs that end at or before v (binary search)
+#pragma unroll
+      for (int step = 16; step > 0; step >>= 1)
+        if (sEnd[run + step - 1] <= v) run += step;
+      const uint32_t o = sOff[run];
+      const uint64_t j = (uint64_t)(v + o) * 2;
+      sP[lane][0] = m.P[j]; sP[lane][1] = m.P[j + 1];
+      if (MODE != 2) { sD[lane][0] = m.D[j]; sD[lane][1] = m.D[j + 1]; }
+    }
+    __syncwarp();
+    const int mcount = (int)min(32u, total - base);
+    if (act) {
+      for (int t = 0; t < mcount; ++t) {
+        const double2 a = sP[t][0], b = sP[t][1];
+        // squared_euclidean: ((qx-px)^2 + (qy-py)^2) + (qz-pz)^2, member iff d2 <= r2
+        const double ax = qx - a.x, ay = qy - a.y, az = qz - b.x;
+        const double d2 = (ax * ax + ay * ay) + az * az;
+        if (d2 <= r2) {
+          ++cnt;
+          if (MODE == 2) continue;
+          const double wt = FILTER == PPM_FILTER_NONE ? 1.0 : (FILTER == PPM_FILTER_CONE ? filter_cone(d2, r2) : filter_gauss(d2, r2));
+          const double2 c = sD[t][0], d = sD[t][1];
+          // photon_to_radiance, optics.rs:224-233
+          const double cos0 = (nv.x * c.x + nv.y * c.y) + nv.z * d.x;
+          const double pw2 = cos0 < 0.0 ? (wt * power) * -cos0 : 0.0;
+          const int w = (int)__double_as_longlong(b.y);
+          if (w == 0) rr = rr + pw2; else if (w == 1) rg = rg + pw2; else rb = rb + pw2;
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
 // MODE 0: fixed radius r2 (estimate_radiance).  MODE 1: per-query squared radius r2q[] (k-NN estimate:
 // membership, filter rmax and normaliser all use the query's own radius).  MODE 2: count only,
 // members are d2 <= r2q[] (the bisection steps of the k-NN radius search).
@@ -49,16 +129,14 @@ __global__ void __launch_bounds__(GATHER_WARPS * 32)
 k_gather(Grid g, const uint32_t* __restrict__ cell_start, MapSoA m, const uint32_t* __restrict__ qkey,
          const uint32_t* __restrict__ qidx, const double* __restrict__ qpos3, const double* __restrict__ qnrm3, int64_t n,
          double power, double r2_fixed, const double* __restrict__ r2q, double* __restrict__ rgb3, uint32_t* __restrict__ counts,
-         unsigned long long* __restrict__ sum_k) {
-  constexpr int REACH = 1;
+         unsigned long long* __restrict__ sum_k, HeavyGroup* __restrict__ heavy, unsigned int* __restrict__ n_heavy, uint32_t heavy_cap) {
   __shared__ double2 sP[GATHER_WARPS][32][2];
   __shared__ double2 sD[GATHER_WARPS][32][2];
   __shared__ uint32_t sEnd[GATHER_WARPS][32], sOff[GATHER_WARPS][32];   // per run: cumulative end, start - exclusive prefix
-  constexpr int W = 2 * REACH + 1, ROWS = W * W;
-  static_assert(ROWS <= 32, "one lane per run");
   const unsigned FULL = 0xffffffffu;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t s = ((int64_t)blockIdx.x * GATHER_WARPS + warp) * 32 + lane;
+  const int64_t s_base = ((int64_t)blockIdx.x * GATHER_WARPS + warp) * 32;
+  const int64_t s = s_base + lane;
   const bool valid = s < n;
   const uint32_t key = valid ? qkey[s] : 0xFFFFFFFFu;
   const uint32_t qi = valid ? qidx[s] : 0u;
@@ -72,7 +150,8 @@ k_gather(Grid g, const uint32_t* __restrict__ cell_start, MapSoA m, const uint32
   }
   double rr = 0.0, rg = 0.0, rb = 0.0;
   uint32_t cnt = 0;
-  const uint32_t nxp = (uint32_t)g.nx, nyp = (uint32_t)g.ny;
+  bool deferred = false;                               // this lane's query was handed to k_gather_heavy
+  const uint32_t nxp = (uint32_t)g.nx;
   unsigned pending = __ballot_sync(FULL, valid);
   while (pending) {
     const int leader = __ffs(pending) - 1;
@@ -85,66 +164,21 @@ k_gather(Grid g, const uint32_t* __restrict__ cell_start, MapSoA m, const uint32
     const unsigned grp = __ballot_sync(FULL, act);
     pending &= ~grp;
     const uint32_t klast = __shfl_sync(FULL, key, 31 - __clz((int)grp));
-    const int cx = (int)(ck % nxp), cy = (int)((ck / nxp) % nyp), cz = (int)(ck / (nxp * nyp));
-    const int x0 = max(cx - REACH, 0), x1 = min((int)(klast % nxp) + REACH, g.nx - 1);
-    // lane l < ROWS looks up run l = (dz, dy) of the neighbourhood
-    uint32_t rbeg = 0, rlen = 0;
-    if (lane < ROWS && x0 <= x1) {
-      const int z = cz + lane / W - REACH, y = cy + lane % W - REACH;
-      if (z >= 0 && z < g.nz && y >= 0 && y < g.ny) {
-        const uint32_t row = ((uint32_t)z * (uint32_t)g.ny + (uint32_t)y) * (uint32_t)g.nx;
-        rbeg = cell_start[row + x0];
-        rlen = cell_start[row + x1 + 1] - rbeg;
+    const uint32_t total = gather_group_runs(g, cell_start, ck, klast, lane, sEnd[warp], sOff[warp]);
+    if (heavy && total > GATHER_HEAVY_MIN) {
+      unsigned int slot = 0;
+      if (lane == 0) slot = atomicAdd(n_heavy, 1u);
+      slot = __shfl_sync(FULL, slot, 0);
+      if (slot < heavy_cap) {                          // (a full list just means the warp does the work itself)
+        if (lane == 0) { HeavyGroup h; h.s_base = (uint32_t)s_base; h.grp = grp; h.ck = ck; h.klast = klast; heavy[slot] = h; }
+        if (act) deferred = true;
+        continue;
       }
     }
-    uint32_t pre = rlen;                               // inclusive prefix of the run lengths
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      uint32_t t = __shfl_up_sync(FULL, pre, o);
-      if (lane >= o) pre += t;
-    }
-    const uint32_t total = __shfl_sync(FULL, pre, 31);
-    __syncwarp();
-    sEnd[warp][lane] = pre;
-    sOff[warp][lane] = rbeg - (pre - rlen);
-    __syncwarp();
-    for (uint32_t base = 0; base < total; base += 32) {
-      const uint32_t v = base + lane;
-      if (v < total) {
-        int run = 0;                                   // number of runs that end at or before v (binary search)
-#pragma unroll
-        for (int step = 16; step > 0; step >>= 1)
-          if (sEnd[warp][run + step - 1] <= v) run += step;
-        const uint32_t o = sOff[warp][run];
-        const uint64_t j = (uint64_t)(v + o) * 2;
-        sP[warp][lane][0] = m.P[j]; sP[warp][lane][1] = m.P[j + 1];
-        if (MODE != 2) { sD[warp][lane][0] = m.D[j]; sD[warp][lane][1] = m.D[j + 1]; }
-      }
-      __syncwarp();
-      const int mcount = (int)min(32u, total - base);
-      if (act) {
-        for (int t = 0; t < mcount; ++t) {
-          const double2 a = sP[warp][t][0], b = sP[warp][t][1];
-          // squared_euclidean: ((qx-px)^2 + (qy-py)^2) + (qz-pz)^2, member iff d2 <= r2
-          const double ax = qx - a.x, ay = qy - a.y, az = qz - b.x;
-          const double d2 = (ax * ax + ay * ay) + az * az;
-          if (d2 <= r2) {
-            ++cnt;
-            if (MODE == 2) continue;
-            const double wt = FILTER == PPM_FILTER_NONE ? 1.0 : (FILTER == PPM_FILTER_CONE ? filter_cone(d2, r2) : filter_gauss(d2, r2));
-            const double2 c = sD[warp][t][0], d = sD[warp][t][1];
-            // photon_to_radiance, optics.rs:224-233
-            const double cos0 = (nv.x * c.x + nv.y * c.y) + nv.z * d.x;
-            const double pw2 = cos0 < 0.0 ? (wt * power) * -cos0 : 0.0;
-            const int w = (int)__double_as_longlong(b.y);
-            if (w == 0) rr = rr + pw2; else if (w == 1) rg = rg + pw2; else rb = rb + pw2;
-          }
-        }
-      }
-      __syncwarp();
-    }
+    gather_chunks<FILTER, MODE>(m, total, 0u, 32u, lane, act, sEnd[warp], sOff[warp], sP[warp], sD[warp], qx, qy, qz, nv, r2, power,
+                                rr, rg, rb, cnt);
   }
-  if (valid) {
+  if (valid && !deferred) {
     if (MODE != 2) {
       const double sc = (1.0 / PPM_PI) / r2;          // rad * (ONE_PI / radius), tracer.rs:193
       rgb3[(uint64_t)qi * 3] = rr * sc; rgb3[(uint64_t)qi * 3 + 1] = rg * sc; rgb3[(uint64_t)qi * 3 + 2] = rb * sc;
@@ -155,6 +189,66 @@ k_gather(Grid g, const uint32_t* __restrict__ cell_start, MapSoA m, const uint32
     unsigned long long c = cnt;
     for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(FULL, c, o);
     if (lane == 0 && c) atomicAdd(sum_k, c);
+  }
+}
+
+// Heavy groups: one CTA of 8 warps per group, persistent over the list.  Every warp holds the
+// group's queries (lane = position in the original warp), the 32-candidate chunks of the stream are dealt round-robin
+// to the warps, and warp 0 adds the eight partial sums in warp order -- deterministic whatever order the list has.
+template <int FILTER, int MODE>
+__global__ void __launch_bounds__(GATHER_HEAVY_WARPS * 32)
+k_gather_heavy(Grid g, const uint32_t* __restrict__ cell_start, MapSoA m, const uint32_t* __restrict__ qidx,
+               const double* __restrict__ qpos3, const double* __restrict__ qnrm3, int64_t n, double power, double r2_fixed,
+               const double* __restrict__ r2q, double* __restrict__ rgb3, uint32_t* __restrict__ counts, unsigned long long* __restrict__ sum_k,
+               const HeavyGroup* __restrict__ heavy, const unsigned int* __restrict__ n_heavy, uint32_t heavy_cap) {
+  __shared__ double2 sP[GATHER_HEAVY_WARPS][32][2];
+  __shared__ double2 sD[GATHER_HEAVY_WARPS][32][2];
+  __shared__ uint32_t sEnd[GATHER_HEAVY_WARPS][32], sOff[GATHER_HEAVY_WARPS][32];
+  __shared__ double sAcc[GATHER_HEAVY_WARPS][3][32];
+  __shared__ uint32_t sCnt[GATHER_HEAVY_WARPS][32];
+  const unsigned FULL = 0xffffffffu;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned int ng = min(*n_heavy, heavy_cap);
+  for (unsigned int gi = blockIdx.x; gi < ng; gi += gridDim.x) {
+    const HeavyGroup h = heavy[gi];
+    const int64_t s = (int64_t)h.s_base + lane;
+    const bool act = ((h.grp >> lane) & 1u) != 0u && s < n;
+    uint32_t qi = 0;
+    double qx = 0.0, qy = 0.0, qz = 0.0;
+    D3 nv = mk3(0.0, 0.0, 0.0);
+    double r2 = r2_fixed;
+    if (act) {
+      qi = qidx[s];
+      qx = qpos3[(uint64_t)qi * 3]; qy = qpos3[(uint64_t)qi * 3 + 1]; qz = qpos3[(uint64_t)qi * 3 + 2];
+      if (MODE != 2) nv = ld3(qnrm3 + (uint64_t)qi * 3);
+      if (MODE != 0) r2 = r2q[qi];
+    }
+    const uint32_t total = gather_group_runs(g, cell_start, h.ck, h.klast, lane, sEnd[warp], sOff[warp]);
+    double rr = 0.0, rg = 0.0, rb = 0.0;
+    uint32_t cnt = 0;
+    gather_chunks<FILTER, MODE>(m, total, (uint32_t)warp * 32u, (uint32_t)GATHER_HEAVY_WARPS * 32u, lane, act, sEnd[warp], sOff[warp],
+                             sP[warp], sD[warp], qx, qy, qz, nv, r2, power, rr, rg, rb, cnt);
+    sAcc[warp][0][lane] = rr; sAcc[warp][1][lane] = rg; sAcc[warp][2][lane] = rb; sCnt[warp][lane] = cnt;
+    __syncthreads();
+    if (warp == 0) {
+      double tr = 0.0, tg = 0.0, tb = 0.0;
+      uint32_t tc = 0;
+#pragma unroll
+      for (int w = 0; w < GATHER_HEAVY_WARPS; ++w) { tr = tr + sAcc[w][0][lane]; tg = tg + sAcc[w][1][lane]; tb = tb + sAcc[w][2][lane]; tc += sCnt[w][lane]; }
+      if (act) {
+        if (MODE != 2) {
+          const double sc = (1.0 / PPM_PI) / r2;
+          rgb3[(uint64_t)qi * 3] = tr * sc; rgb3[(uint64_t)qi * 3 + 1] = tg * sc; rgb3[(uint64_t)qi * 3 + 2] = tb * sc;
+        }
+        if (counts) counts[qi] = tc;
+      }
+      if (sum_k) {
+        unsigned long long c = act ? tc : 0u;
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(FULL, c, o);
+        if (lane == 0 && c) atomicAdd(sum_k, c);
+      }
+    }
+    __syncthreads();
   }
 }
 

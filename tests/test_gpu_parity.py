@@ -229,6 +229,44 @@ def test_gather_parity(engine, oracle, pfilter, r):
     assert RTOL <= RTOL_CONTRACT
 
 
+@pytest.mark.parametrize("pfilter", [K.FILTER_NONE, K.FILTER_GAUSS])
+def test_gather_heavy_groups(engine, oracle, pfilter, monkeypatch):
+    """Work concentrated in few queries (BASELINE config 3: a sunlit patch holding most photons): groups whose
+    candidate stream exceeds GATHER_HEAVY_MIN are split over 8 warps by k_gather_heavy.  Same neighbour counts
+    as the single-warp path and the oracle, radiance equal up to the summation order."""
+    rng = np.random.default_rng(11)
+    n = 400000
+    ph = np.zeros(n, K.PHOTON_DTYPE)
+    dense = rng.random(n) < 0.9                                        # 90 % of the photons on a 0.5 x 0.5 patch of the floor
+    ph["pos"][:, 0] = np.where(dense, rng.uniform(-0.25, 0.25, n), rng.uniform(-2, 2, n))
+    ph["pos"][:, 2] = np.where(dense, rng.uniform(2.0, 2.5, n), rng.uniform(-6, 5, n))
+    d = rng.normal(size=(n, 3)); d[:, 1] = -np.abs(d[:, 1]) - 0.1; d /= np.linalg.norm(d, axis=1, keepdims=True)
+    ph["dir"] = d
+    ph["wl"] = rng.integers(0, 3, n)
+    power = 5.0 / n
+    r = 0.1
+    q = np.zeros((6000, 3))
+    q[:, 0] = rng.uniform(-1.0, 1.0, 6000); q[:, 2] = rng.uniform(1.0, 3.5, 6000)
+    nrm = np.tile([0.0, 1.0, 0.0], (len(q), 1))
+    engine.import_photons(ph, power); engine.build_photonmap(r * r)
+    g, gc = engine.estimate_radiance(q, nrm, pfilter)
+    monkeypatch.setenv("PPM_GATHER_HEAVY", "0")
+    g1, gc1 = engine.estimate_radiance(q, nrm, pfilter)
+    monkeypatch.delenv("PPM_GATHER_HEAVY")
+    assert gc.max() > 20000                                            # really heavy: > 2e4 neighbours per query in the patch
+    assert np.array_equal(gc, gc1)
+    assert_rel(g, g1, 1e-12)
+    assert not np.array_equal(g, g1)                                   # the heavy path did run (different summation order)
+    sub = np.concatenate([np.argsort(gc)[-150:], np.arange(150)])
+    m = oracle.map_build(ph, power, r * r)
+    o, oc = m.gather(q[sub], nrm[sub], pfilter, nthreads=4)
+    assert np.array_equal(gc[sub], oc)
+    assert_rel(g[sub], o, RTOL)
+    # k-NN with k larger than any neighbourhood takes the same (heavy) path and reproduces the fixed radius exactly
+    same, r2k, c2 = engine.estimate_radiance_knn(q, nrm, 10 ** 7, pfilter)
+    assert np.array_equal(same, g) and np.array_equal(c2, gc)
+
+
 def test_gather_empty_map_and_state_errors(engine):
     eng2 = P.Engine(0)
     try:
