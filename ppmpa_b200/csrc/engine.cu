@@ -505,19 +505,22 @@ int gather_launch(ppm_ctx* c, const double* dpos, const double* dnrm, int64_t n,
   const uint32_t* cs = c->cell_start.as<uint32_t>();
   const uint32_t* qk = c->q_key2.as<uint32_t>();
   const uint32_t* qx = c->q_idx2.as<uint32_t>();
-  // heavy groups: the light kernel hands them over through a device-side list, the persistent
-  // heavy kernel (a no-op when the list is empty) splits each over 8 warps
-  HeavyGroup* hv = nullptr;
-  unsigned int* nhv = nullptr;
-  const uint32_t hcap = 1u << 16;
+  // heavy groups: warps publish them as parts in a device-side list; k_gather_heavy is launched only if there are any
+  HeavyList hl;
+  std::memset(&hl, 0, sizeof hl);
   if (!(std::getenv("PPM_GATHER_HEAVY") && std::getenv("PPM_GATHER_HEAVY")[0] == '0')) {
-    CK(c, c->heavy.ensure((size_t)hcap * sizeof(HeavyGroup) + 16));
-    nhv = c->heavy.as<unsigned int>();
-    hv = (HeavyGroup*)(c->heavy.as<char>() + 16);
-    CK(c, cudaMemsetAsync(nhv, 0, 4, c->stream));
+    const uint32_t cap = 1u << 15;                     // parts: 32 MB of partial sums per context
+    const size_t off_groups = 64, off_parts = off_groups + (size_t)(cap / 2) * sizeof(HeavyGroup),
+                 off_partials = off_parts + (size_t)cap * sizeof(HeavyPart), bytes = off_partials + (size_t)cap * sizeof(HeavyPartial);
+    CK(c, c->heavy.ensure(bytes));
+    char* base = c->heavy.as<char>();
+    hl.ctr = (unsigned int*)base; hl.groups = (HeavyGroup*)(base + off_groups); hl.parts = (HeavyPart*)(base + off_parts);
+    hl.partials = (HeavyPartial*)(base + off_partials);
+    hl.cap_parts = cap;
+    CK(c, cudaMemsetAsync(hl.ctr, 0, 16, c->stream));  // [0] parts reserved, [1] ticket of k_gather_heavy, [2] groups
   }
-#define GATHER_LAUNCH(F, M) k_gather<F, M><<<nblk(n, B), B, 0, c->stream>>>(c->grid, cs, mapsoa(c), qk, qx, dpos, dnrm, n, c->power, c->r2, r2q, drgb, dcounts, dsumk, hv, nhv, hcap)
-#define HEAVY_LAUNCH(F, M) k_gather_heavy<F, M><<<c->sm_count * 2, GATHER_HEAVY_WARPS * 32, 0, c->stream>>>(c->grid, cs, mapsoa(c), qx, dpos, dnrm, n, c->power, c->r2, r2q, drgb, dcounts, dsumk, hv, nhv, hcap)
+  if (c->timed) cudaEventRecord(c->ev[ppm_ctx::EV_A4], c->stream);   // start of k_gather
+#define GATHER_LAUNCH(F, M) k_gather<F, M><<<nblk(n, B), B, 0, c->stream>>>(c->grid, cs, mapsoa(c), qk, qx, dpos, dnrm, n, c->power, c->r2, r2q, drgb, dcounts, dsumk, hl)
   if (mode == 2) GATHER_LAUNCH(PPM_FILTER_NONE, 2);
   else if (mode == 1) {
     switch (filter) {
@@ -534,24 +537,33 @@ int gather_launch(ppm_ctx* c, const double* dpos, const double* dnrm, int64_t n,
   }
 #undef GATHER_LAUNCH
   KCHECK(c);
-  if (hv) {
-    if (mode == 2) HEAVY_LAUNCH(PPM_FILTER_NONE, 2);
-    else if (mode == 1) {
-      switch (filter) {
-        case PPM_FILTER_NONE: HEAVY_LAUNCH(PPM_FILTER_NONE, 1); break;
-        case PPM_FILTER_CONE: HEAVY_LAUNCH(PPM_FILTER_CONE, 1); break;
-        default:              HEAVY_LAUNCH(PPM_FILTER_GAUSS, 1); break;
+  if (c->timed) cudaEventRecord(c->ev[ppm_ctx::EV_A5], c->stream);   // end of k_gather (re-recorded after k_gather_heavy)
+  if (hl.ctr) {
+    unsigned int nparts = 0;
+    CK(c, cudaMemcpyAsync(&nparts, hl.ctr, 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    if (nparts > 0) {
+      const unsigned grid = std::min<unsigned>((nparts + GATHER_WARPS - 1) / GATHER_WARPS, (unsigned)c->sm_count * 16u);
+#define HEAVY_LAUNCH(F, M) k_gather_heavy<F, M><<<grid, B, 0, c->stream>>>(c->grid, cs, mapsoa(c), qx, dpos, dnrm, n, c->power, c->r2, r2q, drgb, dcounts, dsumk, hl)
+      if (mode == 2) HEAVY_LAUNCH(PPM_FILTER_NONE, 2);
+      else if (mode == 1) {
+        switch (filter) {
+          case PPM_FILTER_NONE: HEAVY_LAUNCH(PPM_FILTER_NONE, 1); break;
+          case PPM_FILTER_CONE: HEAVY_LAUNCH(PPM_FILTER_CONE, 1); break;
+          default:              HEAVY_LAUNCH(PPM_FILTER_GAUSS, 1); break;
+        }
+      } else {
+        switch (filter) {
+          case PPM_FILTER_NONE: HEAVY_LAUNCH(PPM_FILTER_NONE, 0); break;
+          case PPM_FILTER_CONE: HEAVY_LAUNCH(PPM_FILTER_CONE, 0); break;
+          default:              HEAVY_LAUNCH(PPM_FILTER_GAUSS, 0); break;
+        }
       }
-    } else {
-      switch (filter) {
-        case PPM_FILTER_NONE: HEAVY_LAUNCH(PPM_FILTER_NONE, 0); break;
-        case PPM_FILTER_CONE: HEAVY_LAUNCH(PPM_FILTER_CONE, 0); break;
-        default:              HEAVY_LAUNCH(PPM_FILTER_GAUSS, 0); break;
-      }
-    }
-    KCHECK(c);
-  }
 #undef HEAVY_LAUNCH
+      KCHECK(c);
+      if (c->timed) cudaEventRecord(c->ev[ppm_ctx::EV_A5], c->stream);
+    }
+  }
   return PPM_OK;
 }
 int launch_gather(ppm_ctx* c, const double* dpos, const double* dnrm, int64_t n, int filter, double* drgb, uint32_t* dcounts,
@@ -560,7 +572,6 @@ int launch_gather(ppm_ctx* c, const double* dpos, const double* dnrm, int64_t n,
   if (filter < PPM_FILTER_NONE || filter > PPM_FILTER_GAUSS) return fail(c, PPM_ERR_ARG, "bad filter");
   int rc = gather_sort_queries(c, dpos, n);
   if (rc) return rc;
-  if (c->timed) cudaEventRecord(c->ev[ppm_ctx::EV_A4], c->stream);
   return gather_launch(c, dpos, dnrm, n, filter, 0, nullptr, drgb, dcounts, dsumk);
 }
 // k-NN estimate (no reference implementation exists: n_sample_photon is dead code, photonmap.rs:18,
@@ -649,7 +660,6 @@ int eye_gather(ppm_ctx* c, uint32_t nn) {
   int rc = launch_gather(c, c->e_pos.as<double>(), c->e_nrm.as<double>(), nn, c->cam.pfilter, c->e_photon.as<double>(), nullptr,
                          c->stats.as<unsigned long long>() + 1);
   if (rc) return rc;
-  if (c->timed) cudaEventRecord(c->ev[ppm_ctx::EV_A5], c->stream);
   c->counters[3] = nn;
   return PPM_OK;
 }

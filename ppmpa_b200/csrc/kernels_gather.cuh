@@ -40,13 +40,28 @@ __global__ void k_query_key(Grid g, const double* __restrict__ qpos3, int64_t n,
 // per-lane loop lengths, no scattered global loads.
 #define GATHER_WARPS 4
 #define GATHER_SPAN 3        // a group may span cells cx .. cx+3 of one row
-#define GATHER_HEAVY_WARPS 8 // warps that share one heavy group (k_gather_heavy)
-// A group whose candidate stream is longer than this is not processed by its warp but handed to
-// k_gather_heavy, where 8 warps split the stream.  Work concentrated in few queries (a sunlit patch that
-// holds most photons: 10^4..10^5 neighbours for ~1 % of the queries, BASELINE config 3) otherwise leaves
-// ~1000 long-running warps for 592 schedulers.
-#define GATHER_HEAVY_MIN 4096u
-struct HeavyGroup { uint32_t s_base, grp, ck, klast; };   // warp's first sorted query, lane mask, leader / last cell key
+// A group whose candidate stream is longer than GATHER_HEAVY_MIN is not processed by its warp alone: the warp
+// publishes it as S = ceil(total / GATHER_HEAVY_MIN) (<= 64) independent PARTS in a device-side list; part k takes the
+// 32-candidate chunks k, k + S, k + 2S, ... of the stream.  k_gather_heavy (launched only when the list is not empty)
+// lets every warp of the GPU claim parts one at a time, write the 32 partial sums of its part to a pool, and the warp
+// that completes a group adds the S partials in part order and writes the result: deterministic whoever did which part.
+// (Letting the light kernel's warps help after their own queries was tried: helpers leave whenever the list is
+// momentarily empty, so the tail ran on a handful of warps -- 36 ms.)
+// Work concentrated in few queries (a sunlit patch that holds most photons: 10^4..10^5 neighbours for ~1 % of the
+// queries, BASELINE config 3) otherwise leaves ~1000 long-running warps for 592 schedulers (config 3 at 1024^2:
+// k_gather 8.2 -> 3 ms).  Config 2 has no heavy groups from the second pass on.
+#define GATHER_HEAVY_MIN 2048u
+#define GATHER_HEAVY_MAXPARTS 64u
+struct HeavyGroup { uint32_t s_base, grp, ck, klast, nparts, part0, done, _pad; };  // warp's first sorted query, lane mask, leader / last cell key, parts, completed parts
+struct HeavyPart { uint32_t group; };
+struct HeavyPartial { double rgb[3][32]; uint32_t cnt[32]; };                      // one part's partial sums, one column per lane
+struct HeavyList {
+  unsigned int* ctr;        // [0] parts reserved, [1] next unclaimed part, [2] groups
+  HeavyGroup* groups;       // [cap_parts / 2]
+  HeavyPart* parts;         // [cap_parts]
+  HeavyPartial* partials;   // [cap_parts]
+  uint32_t cap_parts;
+};
 
 // lanes 0..8 look up the nine runs of the group's neighbourhood; returns the length of the candidate stream and
 // leaves, per run, its cumulative end (sEnd) and start minus exclusive prefix (sOff) in the warp's shared arrays
@@ -129,7 +144,7 @@ __global__ void __launch_bounds__(GATHER_WARPS * 32)
 k_gather(Grid g, const uint32_t* __restrict__ cell_start, MapSoA m, const uint32_t* __restrict__ qkey,
          const uint32_t* __restrict__ qidx, const double* __restrict__ qpos3, const double* __restrict__ qnrm3, int64_t n,
          double power, double r2_fixed, const double* __restrict__ r2q, double* __restrict__ rgb3, uint32_t* __restrict__ counts,
-         unsigned long long* __restrict__ sum_k, HeavyGroup* __restrict__ heavy, unsigned int* __restrict__ n_heavy, uint32_t heavy_cap) {
+         unsigned long long* __restrict__ sum_k, HeavyList hl) {
   __shared__ double2 sP[GATHER_WARPS][32][2];
   __shared__ double2 sD[GATHER_WARPS][32][2];
   __shared__ uint32_t sEnd[GATHER_WARPS][32], sOff[GATHER_WARPS][32];   // per run: cumulative end, start - exclusive prefix
@@ -165,12 +180,24 @@ k_gather(Grid g, const uint32_t* __restrict__ cell_start, MapSoA m, const uint32
     pending &= ~grp;
     const uint32_t klast = __shfl_sync(FULL, key, 31 - __clz((int)grp));
     const uint32_t total = gather_group_runs(g, cell_start, ck, klast, lane, sEnd[warp], sOff[warp]);
-    if (heavy && total > GATHER_HEAVY_MIN) {
-      unsigned int slot = 0;
-      if (lane == 0) slot = atomicAdd(n_heavy, 1u);
-      slot = __shfl_sync(FULL, slot, 0);
-      if (slot < heavy_cap) {                          // (a full list just means the warp does the work itself)
-        if (lane == 0) { HeavyGroup h; h.s_base = (uint32_t)s_base; h.grp = grp; h.ck = ck; h.klast = klast; heavy[slot] = h; }
+    if (hl.ctr && total > GATHER_HEAVY_MIN) {
+      const uint32_t nparts = min(GATHER_HEAVY_MAXPARTS, (total + GATHER_HEAVY_MIN - 1u) / GATHER_HEAVY_MIN);
+      uint32_t part0 = 0xFFFFFFFFu;
+      if (lane == 0) {
+        for (;;) {                                       // reserve nparts consecutive parts, never partially
+          const unsigned int old = *(volatile unsigned int*)hl.ctr;
+          if (old + nparts > hl.cap_parts) break;        // pool exhausted: the warp does the work itself
+          if (atomicCAS(hl.ctr, old, old + nparts) == old) { part0 = old; break; }
+        }
+        if (part0 != 0xFFFFFFFFu) {
+          const unsigned int gs = atomicAdd(hl.ctr + 2, 1u);   // groups <= parts / 2: cannot overflow
+          HeavyGroup* h = hl.groups + gs;
+          h->s_base = (uint32_t)s_base; h->grp = grp; h->ck = ck; h->klast = klast; h->nparts = nparts; h->part0 = part0; h->done = 0u;
+          for (uint32_t k = 0; k < nparts; ++k) hl.parts[part0 + k].group = gs;
+        }
+      }
+      part0 = __shfl_sync(FULL, part0, 0);
+      if (part0 != 0xFFFFFFFFu) {
         if (act) deferred = true;
         continue;
       }
@@ -192,63 +219,72 @@ k_gather(Grid g, const uint32_t* __restrict__ cell_start, MapSoA m, const uint32
   }
 }
 
-// Heavy groups: one CTA of 8 warps per group, persistent over the list.  Every warp holds the
-// group's queries (lane = position in the original warp), the 32-candidate chunks of the stream are dealt round-robin
-// to the warps, and warp 0 adds the eight partial sums in warp order -- deterministic whatever order the list has.
+// Heavy parts: every warp claims parts by ticket (ctr[1]) until the list (ctr[0] parts, all published before this
+// kernel starts) is exhausted.
 template <int FILTER, int MODE>
-__global__ void __launch_bounds__(GATHER_HEAVY_WARPS * 32)
+__global__ void __launch_bounds__(GATHER_WARPS * 32)
 k_gather_heavy(Grid g, const uint32_t* __restrict__ cell_start, MapSoA m, const uint32_t* __restrict__ qidx,
                const double* __restrict__ qpos3, const double* __restrict__ qnrm3, int64_t n, double power, double r2_fixed,
-               const double* __restrict__ r2q, double* __restrict__ rgb3, uint32_t* __restrict__ counts, unsigned long long* __restrict__ sum_k,
-               const HeavyGroup* __restrict__ heavy, const unsigned int* __restrict__ n_heavy, uint32_t heavy_cap) {
-  __shared__ double2 sP[GATHER_HEAVY_WARPS][32][2];
-  __shared__ double2 sD[GATHER_HEAVY_WARPS][32][2];
-  __shared__ uint32_t sEnd[GATHER_HEAVY_WARPS][32], sOff[GATHER_HEAVY_WARPS][32];
-  __shared__ double sAcc[GATHER_HEAVY_WARPS][3][32];
-  __shared__ uint32_t sCnt[GATHER_HEAVY_WARPS][32];
+               const double* __restrict__ r2q, double* __restrict__ rgb3, uint32_t* __restrict__ counts,
+               unsigned long long* __restrict__ sum_k, HeavyList hl) {
+  __shared__ double2 sP[GATHER_WARPS][32][2];
+  __shared__ double2 sD[GATHER_WARPS][32][2];
+  __shared__ uint32_t sEnd[GATHER_WARPS][32], sOff[GATHER_WARPS][32];
   const unsigned FULL = 0xffffffffu;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const unsigned int ng = min(*n_heavy, heavy_cap);
-  for (unsigned int gi = blockIdx.x; gi < ng; gi += gridDim.x) {
-    const HeavyGroup h = heavy[gi];
-    const int64_t s = (int64_t)h.s_base + lane;
-    const bool act = ((h.grp >> lane) & 1u) != 0u && s < n;
-    uint32_t qi = 0;
-    double qx = 0.0, qy = 0.0, qz = 0.0;
-    D3 nv = mk3(0.0, 0.0, 0.0);
-    double r2 = r2_fixed;
-    if (act) {
-      qi = qidx[s];
-      qx = qpos3[(uint64_t)qi * 3]; qy = qpos3[(uint64_t)qi * 3 + 1]; qz = qpos3[(uint64_t)qi * 3 + 2];
-      if (MODE != 2) nv = ld3(qnrm3 + (uint64_t)qi * 3);
-      if (MODE != 0) r2 = r2q[qi];
+  const unsigned int nparts_total = hl.ctr[0];
+  for (;;) {
+    unsigned int t = 0xFFFFFFFFu;
+    if (lane == 0) { t = atomicAdd(hl.ctr + 1, 1u); if (t >= nparts_total) t = 0xFFFFFFFFu; }
+    t = __shfl_sync(FULL, t, 0);
+    if (t == 0xFFFFFFFFu) break;
+    const uint32_t gs = __ldcg(&hl.parts[t].group);
+    HeavyGroup* hg = hl.groups + gs;
+    const uint32_t h_base = __ldcg(&hg->s_base), h_grp = __ldcg(&hg->grp), h_ck = __ldcg(&hg->ck), h_klast = __ldcg(&hg->klast),
+                   h_np = __ldcg(&hg->nparts), h_p0 = __ldcg(&hg->part0);
+    const int64_t hs = (int64_t)h_base + lane;
+    const bool hact = ((h_grp >> lane) & 1u) != 0u && hs < n;
+    uint32_t hqi = 0;
+    double hx = 0.0, hy = 0.0, hz = 0.0, hr2 = r2_fixed;
+    D3 hnv = mk3(0.0, 0.0, 0.0);
+    if (hact) {
+      hqi = qidx[hs];
+      hx = qpos3[(uint64_t)hqi * 3]; hy = qpos3[(uint64_t)hqi * 3 + 1]; hz = qpos3[(uint64_t)hqi * 3 + 2];
+      if (MODE != 2) hnv = ld3(qnrm3 + (uint64_t)hqi * 3);
+      if (MODE != 0) hr2 = r2q[hqi];
     }
-    const uint32_t total = gather_group_runs(g, cell_start, h.ck, h.klast, lane, sEnd[warp], sOff[warp]);
-    double rr = 0.0, rg = 0.0, rb = 0.0;
-    uint32_t cnt = 0;
-    gather_chunks<FILTER, MODE>(m, total, (uint32_t)warp * 32u, (uint32_t)GATHER_HEAVY_WARPS * 32u, lane, act, sEnd[warp], sOff[warp],
-                             sP[warp], sD[warp], qx, qy, qz, nv, r2, power, rr, rg, rb, cnt);
-    sAcc[warp][0][lane] = rr; sAcc[warp][1][lane] = rg; sAcc[warp][2][lane] = rb; sCnt[warp][lane] = cnt;
-    __syncthreads();
-    if (warp == 0) {
-      double tr = 0.0, tg = 0.0, tb = 0.0;
-      uint32_t tc = 0;
-#pragma unroll
-      for (int w = 0; w < GATHER_HEAVY_WARPS; ++w) { tr = tr + sAcc[w][0][lane]; tg = tg + sAcc[w][1][lane]; tb = tb + sAcc[w][2][lane]; tc += sCnt[w][lane]; }
-      if (act) {
-        if (MODE != 2) {
-          const double sc = (1.0 / PPM_PI) / r2;
-          rgb3[(uint64_t)qi * 3] = tr * sc; rgb3[(uint64_t)qi * 3 + 1] = tg * sc; rgb3[(uint64_t)qi * 3 + 2] = tb * sc;
-        }
-        if (counts) counts[qi] = tc;
-      }
-      if (sum_k) {
-        unsigned long long c = act ? tc : 0u;
-        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(FULL, c, o);
-        if (lane == 0 && c) atomicAdd(sum_k, c);
-      }
+    const uint32_t total = gather_group_runs(g, cell_start, h_ck, h_klast, lane, sEnd[warp], sOff[warp]);
+    double ar = 0.0, ag = 0.0, ab = 0.0;
+    uint32_t ac = 0;
+    gather_chunks<FILTER, MODE>(m, total, (t - h_p0) * 32u, h_np * 32u, lane, hact, sEnd[warp], sOff[warp], sP[warp], sD[warp],
+                                hx, hy, hz, hnv, hr2, power, ar, ag, ab, ac);
+    HeavyPartial* hp = hl.partials + t;
+    __stcg(&hp->rgb[0][lane], ar); __stcg(&hp->rgb[1][lane], ag); __stcg(&hp->rgb[2][lane], ab); __stcg(&hp->cnt[lane], ac);
+    __threadfence();
+    __syncwarp();
+    unsigned int fin = 0;
+    if (lane == 0) fin = atomicAdd(&hg->done, 1u) + 1u == h_np ? 1u : 0u;
+    fin = __shfl_sync(FULL, fin, 0);
+    if (!fin) continue;
+    __threadfence();                                     // this warp completed the group: add the parts in order
+    double tr = 0.0, tg = 0.0, tb = 0.0;
+    uint32_t tc = 0;
+    for (uint32_t k = 0; k < h_np; ++k) {
+      const HeavyPartial* q = hl.partials + h_p0 + k;
+      tr = tr + __ldcg(&q->rgb[0][lane]); tg = tg + __ldcg(&q->rgb[1][lane]); tb = tb + __ldcg(&q->rgb[2][lane]); tc += __ldcg(&q->cnt[lane]);
     }
-    __syncthreads();
+    if (hact) {
+      if (MODE != 2) {
+        const double sc = (1.0 / PPM_PI) / hr2;
+        rgb3[(uint64_t)hqi * 3] = tr * sc; rgb3[(uint64_t)hqi * 3 + 1] = tg * sc; rgb3[(uint64_t)hqi * 3 + 2] = tb * sc;
+      }
+      if (counts) counts[hqi] = tc;
+    }
+    if (sum_k) {
+      unsigned long long c = hact ? tc : 0u;
+      for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(FULL, c, o);
+      if (lane == 0 && c) atomicAdd(sum_k, c);
+    }
   }
 }
 
