@@ -25,5 +25,20 @@ for f in (0, 1, 2):
     eng.estimate_radiance(q, nrm, f)
 eng.estimate_radiance_knn(q, nrm, 20, 1)
 eng.within(q, 64)
+eng.set_scene(P.read_scene(os.path.join(EX, "sample1.scene")))
+eng.direct_light(q, nrm)                              # culled shadow rays (spheres, planes, emitter quad)
+os.environ["PPM_DL_CULL"] = "0"
+eng.direct_light(q, nrm)
+del os.environ["PPM_DL_CULL"]
+# heavy gather groups: 6000 photons in one cell neighbourhood -> parts + k_gather_heavy, all modes
+rng = np.random.default_rng(3)
+hp = np.zeros(6000, K.PHOTON_DTYPE)
+hp["pos"][:, 0] = rng.uniform(-0.05, 0.05, 6000); hp["pos"][:, 2] = rng.uniform(-0.05, 0.05, 6000)
+hp["dir"][:, 1] = -1.0
+eng.import_photons(hp, 1e-3); eng.build_photonmap(0.04)
+hq = np.zeros((100, 3)); hq[:, 0] = rng.uniform(-0.1, 0.1, 100)
+g, cnt = eng.estimate_radiance(hq, nrm[:100], 2)
+assert cnt.max() > 4000
+eng.estimate_radiance_knn(hq, nrm[:100], 50, 0)
 print("sanitize run ok", float(img.sum()))
 eng.close()
