@@ -34,13 +34,28 @@ __global__ void k_bbox(const double* __restrict__ pos3, uint64_t n, unsigned lon
       lo[k] = e < lo[k] ? e : lo[k];
       hi[k] = e > hi[k] ? e : hi[k];
     }
+  // warp shuffle reduction, then one shared-memory step per block: 6 global atomics per block instead of per warp
+  __shared__ unsigned long long slo[3][8], shi[3][8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int k = 0; k < 3; ++k) {
     for (int o = 16; o > 0; o >>= 1) {
       unsigned long long a = __shfl_xor_sync(0xffffffffu, lo[k], o), b = __shfl_xor_sync(0xffffffffu, hi[k], o);
       lo[k] = a < lo[k] ? a : lo[k];
       hi[k] = b > hi[k] ? b : hi[k];
     }
-    if ((threadIdx.x & 31) == 0) { atomicMin(&mm[k], lo[k]); atomicMax(&mm[3 + k], hi[k]); }
+    if (lane == 0) { slo[k][warp] = lo[k]; shi[k][warp] = hi[k]; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    const int k = threadIdx.x % 3;
+    const bool is_hi = threadIdx.x >= 3;
+    const int nw = (blockDim.x + 31) >> 5;
+    unsigned long long v = is_hi ? shi[k][0] : slo[k][0];
+    for (int w = 1; w < nw; ++w) {
+      const unsigned long long x = is_hi ? shi[k][w] : slo[k][w];
+      v = is_hi ? (x > v ? x : v) : (x < v ? x : v);
+    }
+    if (is_hi) atomicMax(&mm[3 + k], v); else atomicMin(&mm[k], v);
   }
 }
 // Per-axis histograms (AXIS_BINS bins over [lo, lo + AXIS_BINS*w)) for the trimmed grid region.
