@@ -517,7 +517,7 @@ int gather_launch(ppm_ctx* c, const double* dpos, const double* dnrm, int64_t n,
     hl.ctr = (unsigned int*)base; hl.groups = (HeavyGroup*)(base + off_groups); hl.parts = (HeavyPart*)(base + off_parts);
     hl.partials = (HeavyPartial*)(base + off_partials);
     hl.cap_parts = cap;
-    CK(c, cudaMemsetAsync(hl.ctr, 0, 16, c->stream));  // [0] parts reserved, [1] ticket of k_gather_heavy, [2] groups
+    CK(c, cudaMemsetAsync(hl.ctr, 0, 16, c->stream));  // [0] reservations, [1] ticket of k_gather_heavy, [2] groups, [3] parts published
   }
   if (c->timed) cudaEventRecord(c->ev[ppm_ctx::EV_A4], c->stream);   // start of k_gather
 #define GATHER_LAUNCH(F, M) k_gather<F, M><<<nblk(n, B), B, 0, c->stream>>>(c->grid, cs, mapsoa(c), qk, qx, dpos, dnrm, n, c->power, c->r2, r2q, drgb, dcounts, dsumk, hl)
@@ -540,7 +540,7 @@ int gather_launch(ppm_ctx* c, const double* dpos, const double* dnrm, int64_t n,
   if (c->timed) cudaEventRecord(c->ev[ppm_ctx::EV_A5], c->stream);   // end of k_gather (re-recorded after k_gather_heavy)
   if (hl.ctr) {
     unsigned int nparts = 0;
-    CK(c, cudaMemcpyAsync(&nparts, hl.ctr, 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaMemcpyAsync(&nparts, hl.ctr + 3, 4, cudaMemcpyDeviceToHost, c->stream));
     CK(c, cudaStreamSynchronize(c->stream));
     if (nparts > 0) {
       const unsigned grid = std::min<unsigned>((nparts + GATHER_WARPS - 1) / GATHER_WARPS, (unsigned)c->sm_count * 16u);

@@ -56,7 +56,7 @@ struct HeavyGroup { uint32_t s_base, grp, ck, klast, nparts, part0, done, _pad; 
 struct HeavyPart { uint32_t group; };
 struct HeavyPartial { double rgb[3][32]; uint32_t cnt[32]; };                      // one part's partial sums, one column per lane
 struct HeavyList {
-  unsigned int* ctr;        // [0] parts reserved, [1] next unclaimed part, [2] groups
+  unsigned int* ctr;        // [0] reservation counter, [1] ticket of k_gather_heavy, [2] groups, [3] parts published
   HeavyGroup* groups;       // [cap_parts / 2]
   HeavyPart* parts;         // [cap_parts]
   HeavyPartial* partials;   // [cap_parts]
@@ -184,10 +184,12 @@ k_gather(Grid g, const uint32_t* __restrict__ cell_start, MapSoA m, const uint32
       const uint32_t nparts = min(GATHER_HEAVY_MAXPARTS, (total + GATHER_HEAVY_MIN - 1u) / GATHER_HEAVY_MIN);
       uint32_t part0 = 0xFFFFFFFFu;
       if (lane == 0) {
-        for (;;) {                                       // reserve nparts consecutive parts, never partially
-          const unsigned int old = *(volatile unsigned int*)hl.ctr;
-          if (old + nparts > hl.cap_parts) break;        // pool exhausted: the warp does the work itself
-          if (atomicCAS(hl.ctr, old, old + nparts) == old) { part0 = old; break; }
+        // Reserve nparts consecutive parts with ONE atomicAdd (a CAS loop collapses when every warp of a uniformly
+        // dense map publishes at once).  The counter only grows, so the successful reservations are exactly a prefix
+        // [0, ctr[3]) of the pool; once it is exhausted the warps do the work themselves.
+        if (*(volatile unsigned int*)hl.ctr < hl.cap_parts) {
+          const unsigned int old = atomicAdd(hl.ctr, nparts);
+          if (old + nparts <= hl.cap_parts) { part0 = old; atomicMax(hl.ctr + 3, old + nparts); }
         }
         if (part0 != 0xFFFFFFFFu) {
           const unsigned int gs = atomicAdd(hl.ctr + 2, 1u);   // groups <= parts / 2: cannot overflow
@@ -219,7 +221,7 @@ k_gather(Grid g, const uint32_t* __restrict__ cell_start, MapSoA m, const uint32
   }
 }
 
-// Heavy parts: every warp claims parts by ticket (ctr[1]) until the list (ctr[0] parts, all published before this
+// Heavy parts: every warp claims parts by ticket (ctr[1]) until the list (ctr[3] parts, all published before this
 // kernel starts) is exhausted.
 template <int FILTER, int MODE>
 __global__ void __launch_bounds__(GATHER_WARPS * 32)
@@ -232,7 +234,7 @@ k_gather_heavy(Grid g, const uint32_t* __restrict__ cell_start, MapSoA m, const 
   __shared__ uint32_t sEnd[GATHER_WARPS][32], sOff[GATHER_WARPS][32];
   const unsigned FULL = 0xffffffffu;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const unsigned int nparts_total = hl.ctr[0];
+  const unsigned int nparts_total = hl.ctr[3];
   for (;;) {
     unsigned int t = 0xFFFFFFFFu;
     if (lane == 0) { t = atomicAdd(hl.ctr + 1, 1u); if (t >= nparts_total) t = 0xFFFFFFFFu; }
