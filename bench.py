@@ -109,7 +109,9 @@ def run_reference(args):
     if rank != 0:
         return 0
     cores = os.cpu_count() or 1
-    rows = env_int("PPM_BENCH_CPU_ROWS", 64)
+    # bounded sample: every step traces the full 1 M photons (~1 s per core) plus `rows` image rows; the row count
+    # shrinks with --steps so that the whole run stays within a few minutes whatever K the driver passes
+    rows = env_int("PPM_BENCH_CPU_ROWS", max(4, min(64, 640 // max(args.steps + min(args.warmup, 1), 1))))
     for w in range(min(args.warmup, 1)):
         cpu_pass_sample(rows, cores, w)
     eq = []
