@@ -296,7 +296,7 @@ def run_gpu(args):
     # reference's NPARA = 4 processes (util/iterator.rb:18) -- E2E_LANES engine contexts per GPU are driven by as
     # many host threads, each doing whole steps through the public API (PPM_E2E_LANES, default 4).
     import threading
-    E2E_LANES = max(1, env_int("PPM_E2E_LANES", 4))
+    E2E_LANES = max(1, env_int("PPM_E2E_LANES", max(2, min(4, (os.cpu_count() or 8) // max(world, 1)))))
     engs = [eng] + [P.Engine(local) for _ in range(E2E_LANES - 1)]
     bufs = [torch.empty((npix, 3), dtype=torch.float64).pin_memory().numpy() for _ in range(E2E_LANES)]
     h2d = (C.sizeof(P._capi.Prim) * sc.nprims + C.sizeof(P._capi.Material) * sc.nmats + C.sizeof(P._capi.Light) * sc.nlights
