@@ -437,8 +437,8 @@ int do_map_build(ppm_ctx* c, double radius2) {
   c->grid = g;
   {
     // cudaFree/cudaMalloc stall for 10-400 ms on this platform: size the cell tables for at
-    // least 2^23 cells up front so the shrinking radius does not regrow them every few passes
-    size_t want = std::max<size_t>((size_t)g.ncells + 1, (size_t)1 << 23) * 4;
+    // least 2^24 cells up front (64 MB per table) so the shrinking radius does not regrow them every few passes
+    size_t want = std::max<size_t>((size_t)g.ncells + 1, (size_t)1 << 24) * 4;
     CK(c, c->hist.ensure(want));
     CK(c, c->cell_start.ensure(want));
   }
