@@ -85,7 +85,7 @@ struct ppm_ctx {
   // light) of a pass are independent until the gather, so render_pass runs them concurrently.
   cudaStream_t stream2 = nullptr;
   DBuf cub_tmp2;
-  enum { EV_A0, EV_A1, EV_A2, EV_A3, EV_A4, EV_A5, EV_A6, EV_A7, EV_B0, EV_B1, EV_B2, EV_COUNT };
+  enum { EV_A0, EV_A1, EV_A2, EV_A3, EV_A4, EV_A5, EV_A6, EV_A7, EV_A8, EV_B0, EV_B1, EV_B2, EV_B3, EV_COUNT };
   cudaEvent_t ev[EV_COUNT] = {nullptr};
   bool timed = false;             // record the phase events (render_pass only)
   uint64_t launches = 0;
@@ -270,7 +270,8 @@ const DevCull* cull_arg(ppm_ctx* c) {
   return c->cull.as<DevCull>();
 }
 
-int launch_direct_light(ppm_ctx* c, cudaStream_t st, const double* dpos, const double* dnrm, int64_t n, double* dout) {
+int launch_direct_light(ppm_ctx* c, cudaStream_t st, const double* dpos, const double* dnrm, int64_t n, double* dout,
+                        const uint32_t* order = nullptr) {
   unsigned long long* dbg = nullptr;
   const bool stats = std::getenv("PPM_DL_STATS") != nullptr;
   if (stats) {
@@ -278,7 +279,7 @@ int launch_direct_light(ppm_ctx* c, cudaStream_t st, const double* dpos, const d
     CK(c, cudaMemsetAsync(c->dl_dbg.p, 0, 160, st));
     dbg = c->dl_dbg.as<unsigned long long>();
   }
-  k_direct_light<<<nblk(n, 128), 128, 0, st>>>(c->scene, cull_arg(c), dpos, dnrm, n, dout, dbg);
+  k_direct_light<<<nblk(n, 128), 128, 0, st>>>(c->scene, cull_arg(c), order, dpos, dnrm, n, dout, dbg);
   KCHECK(c);
   if (stats) {
     unsigned long long h[20];
@@ -616,7 +617,7 @@ int launch_gather_knn(ppm_ctx* c, const double* dpos, const double* dnrm, int64_
 // Eye branch, part 1 (stream `st`): expand the eye paths into the gather-node list and
 // compute the classic direct light at every node.  drays == NULL generates camera rays.
 int eye_front(ppm_ctx* c, cudaStream_t st, DBuf& tmpbuf, const double* drays, int64_t n, int64_t first_pixel, uint64_t seed,
-              uint32_t pass, int uc, uint32_t* nn_out, int classic = 0) {
+              uint32_t pass, int uc, uint32_t* nn_out, int classic = 0, bool defer_direct = false) {
   (void)tmpbuf;
   CK(c, c->e_head.ensure((size_t)n * 4));
   CK(c, c->e_emit.ensure((size_t)n * 24)); CK(c, c->stats.ensure(64));
@@ -644,22 +645,43 @@ int eye_front(ppm_ctx* c, cudaStream_t st, DBuf& tmpbuf, const double* drays, in
   }
   EyeNodes nodes = {c->e_pos.as<double>(), c->e_nrm.as<double>(), c->e_w.as<double>(), c->e_prev.as<uint32_t>()};
   cudaEventRecord(c->ev[ppm_ctx::EV_B1], st);
+  *nn_out = nn;
+  if (defer_direct) return PPM_OK;                           // render_pass launches it in cell-sorted order
+  cudaEventRecord(c->ev[ppm_ctx::EV_B3], st);
   if (uc && nn) {
     int rc = launch_direct_light(c, st, nodes.pos3, nodes.nrm3, nn, c->e_direct.as<double>());
     if (rc) return rc;
   }
   cudaEventRecord(c->ev[ppm_ctx::EV_B2], st);
-  *nn_out = nn;
   return PPM_OK;
 }
 // Eye branch, part 2 (main stream; the photon map must be built): gather at every node.
 // Needs the node list (event EV_B1) but not the direct light, so in render_pass it runs
 // concurrently with k_direct_light.
-int eye_gather(ppm_ctx* c, uint32_t nn) {
+int eye_gather(ppm_ctx* c, uint32_t nn, int uc_sorted_direct = 0) {
   if (c->timed) cudaEventRecord(c->ev[ppm_ctx::EV_A3], c->stream);
-  int rc = launch_gather(c, c->e_pos.as<double>(), c->e_nrm.as<double>(), nn, c->cam.pfilter, c->e_photon.as<double>(), nullptr,
-                         c->stats.as<unsigned long long>() + 1);
-  if (rc) return rc;
+  if (nn) {
+    if (c->cam.pfilter < PPM_FILTER_NONE || c->cam.pfilter > PPM_FILTER_GAUSS) return fail(c, PPM_ERR_ARG, "bad filter");
+    int rc = gather_sort_queries(c, c->e_pos.as<double>(), nn);
+    if (rc) return rc;
+    if (uc_sorted_direct) {
+      // direct light on stream2, over the nodes in the cell-sorted order the gather uses (coherent culling masks);
+      // it runs concurrently with k_gather on the main stream
+      cudaEventRecord(c->ev[ppm_ctx::EV_A8], c->stream);
+      cudaStreamWaitEvent(c->stream2, c->ev[ppm_ctx::EV_A8], 0);
+      cudaEventRecord(c->ev[ppm_ctx::EV_B3], c->stream2);
+      rc = launch_direct_light(c, c->stream2, c->e_pos.as<double>(), c->e_nrm.as<double>(), nn, c->e_direct.as<double>(),
+                               c->q_idx2.as<uint32_t>());
+      if (rc) return rc;
+      cudaEventRecord(c->ev[ppm_ctx::EV_B2], c->stream2);
+    }
+    rc = gather_launch(c, c->e_pos.as<double>(), c->e_nrm.as<double>(), nn, c->cam.pfilter, 0, nullptr, c->e_photon.as<double>(), nullptr,
+                       c->stats.as<unsigned long long>() + 1);
+    if (rc) return rc;
+  } else if (uc_sorted_direct) {
+    cudaEventRecord(c->ev[ppm_ctx::EV_B3], c->stream2);
+    cudaEventRecord(c->ev[ppm_ctx::EV_B2], c->stream2);
+  }
   c->counters[3] = nn;
   return PPM_OK;
 }
@@ -1055,13 +1077,13 @@ int ppm_render_pass(ppm_ctx* c, uint64_t seed, uint32_t pass, int64_t nphoton, d
   uint32_t nn = 0;
   rc = trace_photons_launch(c, seed, pass, uc, ns, &cap);
   cudaEventRecord(c->ev[E::EV_A1], c->stream);
-  if (!rc) rc = eye_front(c, c->stream2, c->cub_tmp2, nullptr, npix, 0, seed, pass, uc, &nn);
+  if (!rc) rc = eye_front(c, c->stream2, c->cub_tmp2, nullptr, npix, 0, seed, pass, uc, &nn, 0, /*defer_direct=*/uc != 0);
   if (!rc) rc = trace_photons_finish(c, cap, power);
   if (!rc) rc = do_map_build(c, radius2);
   cudaEventRecord(c->ev[E::EV_A2], c->stream);
   if (!rc) {
     cudaStreamWaitEvent(c->stream, c->ev[E::EV_B1], 0);      // node list ready
-    rc = eye_gather(c, nn);                                   // runs concurrently with k_direct_light (stream2)
+    rc = eye_gather(c, nn, uc);                               // k_gather runs concurrently with k_direct_light (stream2)
   }
   if (!rc) {
     cudaStreamWaitEvent(c->stream, c->ev[E::EV_B2], 0);      // direct light done
@@ -1080,7 +1102,7 @@ int ppm_render_pass(ppm_ctx* c, uint64_t seed, uint32_t pass, int64_t nphoton, d
   c->ms[0] = el(E::EV_A0, E::EV_A1);                 // photon trace
   c->ms[1] = el(E::EV_A1, E::EV_A2);                 // map build (includes waiting for host readbacks)
   c->ms[2] = el(E::EV_B0, E::EV_B1);                 // eye expand (stream2, concurrent with the photon branch)
-  c->ms[3] = el(E::EV_B1, E::EV_B2);                 // direct light (stream2)
+  c->ms[3] = el(E::EV_B3, E::EV_B2);                 // direct light (stream2)
   c->ms[4] = el(E::EV_A3, E::EV_A5);                 // gather: query sort + kernel
   c->ms[5] = el(E::EV_A7, E::EV_A6);                 // combine + accumulate
   c->ms[6] = el(E::EV_A0, E::EV_A6);                 // whole pass
