@@ -56,7 +56,8 @@ struct ppm_ctx {
   std::string err;
   bool have_scene = false, have_camera = false, have_map = false;
   DevScene scene;
-  DBuf dl_dbg;
+  DBuf dl_dbg, dl_masks;
+  const unsigned long long* dl_masks_cur = nullptr;   // masks of the current node list (render_pass)
   DBuf cull;                      // DevCull: per-scene table for the shadow-ray culling of k_direct_light
   ppm_camera cam;
   // unsorted records
@@ -206,6 +207,13 @@ void build_cull(const DevScene& sc, DevCull& cu) {
     } else if (s.type == PPM_SHAPE_POLYGON || s.type == PPM_SHAPE_PARALLELOGRAM) {
       cp.kind = 2;               // the triangle u + v <= 1 is a subset of its parallelogram
       quad_sphere(s.position, s.dir1, s.dir2, cp.c, &cp.r);
+      cp.nvtx = 4;
+      for (int j = 0; j < 4; ++j)
+        for (int k = 0; k < 3; ++k)
+          cp.vtx[j][k] = s.position[k] + ((j == 1 || j == 2) ? s.dir1[k] : 0.0) + ((j >= 2) ? s.dir2[k] : 0.0);
+      for (int j = 0; j < 4 && cp.nvtx; ++j)
+        for (int k = 0; k < 3; ++k)
+          if (!(std::fabs(cp.vtx[j][k]) < 1e150)) cp.nvtx = 0;
     } else {
       cp.kind = 0;               // Point: calc_distance never yields a root
     }
@@ -216,6 +224,9 @@ void build_cull(const DevScene& sc, DevCull& cu) {
     CullLight& cl = cu.light[li];
     if (l.type != PPM_LIGHT_PARALLELOGRAM) continue;
     quad_sphere(l.pos, l.dir1, l.dir2, cl.c, &cl.r);
+    for (int j = 0; j < 4; ++j)
+      for (int k = 0; k < 3; ++k)
+        cl.corner[j][k] = l.pos[k] + ((j == 1 || j == 2) ? l.dir1[k] : 0.0) + ((j >= 2) ? l.dir2[k] : 0.0);
     if (!(cl.r < 1e150)) { cl.r = 1e300; }              // r^2 overflows -> the cone test is off, planes below stay valid or NaN
     // unit normal of the light's plane and the polygons / parallelograms lying in it (the emitter's own
     // geometry): every vertex within 1e-12 (relative to the scene scale) of the plane through the quad
@@ -270,8 +281,19 @@ const DevCull* cull_arg(ppm_ctx* c) {
   return c->cull.as<DevCull>();
 }
 
+// k_dl_classify: per-node culling masks for every light (nullptr result = culling off: PPM_DL_CULL=0 or 64 primitives)
+int launch_dl_classify(ppm_ctx* c, cudaStream_t st, const double* dpos, int64_t n, const unsigned long long** masks_out) {
+  *masks_out = nullptr;
+  const DevCull* cull = cull_arg(c);
+  if (!cull || c->scene.nprims > 63 || c->scene.nlights <= 0 || n <= 0) return PPM_OK;
+  CK(c, c->dl_masks.ensure((size_t)n * (size_t)c->scene.nlights * 8));
+  k_dl_classify<<<nblk(n, 128), 128, 0, st>>>(c->scene, cull, dpos, n, c->dl_masks.as<unsigned long long>());
+  KCHECK(c);
+  *masks_out = c->dl_masks.as<unsigned long long>();
+  return PPM_OK;
+}
 int launch_direct_light(ppm_ctx* c, cudaStream_t st, const double* dpos, const double* dnrm, int64_t n, double* dout,
-                        const uint32_t* order = nullptr) {
+                        const unsigned long long* masks, const uint32_t* order = nullptr) {
   unsigned long long* dbg = nullptr;
   const bool stats = std::getenv("PPM_DL_STATS") != nullptr;
   if (stats) {
@@ -279,7 +301,7 @@ int launch_direct_light(ppm_ctx* c, cudaStream_t st, const double* dpos, const d
     CK(c, cudaMemsetAsync(c->dl_dbg.p, 0, 160, st));
     dbg = c->dl_dbg.as<unsigned long long>();
   }
-  k_direct_light<<<nblk(n, 128), 128, 0, st>>>(c->scene, cull_arg(c), order, dpos, dnrm, n, dout, dbg);
+  k_direct_light<<<nblk(n, 128), 128, 0, st>>>(c->scene, masks, order, dpos, dnrm, n, dout, dbg);
   KCHECK(c);
   if (stats) {
     unsigned long long h[20];
@@ -646,10 +668,15 @@ int eye_front(ppm_ctx* c, cudaStream_t st, DBuf& tmpbuf, const double* drays, in
   EyeNodes nodes = {c->e_pos.as<double>(), c->e_nrm.as<double>(), c->e_w.as<double>(), c->e_prev.as<uint32_t>()};
   cudaEventRecord(c->ev[ppm_ctx::EV_B1], st);
   *nn_out = nn;
-  if (defer_direct) return PPM_OK;                           // render_pass launches it in cell-sorted order
+  c->dl_masks_cur = nullptr;
+  if (uc && nn) {                                            // culling masks: right after the expansion, beside the photon branch
+    int rc = launch_dl_classify(c, st, nodes.pos3, nn, &c->dl_masks_cur);
+    if (rc) return rc;
+  }
+  if (defer_direct) return PPM_OK;                           // render_pass launches the direct light in cell-sorted order
   cudaEventRecord(c->ev[ppm_ctx::EV_B3], st);
   if (uc && nn) {
-    int rc = launch_direct_light(c, st, nodes.pos3, nodes.nrm3, nn, c->e_direct.as<double>());
+    int rc = launch_direct_light(c, st, nodes.pos3, nodes.nrm3, nn, c->e_direct.as<double>(), c->dl_masks_cur);
     if (rc) return rc;
   }
   cudaEventRecord(c->ev[ppm_ctx::EV_B2], st);
@@ -671,7 +698,7 @@ int eye_gather(ppm_ctx* c, uint32_t nn, int uc_sorted_direct = 0) {
       cudaStreamWaitEvent(c->stream2, c->ev[ppm_ctx::EV_A8], 0);
       cudaEventRecord(c->ev[ppm_ctx::EV_B3], c->stream2);
       rc = launch_direct_light(c, c->stream2, c->e_pos.as<double>(), c->e_nrm.as<double>(), nn, c->e_direct.as<double>(),
-                               c->q_idx2.as<uint32_t>());
+                               c->dl_masks_cur, c->q_idx2.as<uint32_t>());
       if (rc) return rc;
       cudaEventRecord(c->ev[ppm_ctx::EV_B2], c->stream2);
     }
@@ -748,7 +775,7 @@ void ppm_destroy(ppm_ctx* c) {
                  &c->cell_start, &c->hist, &c->bbox, &c->axis_hist, &c->m_P, &c->m_D, &c->m_orig, &c->q_key, &c->q_key2, &c->q_idx, &c->q_idx2, &c->knn_lo, &c->knn_hi, &c->knn_thr, &c->knn_cnt,
                  &c->st_in0, &c->st_in1, &c->st_out0, &c->st_out1, &c->st_out2, &c->st_out3, &c->st_out4,
                  &c->e_head, &c->e_prev, &c->e_pos, &c->e_nrm, &c->e_w, &c->e_emit, &c->e_direct, &c->e_photon, &c->e_rays,
-                 &c->pass_img, &c->accum, &c->npass, &c->stats, &c->cub_tmp2, &c->cull, &c->dl_dbg, &c->heavy};
+                 &c->pass_img, &c->accum, &c->npass, &c->stats, &c->cub_tmp2, &c->cull, &c->dl_dbg, &c->dl_masks, &c->heavy};
   for (DBuf* b : all) b->release();
   for (int i = 0; i < ppm_ctx::EV_COUNT; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   cudaStreamSynchronize(c->stream2);
@@ -992,7 +1019,9 @@ int ppm_direct_light(ppm_ctx* c, const double* pos3, const double* nrm3, int64_t
   if ((rc = stage_in(c, pos3, (size_t)n * 24, c->st_in0, &dp))) return rc;
   if ((rc = stage_in(c, nrm3, (size_t)n * 24, c->st_in1, &dn))) return rc;
   if ((rc = stage_out(c, rgb3, (size_t)n * 24, c->st_out0, &dr))) return rc;
-  if ((rc = launch_direct_light(c, c->stream, (const double*)dp, (const double*)dn, n, (double*)dr))) return rc;
+  const unsigned long long* masks = nullptr;
+  if ((rc = launch_dl_classify(c, c->stream, (const double*)dp, n, &masks))) return rc;
+  if ((rc = launch_direct_light(c, c->stream, (const double*)dp, (const double*)dn, n, (double*)dr, masks))) return rc;
   if ((rc = finish_out(c, rgb3, (size_t)n * 24, dr))) return rc;
   CK(c, cudaStreamSynchronize(c->stream));
   return PPM_OK;

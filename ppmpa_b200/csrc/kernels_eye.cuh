@@ -151,6 +151,9 @@ k_eye_expand(const __grid_constant__ DevScene sc, const __grid_constant__ ppm_ca
 //      - bounded primitive whose bounding sphere (radius inflated by 1e-6) lies outside the cone
 //        apex = node, through the light's bounding sphere, with a 2e-7 margin on the cosine -- ten
 //        orders above the rounding of the tests;
+//      - polygon / parallelogram that passes the sphere test but lies entirely outside one side plane of the
+//        pyramid apex = node over the light quad (all four corners beyond the plane through the node and one
+//        light edge, by an angular margin of 1e-6; only evaluated when the pyramid is well conditioned);
 //      - the plane the node itself lies on: with h = dist + n.p (the very value calc_distance
 //        computes, identical for all 25 rays) and h_g the same at the sample, den = (h - h_g)/ldist
 //        +- 1e-15, so |t| <= |h| ldist / (|h_g| - |h|) < NEARLY0 / 2 when the light is well off
@@ -171,11 +174,13 @@ struct CullPrim {
   double c[3];      // bounded: bounding-sphere centre | plane: c[0] = D, c[1] = gap
   double r;         // bounded: inflated radius
   int32_t kind;     // 0 = can never be hit (Point), 1 = plane, 2 = bounded (sphere, polygon, parallelogram), 3 = always tested
-  int32_t _pad;
+  int32_t nvtx;     // 4 for polygons / parallelograms (vtx = the parallelogram's corners, a superset of the triangle), else 0
+  double vtx[4][3];
 };
 struct CullLight {
   double c[3], r;                                   // bounding sphere of the light quad (inflated)
   double nl[3];                                     // unit normal of the light's plane (through c)
+  double corner[4][3];                              // the quad's corners in cyclic order: pos, +dir1, +dir1+dir2, +dir2
   unsigned long long coplanar;                      // polygons / parallelograms lying in that plane
   double hmin[PPM_MAX_PRIMS], hmax[PPM_MAX_PRIMS];  // planes: min / max of dist + n.corner over the quad's corners
 };
@@ -196,6 +201,9 @@ __device__ __forceinline__ unsigned long long cull_classify(const DevScene& sc, 
   const double L = sqrt(uu) + rl;                   // every ldist is below this
   const bool off_light_plane = fabs(dot(ld3(cl.nl), u)) > 1e-6 * (1.0 + L);
   unsigned long long mask = 0, harmless = 0;
+  int pyr_state = 0;                                // 0 = side planes not built yet, 1 = usable, 2 = ill conditioned
+  D3 pn[4];
+  double pnn[4];
   const int np = sc.nprims;
   for (int o = 0; o < np; ++o) {
     const CullPrim& cp = cull->prim[o];
@@ -225,6 +233,44 @@ __device__ __forceinline__ unsigned long long cull_classify(const DevScene& sc, 
           keep = !(dot(u, v) < rhs);
         }
       }
+      if (keep && cp.nvtx == 4 && off_light_plane) {
+        if (pyr_state == 0) {                           // side planes of the pyramid, built on first use
+          pyr_state = 2;
+          D3 a[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) a[j] = ld3(cl.corner[j]) - p;
+          bool ok = true;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const D3 n = cross(a[j], a[(j + 1) & 3]);
+            const double nn = dot(n, n);
+            const double s = dot(n, a[(j + 2) & 3]);    // the opposite corner is inside
+            // well conditioned: the two edge directions are not (nearly) collinear and the opposite corner is
+            // clearly off the side plane, so the plane's orientation is known to ~1e-10 rad
+            ok = ok && nn > 1e-12 * (dot(a[j], a[j]) * dot(a[(j + 1) & 3], a[(j + 1) & 3])) &&
+                 s * s > 1e-12 * (nn * dot(a[(j + 2) & 3], a[(j + 2) & 3]));
+            pn[j] = s < 0.0 ? -n : n;                   // oriented inward
+            pnn[j] = nn;
+          }
+          if (ok) pyr_state = 1;
+        }
+        if (pyr_state == 1) {
+          D3 w[4];
+          double ww[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) { w[k] = ld3(cp.vtx[k]) - p; ww[k] = dot(w[k], w[k]); }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            bool all_out = true;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const double d = dot(pn[j], w[k]);
+              all_out = all_out && d < 0.0 && d * d > 1e-12 * (pnn[j] * ww[k]);   // outside by > 1e-6 rad
+            }
+            if (all_out) keep = false;
+          }
+        }
+      }
       if (keep) mask |= bit;
     } else if (cp.kind == 3) {
       mask |= bit;
@@ -234,13 +280,36 @@ __device__ __forceinline__ unsigned long long cull_classify(const DevScene& sc, 
   return mask;
 }
 
+// One thread per node: the conservative classification above, for every area light.  masks[li * n + node] = the
+// primitives the node's shadow rays towards light li must test, bit 63 = the node has a certificate.  A separate
+// kernel so that it has its own register budget (k_direct_light is compiled for 64 registers) and can run right after
+// the eye-path expansion, concurrently with the photon branch.
+#define PPM_CULL_CERT (1ull << 63)
+__global__ void __launch_bounds__(128)
+k_dl_classify(const __grid_constant__ DevScene sc, const DevCull* __restrict__ cull, const double* __restrict__ pos3, int64_t n,
+              unsigned long long* __restrict__ masks) {
+  const int64_t node = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (node >= n) return;
+  const D3 p = ld3(pos3 + node * 3);
+  const unsigned long long all = (1ull << sc.nprims) - 1ull;       // nprims <= 63 here (bit 63 is the certificate)
+  for (int li = 0; li < sc.nlights; ++li) {
+    unsigned long long m = 0;
+    if (sc.lights[li].type == PPM_LIGHT_PARALLELOGRAM) {
+      bool cert;
+      m = cull_classify(sc, cull, li, p, all, cert);
+      if (cert) m |= PPM_CULL_CERT;
+    }
+    masks[(int64_t)li * n + node] = m;
+  }
+}
+
 __device__ __forceinline__ double ts5(unsigned i) {   // the literals 0.1, 0.3, 0.5, 0.7, 0.9 (light.rs:164-170)
   return i == 0 ? 0.1 : (i == 1 ? 0.3 : (i == 2 ? 0.5 : (i == 3 ? 0.7 : 0.9)));
 }
 // 64 registers (8 CTAs per SM): the kernel is latency bound, so occupancy beats the ~100 bytes of spills
 // (96 registers / 5 CTAs: 2.1 ms, 64 / 8: 1.35 ms on config 2).
 __global__ void __launch_bounds__(128, 8)
-k_direct_light(const __grid_constant__ DevScene sc, const DevCull* __restrict__ cull, const uint32_t* __restrict__ order,
+k_direct_light(const __grid_constant__ DevScene sc, const unsigned long long* __restrict__ masks, const uint32_t* __restrict__ order,
                const double* __restrict__ pos3, const double* __restrict__ nrm3, int64_t n, double* __restrict__ out3,
                unsigned long long* __restrict__ dbg) {
   __shared__ double s_gp[25][3];
@@ -268,16 +337,18 @@ k_direct_light(const __grid_constant__ DevScene sc, const DevCull* __restrict__ 
     __syncthreads();
     bool cert = false;
     unsigned long long mask = all;
-    if (cull) {
-      mask = cull_classify(sc, cull, li, p, all, cert);
-      const unsigned long long own = mask;
+    if (masks) {
+      const unsigned long long own = masks[(int64_t)li * n + node];     // k_dl_classify
+      cert = (own & PPM_CULL_CERT) != 0ull;
+      mask = own & ~PPM_CULL_CERT;
       const unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)mask);
       const unsigned hi = __reduce_or_sync(0xffffffffu, (unsigned)(mask >> 32));
       mask = ((unsigned long long)hi << 32) | lo;
       if (dbg && live) {                                      // diagnostic (PPM_DL_STATS): primitives tested per node
-        atomicAdd(dbg, 1ull); atomicAdd(dbg + 1, (unsigned long long)__popcll(own));
+        const unsigned long long o1 = own & ~PPM_CULL_CERT;
+        atomicAdd(dbg, 1ull); atomicAdd(dbg + 1, (unsigned long long)__popcll(o1));
         atomicAdd(dbg + 2, (unsigned long long)__popcll(mask)); atomicAdd(dbg + 3, cert ? 1ull : 0ull);
-        atomicAdd(dbg + 4 + min(__popcll(own), 7), 1ull); atomicAdd(dbg + 12 + min(__popcll(mask), 7), 1ull);
+        atomicAdd(dbg + 4 + min(__popcll(o1), 7), 1ull); atomicAdd(dbg + 12 + min(__popcll(mask), 7), 1ull);
       }
     }
     PrimMasks pm;
