@@ -261,13 +261,15 @@ __device__ __forceinline__ unsigned long long cull_classify(const DevScene& sc, 
           for (int k = 0; k < 4; ++k) { w[k] = ld3(cp.vtx[k]) - p; ww[k] = dot(w[k], w[k]); }
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            bool all_out = true;
+            if (keep) {                                  // (static indices: pn / pnn stay in registers)
+              bool all_out = true;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const double d = dot(pn[j], w[k]);
-              all_out = all_out && d < 0.0 && d * d > 1e-12 * (pnn[j] * ww[k]);   // outside by > 1e-6 rad
+              for (int k = 0; k < 4; ++k) {
+                const double d = dot(pn[j], w[k]);
+                all_out = all_out && d < 0.0 && d * d > 1e-12 * (pnn[j] * ww[k]);   // outside by > 1e-6 rad
+              }
+              if (all_out) keep = false;
             }
-            if (all_out) keep = false;
           }
         }
       }
