@@ -287,7 +287,11 @@ __device__ __forceinline__ unsigned long long cull_classify(const DevScene& sc, 
 // kernel so that it has its own register budget (k_direct_light is compiled for 64 registers) and can run right after
 // the eye-path expansion, concurrently with the photon branch.
 #define PPM_CULL_CERT (1ull << 63)
+#ifdef PPM_CLS_MINB                                   // tuning builds (tools/build_variants.sh): 5 / 6 / 8 CTAs per SM are all slower
+__global__ void __launch_bounds__(128, PPM_CLS_MINB)
+#else
 __global__ void __launch_bounds__(128)
+#endif
 k_dl_classify(const __grid_constant__ DevScene sc, const DevCull* __restrict__ cull, const double* __restrict__ pos3, int64_t n,
               unsigned long long* __restrict__ masks) {
   const int64_t node = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -310,7 +314,10 @@ __device__ __forceinline__ double ts5(unsigned i) {   // the literals 0.1, 0.3, 
 }
 // 64 registers (8 CTAs per SM): the kernel is latency bound, so occupancy beats the ~100 bytes of spills
 // (96 registers / 5 CTAs: 2.1 ms, 64 / 8: 1.35 ms on config 2).
-__global__ void __launch_bounds__(128, 8)
+#ifndef PPM_DL_MINB
+#define PPM_DL_MINB 8
+#endif
+__global__ void __launch_bounds__(128, PPM_DL_MINB)
 k_direct_light(const __grid_constant__ DevScene sc, const unsigned long long* __restrict__ masks, const uint32_t* __restrict__ order,
                const double* __restrict__ pos3, const double* __restrict__ nrm3, int64_t n, double* __restrict__ out3,
                unsigned long long* __restrict__ dbg) {

@@ -38,8 +38,12 @@ __global__ void k_query_key(Grid g, const double* __restrict__ qpos3, int64_t n,
 // 32 candidates at a time are fetched with coalesced 16-byte loads, staged in shared memory,
 // and every lane tests the SAME photon (broadcast LDS.128) against its own query -- no
 // per-lane loop lengths, no scattered global loads.
+#ifndef GATHER_WARPS
 #define GATHER_WARPS 4
+#endif
+#ifndef GATHER_SPAN
 #define GATHER_SPAN 3        // a group may span cells cx .. cx+3 of one row
+#endif
 // A group whose candidate stream is longer than GATHER_HEAVY_MIN is not processed by its warp alone: the warp
 // publishes it as S = ceil(total / GATHER_HEAVY_MIN) (<= 64) independent PARTS in a device-side list; part k takes the
 // 32-candidate chunks k, k + S, k + 2S, ... of the stream.  k_gather_heavy (launched only when the list is not empty)
