@@ -483,10 +483,14 @@ def _cull_probe_nodes(engine, seed):
     return np.ascontiguousarray(P3), np.ascontiguousarray(N3)
 
 
+@pytest.mark.parametrize("coherent", [False, True])
 @pytest.mark.parametrize("name", SCENES + ["adversarial"])
-def test_direct_light_cull_is_exact(engine, oracle, name, tmp_path, monkeypatch):
+def test_direct_light_cull_is_exact(engine, oracle, name, coherent, tmp_path, monkeypatch):
     """k_direct_light's conservative per-node culling must not change a single bit: compare with the
-    culling switched off (PPM_DL_CULL=0) and with the oracle's get_radiance_from_light."""
+    culling switched off (PPM_DL_CULL=0) and with the oracle's get_radiance_from_light.
+    coherent=True feeds the probe nodes sorted by a 5 cm grid, as ppm_render_pass does (cell-sorted order): the 32
+    nodes of a warp are then neighbours, which is the case the warp-wide mask OR (and any per-warp classification)
+    is built for; the unsorted order makes every warp a random mix."""
     if name == "adversarial":
         f = tmp_path / "adversarial.scene"
         f.write_text(ADVERSARIAL_SCENE)
@@ -495,6 +499,10 @@ def test_direct_light_cull_is_exact(engine, oracle, name, tmp_path, monkeypatch)
         sc = load_scene(name)
     engine.set_scene(sc)
     pos, nrm = _cull_probe_nodes(engine, 77)
+    if coherent:
+        cell = np.floor(pos / 0.05).astype(np.int64)
+        order = np.lexsort((cell[:, 0], cell[:, 1], cell[:, 2]))
+        pos, nrm = np.ascontiguousarray(pos[order]), np.ascontiguousarray(nrm[order])
     monkeypatch.setenv("PPM_DL_CULL", "1")
     a = engine.direct_light(pos, nrm)
     monkeypatch.setenv("PPM_DL_CULL", "0")
