@@ -284,10 +284,6 @@ const DevCull* cull_arg(ppm_ctx* c) {
 // k_dl_classify: per-node culling masks for every light (nullptr result = culling off: PPM_DL_CULL=0 or 64 primitives)
 int launch_dl_classify(ppm_ctx* c, cudaStream_t st, const double* dpos, int64_t n, const unsigned long long** masks_out) {
   *masks_out = nullptr;
-#if PPM_DL_REGION
-  (void)st; (void)dpos; (void)n;
-  return PPM_OK;                                     // experimental build: k_direct_light classifies per warp region itself
-#endif
   const DevCull* cull = cull_arg(c);
   if (!cull || c->scene.nprims > 63 || c->scene.nlights <= 0 || n <= 0) return PPM_OK;
   CK(c, c->dl_masks.ensure((size_t)n * (size_t)c->scene.nlights * 8));
@@ -305,22 +301,7 @@ int launch_direct_light(ppm_ctx* c, cudaStream_t st, const double* dpos, const d
     CK(c, cudaMemsetAsync(c->dl_dbg.p, 0, 160, st));
     dbg = c->dl_dbg.as<unsigned long long>();
   }
-#if PPM_DL_REGION
-  {
-    const DevCull* cull = (c->scene.nprims > 63 || c->scene.nlights <= 0) ? nullptr : cull_arg(c);
-    ulonglong2* region = nullptr;
-    if (cull) {
-      const int64_t nw = (n + 31) / 32;
-      CK(c, c->dl_masks.ensure((size_t)nw * (size_t)c->scene.nlights * sizeof(ulonglong2)));
-      region = c->dl_masks.as<ulonglong2>();
-      k_dl_region<<<nblk(nw * 32, 128), 128, 0, st>>>(c->scene, cull, order, dpos, n, region);
-      KCHECK(c);
-    }
-    k_direct_light<<<nblk(n, 128), 128, 0, st>>>(c->scene, masks, order, dpos, dnrm, n, dout, dbg, cull, region);
-  }
-#else
   k_direct_light<<<nblk(n, 128), 128, 0, st>>>(c->scene, masks, order, dpos, dnrm, n, dout, dbg);
-#endif
   KCHECK(c);
   if (stats) {
     unsigned long long h[20];

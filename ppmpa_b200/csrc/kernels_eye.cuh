@@ -309,166 +309,6 @@ k_dl_classify(const __grid_constant__ DevScene sc, const DevCull* __restrict__ c
   }
 }
 
-#ifndef PPM_DL_REGION
-#define PPM_DL_REGION 0      // 1 = experimental: bounded primitives are classified once per WARP of cell-sorted nodes
-#endif
-#if PPM_DL_REGION
-// ---- experimental (round-2 candidate, NOT the shipped path; build with tools/build_variants.sh dlregion:-DPPM_DL_REGION=1) --
-// k_dl_classify spends ~80 % of its instructions on the bounded primitives (cone test + pyramid test, per node).  Inside
-// ppm_render_pass the 32 nodes of a k_direct_light warp are neighbours in the gather's cell-sorted order, so the bounded
-// primitives can be classified ONCE PER WARP for the ball B(c, rho) that contains the warp's 32 nodes, one primitive
-// per lane, inside k_direct_light itself (no k_dl_classify launch, no mask traffic).  Planes stay per node (cheap, and
-// the own-plane criterion needs the node's own h).  Conservative for every apex p = c + delta, |delta| <= rho:
-//  (a) cone test with BOTH radii inflated by rho at apex c: a ray from p through a point g of the light's bounding sphere
-//      that meets the primitive's bounding sphere, translated by -delta, is a ray from c through B(l, R_l + rho) that
-//      meets B(v, R + rho); if no such ray exists at c, none exists at p.  Class (a): no candidate at all.
-//  (b) pyramid test at apex c: side plane j through c and light edge (j, j+1), inward unit normal n: f(x) = n.(x - c).
-//      The light quad has f >= 0, every apex has f(p) >= -rho, so every SEGMENT p -> g has f >= -rho.  A primitive whose
-//      four corners have f < -(rho + margin) cannot be met between the node and the light: it can only be hit BEYOND the
-//      light (t > ldist), which never occludes (sq_ldist - t^2 <= 0 < 0.002).  That is a class (b) "harmless root": it
-//      is skipped only for nodes that hold a certificate, exactly like the same-side planes.
-// A warp whose nodes are far apart (rho large) simply keeps every bounded primitive.
-__device__ __forceinline__ void cull_region_bounded(const DevScene& sc, const DevCull* __restrict__ cull, int li, D3 c, double rho,
-                                                    int lane, unsigned long long& keep_mask, unsigned long long& harmless_mask) {
-  const unsigned FULL = 0xffffffffu;
-  const CullLight& cl = cull->light[li];
-  const D3 u = ld3(cl.c) - c;
-  const double uu = dot(u, u);
-  const bool sane = uu < 1e6 && rho < 1e3;            // absurd scale or NaN: no culling
-  const double rl = cl.r + rho;
-  const double ucone = uu - rl * rl;
-  const bool cone = sane && ucone > 0.0;              // every node of the ball is outside the light's bounding sphere
-  const double L = sqrt(uu) + rl;
-  const bool off_light_plane = sane && fabs(dot(ld3(cl.nl), u)) > rho + 1e-6 * (1.0 + L);   // ... and off the light's plane
-  // side planes of the pyramid apex c over the light quad (every lane builds the same four planes)
-  D3 pn[4];
-  double pnn[4];
-  bool pyr_ok = off_light_plane;
-  {
-    D3 a[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) a[j] = ld3(cl.corner[j]) - c;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const D3 n = cross(a[j], a[(j + 1) & 3]);
-      const double nn = dot(n, n);
-      const double s = dot(n, a[(j + 2) & 3]);
-      pyr_ok = pyr_ok && nn > 1e-12 * (dot(a[j], a[j]) * dot(a[(j + 1) & 3], a[(j + 1) & 3])) &&
-               s * s > 1e-12 * (nn * dot(a[(j + 2) & 3], a[(j + 2) & 3]));
-      pn[j] = s < 0.0 ? -n : n;
-      pnn[j] = nn;
-    }
-  }
-  const double rm = rho * (1.0 + 1e-6) + 1e-7;        // distance margin of the side-plane test
-  const double rm2 = rm * rm;
-  keep_mask = 0ull; harmless_mask = 0ull;
-  for (int base = 0; base < sc.nprims; base += 32) {
-    const int o = base + lane;
-    bool keep = false, harmless = false;
-    if (o < sc.nprims) {
-      const CullPrim& cp = cull->prim[o];
-      if (cp.kind == 3 || (cp.kind == 2 && !sane)) keep = true;
-      else if (cp.kind == 2) {
-        if (off_light_plane && ((cl.coplanar >> o) & 1ull)) harmless = true;       // the emitter's own geometry
-        else {
-          keep = true;
-          if (cone) {
-            const D3 v = ld3(cp.c) - c;
-            const double vv = dot(v, v);
-            const double R = cp.r + rho;
-            const double vcone = vv - R * R;
-            if (vcone > 0.0 && vv < 1e12) {
-              const double rhs = (sqrt(ucone * vcone) - rl * R) - 1e-7 * (uu + vv);
-              keep = !(dot(u, v) < rhs);
-            }
-          }
-          if (keep && cp.nvtx == 4 && pyr_ok) {
-            D3 w[4];
-            double ww[4];
-            bool finite = true;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) { w[k] = ld3(cp.vtx[k]) - c; ww[k] = dot(w[k], w[k]); finite = finite && ww[k] < 1e12; }
-            bool out_any = false;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              bool all_out = finite;
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const double d = dot(pn[j], w[k]);
-                all_out = all_out && d < 0.0 && d * d > rm2 * pnn[j] && d * d > 1e-12 * (pnn[j] * ww[k]);
-              }
-              out_any = out_any || all_out;
-            }
-            if (out_any) { keep = false; harmless = true; }   // can only be hit beyond the light
-          }
-        }
-      }
-    }
-    keep_mask |= (unsigned long long)__ballot_sync(FULL, keep) << base;
-    harmless_mask |= (unsigned long long)__ballot_sync(FULL, harmless) << base;
-  }
-}
-// per-node part: the planes (same criteria as cull_classify) -> planes to test, harmless planes, certificate
-__device__ __forceinline__ void cull_node_planes(const DevScene& sc, const DevCull* __restrict__ cull, int li, D3 p,
-                                                 unsigned long long& mask, unsigned long long& harmless, bool& cert, bool& sane) {
-  const CullLight& cl = cull->light[li];
-  const D3 u = ld3(cl.c) - p;
-  const double uu = dot(u, u);
-  mask = 0ull; harmless = 0ull; cert = false;
-  sane = uu < 1e6;
-  if (!sane) return;
-  const double L = sqrt(uu) + cl.r;                   // every ldist is below this
-  const int np = sc.nprims;
-  for (int o = 0; o < np; ++o) {
-    const CullPrim& cp = cull->prim[o];
-    if (cp.kind != 1) continue;
-    const unsigned long long bit = 1ull << o;
-    const ppm_prim& s = sc.prims[o];
-    const double num = s.scalar + dot(ld3(s.nvec), p);
-    const double D = cp.c[0], gap = cp.c[1];
-    const double hmin = cl.hmin[o], hmax = cl.hmax[o];
-    if (num > D && hmin > D) { harmless |= bit; if (hmax < num - gap) cert = true; }
-    else if (num < -D && hmax < -D) { harmless |= bit; if (hmin > num + gap) cert = true; }
-    else {
-      const double habs = hmin > D ? hmin : (hmax < -D ? -hmax : 0.0);
-      const double an = fabs(num);
-      if (!(habs > 0.0 && an * L < 0.4999e-4 * (habs - an))) mask |= bit;
-    }
-  }
-}
-// One warp per 32 consecutive nodes (in `order` if given -- the same slots k_direct_light's warps use): bounding ball of
-// the 32 positions, then one bounded primitive per lane.  region[li * nw + w] = (keep, harmless).
-__global__ void __launch_bounds__(128)
-k_dl_region(const __grid_constant__ DevScene sc, const DevCull* __restrict__ cull, const uint32_t* __restrict__ order,
-            const double* __restrict__ pos3, int64_t n, ulonglong2* __restrict__ region) {
-  const int64_t nw = (n + 31) >> 5;
-  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (w >= nw) return;
-  const int lane = (int)(threadIdx.x & 31u);
-  int64_t slot = w * 32 + lane;
-  if (slot >= n) slot = n - 1;                         // idle lanes of the last warp shadow the last node, as in k_direct_light
-  const int64_t node = order ? (int64_t)order[slot] : slot;
-  const D3 p = ld3(pos3 + node * 3);
-  double lx = p.x, ly = p.y, lz = p.z, hx = p.x, hy = p.y, hz = p.z;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    lx = fmin(lx, __shfl_xor_sync(0xffffffffu, lx, o)); hx = fmax(hx, __shfl_xor_sync(0xffffffffu, hx, o));
-    ly = fmin(ly, __shfl_xor_sync(0xffffffffu, ly, o)); hy = fmax(hy, __shfl_xor_sync(0xffffffffu, hy, o));
-    lz = fmin(lz, __shfl_xor_sync(0xffffffffu, lz, o)); hz = fmax(hz, __shfl_xor_sync(0xffffffffu, hz, o));
-  }
-  const bool nan_any = __any_sync(0xffffffffu, !(p.x == p.x) || !(p.y == p.y) || !(p.z == p.z));   // fmin / fmax drop NaNs
-  const D3 c = mk3(0.5 * (lx + hx), 0.5 * (ly + hy), 0.5 * (lz + hz));
-  const D3 h = mk3(hx - c.x, hy - c.y, hz - c.z);
-  const D3 h2 = mk3(c.x - lx, c.y - ly, c.z - lz);
-  const double rho = nan_any ? 1e300 : sqrt(fmax(dot(h, h), dot(h2, h2))) * (1.0 + 1e-6) + 1e-9;
-  for (int li = 0; li < sc.nlights; ++li) {
-    unsigned long long keep = 0ull, harm = 0ull;
-    if (sc.lights[li].type == PPM_LIGHT_PARALLELOGRAM) cull_region_bounded(sc, cull, li, c, rho, lane, keep, harm);
-    if (lane == 0) region[(int64_t)li * nw + w] = make_ulonglong2(keep, harm);
-  }
-}
-#endif  // PPM_DL_REGION
-
 __device__ __forceinline__ double ts5(unsigned i) {   // the literals 0.1, 0.3, 0.5, 0.7, 0.9 (light.rs:164-170)
   return i == 0 ? 0.1 : (i == 1 ? 0.3 : (i == 2 ? 0.5 : (i == 3 ? 0.7 : 0.9)));
 }
@@ -480,11 +320,7 @@ __device__ __forceinline__ double ts5(unsigned i) {   // the literals 0.1, 0.3, 
 __global__ void __launch_bounds__(128, PPM_DL_MINB)
 k_direct_light(const __grid_constant__ DevScene sc, const unsigned long long* __restrict__ masks, const uint32_t* __restrict__ order,
                const double* __restrict__ pos3, const double* __restrict__ nrm3, int64_t n, double* __restrict__ out3,
-               unsigned long long* __restrict__ dbg
-#if PPM_DL_REGION
-               , const DevCull* __restrict__ cull, const ulonglong2* __restrict__ region
-#endif
-               ) {
+               unsigned long long* __restrict__ dbg) {
   __shared__ double s_gp[25][3];
   const int64_t node0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = node0 < n;
@@ -510,25 +346,6 @@ k_direct_light(const __grid_constant__ DevScene sc, const unsigned long long* __
     __syncthreads();
     bool cert = false;
     unsigned long long mask = all;
-#if PPM_DL_REGION
-    if (cull) {
-      // bounded primitives: classified once per warp of (cell-sorted) nodes by k_dl_region; planes: per node, here
-      const int64_t nw = (n + 31) >> 5;
-      const ulonglong2 rg = region[(int64_t)li * nw + min(node0 >> 5, nw - 1)];   // idle warps shadow the last node      // x = keep, y = harmless (hit only beyond the light)
-      unsigned long long pl_mask, pl_harm;
-      bool sane;
-      cull_node_planes(sc, cull, li, p, pl_mask, pl_harm, cert, sane);
-      const unsigned long long own = sane ? (rg.x | pl_mask | (cert ? 0ull : (rg.y | pl_harm))) : all;
-      const unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)own);
-      const unsigned hi = __reduce_or_sync(0xffffffffu, (unsigned)(own >> 32));
-      mask = ((unsigned long long)hi << 32) | lo;
-      if (dbg && live) {
-        atomicAdd(dbg, 1ull); atomicAdd(dbg + 1, (unsigned long long)__popcll(own));
-        atomicAdd(dbg + 2, (unsigned long long)__popcll(mask)); atomicAdd(dbg + 3, cert ? 1ull : 0ull);
-        atomicAdd(dbg + 4 + min(__popcll(own), 7), 1ull); atomicAdd(dbg + 12 + min(__popcll(mask), 7), 1ull);
-      }
-    } else
-#endif
     if (masks) {
       const unsigned long long own = masks[(int64_t)li * n + node];     // k_dl_classify
       cert = (own & PPM_CULL_CERT) != 0ull;

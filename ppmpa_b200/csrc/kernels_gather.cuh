@@ -98,56 +98,6 @@ __device__ __forceinline__ uint32_t gather_group_runs(const Grid& g, const uint3
   __syncwarp();
   return total;
 }
-#ifndef GATHER_PIPE
-#define GATHER_PIPE 0        // 1 = experimental: the NEXT group's run look-ups are issued before the current group's chunks
-#endif
-#if GATHER_PIPE
-// ---- experimental (round-2 candidate, NOT the shipped path; tools/build_variants.sh pipe:-DGATHER_PIPE=1) ----------------
-// In the small-radius regime every group is one short chunk and the warp waits for two dependent memory round trips per
-// group (run look-ups, then photons).  Group formation only depends on the sorted keys, so the next group is formed and
-// its nine run look-ups are issued BEFORE the current group's candidates are processed: their latency hides behind the
-// current chunk.  Same groups, same order, same sums as the plain loop.
-__device__ __forceinline__ void gather_form_group(unsigned& pending, bool valid, uint32_t key, const Grid& g,
-                                                  const uint32_t* __restrict__ cell_start, int lane, uint32_t& ck, uint32_t& klast,
-                                                  bool& act, unsigned& grp, uint32_t& rbeg, uint32_t& rend) {
-  constexpr int REACH = 1, W = 2 * REACH + 1, ROWS = W * W;
-  const unsigned FULL = 0xffffffffu;
-  const uint32_t nxp = (uint32_t)g.nx, nyp = (uint32_t)g.ny;
-  const int leader = __ffs(pending) - 1;
-  ck = __shfl_sync(FULL, key, leader);
-  act = valid && key >= ck && key - ck <= (uint32_t)GATHER_SPAN && key / nxp == ck / nxp;
-  grp = __ballot_sync(FULL, act);
-  pending &= ~grp;
-  klast = __shfl_sync(FULL, key, 31 - __clz((int)grp));
-  const int cx = (int)(ck % nxp), cy = (int)((ck / nxp) % nyp), cz = (int)(ck / (nxp * nyp));
-  const int x0 = max(cx - REACH, 0), x1 = min((int)(klast % nxp) + REACH, g.nx - 1);
-  rbeg = 0; rend = 0;
-  if (lane < ROWS && x0 <= x1) {
-    const int z = cz + lane / W - REACH, y = cy + lane % W - REACH;
-    if (z >= 0 && z < g.nz && y >= 0 && y < g.ny) {
-      const uint32_t row = ((uint32_t)z * (uint32_t)g.ny + (uint32_t)y) * (uint32_t)g.nx;
-      rbeg = cell_start[row + x0];                    // global loads: consumed by gather_group_scan one iteration later
-      rend = cell_start[row + x1 + 1];
-    }
-  }
-}
-__device__ __forceinline__ uint32_t gather_group_scan(uint32_t rbeg, uint32_t rend, int lane, uint32_t* sEnd, uint32_t* sOff) {
-  const unsigned FULL = 0xffffffffu;
-  const uint32_t rlen = rend - rbeg;
-  uint32_t pre = rlen;                               // inclusive prefix of the run lengths
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    uint32_t t = __shfl_up_sync(FULL, pre, o);
-    if (lane >= o) pre += t;
-  }
-  const uint32_t total = __shfl_sync(FULL, pre, 31);
-  __syncwarp();
-  sEnd[lane] = pre;
-  sOff[lane] = rbeg - (pre - rlen);
-  __syncwarp();
-  return total;
-}
-#endif
 // chunks base = first, first + stride, ... of the candidate stream: stage 32 candidates, test them against the lane's query
 template <int FILTER, int MODE>
 __device__ __forceinline__ void gather_chunks(const MapSoA& m, uint32_t total, uint32_t first, uint32_t stride, int lane, bool act,
@@ -221,46 +171,6 @@ k_gather(Grid g, const uint32_t* __restrict__ cell_start, MapSoA m, const uint32
   uint32_t cnt = 0;
   bool deferred = false;                               // this lane's query was handed to k_gather_heavy
   const uint32_t nxp = (uint32_t)g.nx;
-#if GATHER_PIPE
-  unsigned pending = __ballot_sync(FULL, valid);
-  uint32_t ck = 0, klast = 0, rbeg = 0, rend = 0;
-  bool act = false;
-  unsigned grp = 0;
-  bool have = pending != 0u;
-  if (have) gather_form_group(pending, valid, key, g, cell_start, lane, ck, klast, act, grp, rbeg, rend);
-  while (have) {
-    // the next group (keys only) and its run look-ups, before the current group's candidates are touched
-    const bool have_next = pending != 0u;
-    uint32_t nck = 0, nklast = 0, nrbeg = 0, nrend = 0;
-    bool nact = false;
-    unsigned ngrp = 0;
-    if (have_next) gather_form_group(pending, valid, key, g, cell_start, lane, nck, nklast, nact, ngrp, nrbeg, nrend);
-    const uint32_t total = gather_group_scan(rbeg, rend, lane, sEnd[warp], sOff[warp]);
-    bool published = false;
-    if (hl.ctr && total > GATHER_HEAVY_MIN) {
-      const uint32_t nparts = min(GATHER_HEAVY_MAXPARTS, (total + GATHER_HEAVY_MIN - 1u) / GATHER_HEAVY_MIN);
-      uint32_t part0 = 0xFFFFFFFFu;
-      if (lane == 0) {
-        if (*(volatile unsigned int*)hl.ctr < hl.cap_parts) {
-          const unsigned int old = atomicAdd(hl.ctr, nparts);
-          if (old + nparts <= hl.cap_parts) { part0 = old; atomicMax(hl.ctr + 3, old + nparts); }
-        }
-        if (part0 != 0xFFFFFFFFu) {
-          const unsigned int gs = atomicAdd(hl.ctr + 2, 1u);   // groups <= parts / 2: cannot overflow
-          HeavyGroup* h = hl.groups + gs;
-          h->s_base = (uint32_t)s_base; h->grp = grp; h->ck = ck; h->klast = klast; h->nparts = nparts; h->part0 = part0; h->done = 0u;
-          for (uint32_t k = 0; k < nparts; ++k) hl.parts[part0 + k].group = gs;
-        }
-      }
-      part0 = __shfl_sync(FULL, part0, 0);
-      if (part0 != 0xFFFFFFFFu) { published = true; if (act) deferred = true; }
-    }
-    if (!published)
-      gather_chunks<FILTER, MODE>(m, total, 0u, 32u, lane, act, sEnd[warp], sOff[warp], sP[warp], sD[warp], qx, qy, qz, nv, r2, power,
-                                  rr, rg, rb, cnt);
-    ck = nck; klast = nklast; act = nact; grp = ngrp; rbeg = nrbeg; rend = nrend; have = have_next;
-  }
-#else
   unsigned pending = __ballot_sync(FULL, valid);
   while (pending) {
     const int leader = __ffs(pending) - 1;
@@ -301,7 +211,6 @@ k_gather(Grid g, const uint32_t* __restrict__ cell_start, MapSoA m, const uint32
     gather_chunks<FILTER, MODE>(m, total, 0u, 32u, lane, act, sEnd[warp], sOff[warp], sP[warp], sD[warp], qx, qy, qz, nv, r2, power,
                                 rr, rg, rb, cnt);
   }
-#endif
   if (valid && !deferred) {
     if (MODE != 2) {
       const double sc = (1.0 / PPM_PI) / r2;          // rad * (ONE_PI / radius), tracer.rs:193
