@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define PPM_ABI_VERSION 1
+#define PPM_ABI_VERSION 2
 
 /* ---- error codes ------------------------------------------------------ */
 enum {
@@ -195,6 +195,16 @@ void ppm_destroy(ppm_ctx* ctx);
 const char* ppm_last_error(const ppm_ctx* ctx);   /* never NULL */
 /* the CUDA stream the ctx launches on (a cudaStream_t), for event timing */
 void* ppm_stream(ppm_ctx* ctx);
+/* Engine switches (diagnostics and tests; none changes a result except where stated).  The environment
+ * variables PPM_<NAME> are read ONCE, at ppm_create, as initial values.
+ *   "lanes"         passes of one ppm_render_passes batch rendered concurrently on this GPU (default 2)
+ *   "dl_cull"       1 = conservative shadow-ray culling in the classic direct light (bit-identical to 0)
+ *   "gather_heavy"  1 = split very long candidate streams over many warps (changes only the summation order)
+ *   "dl_stats"      1 = print culling statistics to stderr
+ *   "graph"         1 = whole passes run as CUDA graphs without host round trips (default), 0 = stream mode
+ * Unknown names return PPM_ERR_ARG. */
+int  ppm_option_set(ppm_ctx* ctx, const char* name, int64_t value);
+int  ppm_option_get(ppm_ctx* ctx, const char* name, int64_t* value);
 
 /* replaces the (lgts, objs) pair read_scene returns, scene.rs:443-447 */
 int  ppm_scene_set(ppm_ctx* ctx, const ppm_prim* prims, int32_t nprims,
@@ -298,17 +308,37 @@ int  ppm_pass_image_read(ppm_ctx* ctx, double* rgb3_h_or_d);
 int  ppm_accum_reset(ppm_ctx* ctx);
 int  ppm_accum_read(ppm_ctx* ctx, double* rgb3_h_or_d, uint32_t* n_pass);
 /* raw device pointers of the accumulator (3*W*H doubles) and pass counter
- * (1 double, so both reduce in one dtype) for the per-frame NCCL reduce */
+ * (1 double, so both reduce in one dtype).  The pointers stay valid until the
+ * camera resolution changes or the ctx is destroyed. */
 int  ppm_accum_device(ppm_ctx* ctx, void** sum_dev, void** npass_dev, uint64_t* n_doubles);
-/* mean image: sum / n_pass (averager2.rb:86) */
+/* mean image: sum / n_pass (averager2.rb:86).  PPM_ERR_STATE if no pass has been accumulated. */
 int  ppm_image_mean(ppm_ctx* ctx, double* rgb3_h_or_d);
 
-/* per-phase device times (ms, CUDA events on the ctx stream) of the last
- * ppm_render_pass: [0] photon trace, [1] map build, [2] eye expand,
- * [3] direct light, [4] gather (query sort + kernel), [5] combine+accumulate, [6] total,
- * [7] the k_gather kernel alone;
+/* -- multi-GPU frame: the passes of a frame are independent (util/iterator.rb:90-117 runs them as
+ *    separate processes) and the frame is their plain sum (util/averager2.rb:49-62,86).  Every rank
+ *    renders its own pass ids into its own accumulator; ONE sum-reduce of [3*W*H sums | pass count]
+ *    (f64) per frame combines them.  The collective is NCCL, loaded at run time (libnccl.so.2, the
+ *    copy already mapped into the process if there is one); no other exchange exists on this path.
+ *    ppm_comm_unique_id: rank 0 makes the 128-byte NCCL id and hands it to the other ranks by the
+ *    host's own means (file, pipe, MPI, torch.distributed ...).
+ *    ppm_comm_init: ncclCommInitRank on the ctx's GPU; the communicator is owned by the ctx.
+ *    ppm_accum_reduce: in-place sum of the accumulator onto `root` (root < 0: onto every rank) on
+ *    the ctx stream, over `nccl_comm` (an ncclComm_t made by the caller) or, when NULL, over the
+ *    ctx's own communicator.  Returns after the reduce has completed. */
+int  ppm_comm_unique_id(void* id128);
+int  ppm_comm_init(ppm_ctx* ctx, int32_t nranks, int32_t rank, const void* id128);
+int  ppm_comm_destroy(ppm_ctx* ctx);
+int  ppm_accum_reduce(ppm_ctx* ctx, void* nccl_comm, int32_t root);
+
+/* per-phase device times (ms) of the last ppm_render_pass, or batch totals over the passes of the last
+ * ppm_render_passes (phases of different passes overlap: the sum of [6] exceeds the wall time of a batch).  Taken
+ * from %globaltimer stamps the pass writes at its phase boundaries on the device, in stream order; with the "graph"
+ * switch off, [7] comes from CUDA events recorded around k_gather instead.
+ * [0] photon trace, [1] map build, [2] eye expand, [3] direct light, [4] gather (query sort + kernels),
+ * [5] combine+accumulate, [6] whole pass, [7] k_gather (+ heavy parts) alone;
  * counters: [0] emitted, [1] stored records, [2] eye nodes, [3] gather nodes,
- * [4] sum of K (photons within r over all gather nodes), [5] kernel launches */
+ * [4] sum of K (photons within r over all gather nodes), [5] kernel launches,
+ * [6] candidate distance tests of k_gather, [7] passes rendered again after a buffer overflow */
 int  ppm_last_pass_stats(ppm_ctx* ctx, double ms[8], uint64_t counters[8]);
 
 /* ---- output formats (host) -------------------------------------------- */

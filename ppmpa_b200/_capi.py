@@ -99,6 +99,8 @@ SIGNATURES = {
     "ppm_destroy": (None, [vp]),
     "ppm_last_error": (C.c_char_p, [vp]),
     "ppm_stream": (vp, [vp]),
+    "ppm_option_set": (C.c_int, [vp, C.c_char_p, i64]),
+    "ppm_option_get": (C.c_int, [vp, C.c_char_p, P(i64)]),
     "ppm_scene_set": (C.c_int, [vp, P(Prim), i32, P(Material), i32, P(Light), i32]),
     "ppm_camera_set": (C.c_int, [vp, P(Camera)]),
     "ppm_intersect": (C.c_int, [vp, vp, i64, vp, vp, vp, vp, vp]),
@@ -122,6 +124,10 @@ SIGNATURES = {
     "ppm_accum_read": (C.c_int, [vp, vp, P(u32)]),
     "ppm_accum_device": (C.c_int, [vp, P(vp), P(vp), P(u64)]),
     "ppm_image_mean": (C.c_int, [vp, vp]),
+    "ppm_comm_unique_id": (C.c_int, [vp]),
+    "ppm_comm_init": (C.c_int, [vp, i32, i32, vp]),
+    "ppm_comm_destroy": (C.c_int, [vp]),
+    "ppm_accum_reduce": (C.c_int, [vp, vp, i32]),
     "ppm_last_pass_stats": (C.c_int, [vp, P(dbl), P(u64)]),
     "ppm_format_f64": (C.c_int, [dbl, C.c_int, C.c_char_p, C.c_size_t]),
     "ppm_radiance_to_rgb": (None, [dbl, D3, P(i32)]),

@@ -1,33 +1,39 @@
 // engine.cu -- CUDA engine behind include/ppm.h (sm_100a, f64, no FMA).
 //
-// This file holds the context, the host-side orchestration (streams, lanes, buffers) and the C ABI.
+// This file holds the context, the host-side orchestration (streams, lanes, buffers, CUDA graphs) and the C ABI.
 // The kernels live in headers of the same translation unit (one per hot-path stage of SURVEY.md 8a):
+//   pass_state.cuh      PassDev: the device-resident state of a pass (grid, radius, RNG keys, counters, stamps)
 //   kernels_photon.cuh  k_intersect (calc_intersection probe, tracer.rs:306-350), k_emit (light.rs:67-91),
 //                       k_trace_photons (tracer.rs:31-125), k_import / k_export
-//   kernels_map.cuh     k_bbox, k_axis_hist, k_cell_key, k_scatter: the photon map as a radix-sorted uniform
-//                       grid (replaces the kd-tree of photonmap.rs:23-29)
-//   kernels_gather.cuh  k_query_key, k_gather (estimate_radiance, tracer.rs:179-216), k_knn_*, k_within
+//   kernels_map.cuh     compact cell index, device-length scans, hand-written stable radix sort, counting sort of
+//                       the queries (replaces the kd-tree of photonmap.rs:23-29)
+//   kernels_gather.cuh  k_gather (estimate_radiance, tracer.rs:179-216), k_gather_heavy, k_knn_*, k_within
 //   kernels_eye.cuh     k_gen_rays (camera.rs:58-75), k_eye_expand (trace_ray, tracer.rs:129-177),
 //                       k_direct_light (tracer.rs:263-290), k_combine (surface.rs:135-206, averager2.rb:49-62)
 //   dev_core.cuh        f64 math in reference order, Philox, nearest_hit, BSDF sampling
+//
+// A whole pass (ppmpa.rs:74-84) is a FIXED sequence of launches with fixed arguments: every size that used to be read
+// back (record count, node count, occupied cells, heavy parts) stays in PassDev, grids are sized for the buffer
+// capacities and kernels return early.  The sequence is captured once per lane as a CUDA graph; a batch of passes
+// (util/iterator.rb:96-117) is N graph launches and ONE synchronisation at the end, where the per-pass reports
+// (PassOut) are read and passes that overflowed a buffer are rendered again with larger buffers.
 #include "dev_core.cuh"
+#include "pass_state.cuh"
 #include "kernels_photon.cuh"
 #include "kernels_map.cuh"
 #include "kernels_gather.cuh"
 #include "kernels_eye.cuh"
+#include "cull_table.cuh"
 
-#include <cub/device/device_radix_sort.cuh>
-#include <cub/device/device_scan.cuh>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <array>
-#include <chrono>
 #include <cmath>
 #include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <string>
-#include <thread>
 #include <vector>
 
 // ===========================================================================
@@ -36,11 +42,11 @@
 struct DBuf {
   void* p = nullptr;
   size_t cap = 0;
-  cudaError_t ensure(size_t bytes) {
-    if (bytes <= cap) return cudaSuccess;
+  // grows to exactly what is asked (+ 1/16 slack): capacities are calibrated per scene, not doubled
+  cudaError_t grow(size_t bytes) {
     if (p) cudaFree(p);
     p = nullptr; cap = 0;
-    size_t want = bytes * 2 + 256;   // geometric growth: steady state never reallocates
+    size_t want = bytes + bytes / 16 + 256;
     cudaError_t e = cudaMalloc(&p, want);
     if (e == cudaSuccess) cap = want;
     return e;
@@ -49,52 +55,87 @@ struct DBuf {
   template <typename T> T* as() const { return (T*)p; }
 };
 
+#define PPM_DEFAULT_LANES 2
+#define PPM_MAX_LANES 8
+#define PPM_CAL_PASS 0xFFFFFFFFu        // Philox pass id of the per-scene calibration (never a rendered pass)
+#define PPM_CAL_PHOTONS (1 << 17)
+
+struct CalKey {
+  uint64_t scene_ver = 0, cam_ver = 0, seed = 0;
+  int64_t nphoton = 0;
+  int uc = 0;
+  bool operator==(const CalKey& o) const { return scene_ver == o.scene_ver && cam_ver == o.cam_ver && seed == o.seed && nphoton == o.nphoton && uc == o.uc; }
+};
+struct GraphKey {
+  uint64_t scene_ver = 0, cam_ver = 0, buf_gen = 0, rec_cap = 0, eye_cap = 0;
+  int64_t nphoton = 0;
+  int uc = 0, cull = 0, heavy = 0, accumulate = 0;
+  bool operator==(const GraphKey& o) const {
+    return scene_ver == o.scene_ver && cam_ver == o.cam_ver && buf_gen == o.buf_gen && rec_cap == o.rec_cap && eye_cap == o.eye_cap &&
+           nphoton == o.nphoton && uc == o.uc && cull == o.cull && heavy == o.heavy && accumulate == o.accumulate;
+  }
+};
+
 struct ppm_ctx {
   int device = 0;
   int sm_count = 148;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;     // photon branch + gather + combine (highest priority)
+  cudaStream_t stream2 = nullptr;    // eye branch: expansion, classification, query sort, direct light
   std::string err;
   bool have_scene = false, have_camera = false, have_map = false;
+  uint64_t scene_ver = 0, cam_ver = 0, buf_gen = 0;
   DevScene scene;
-  DBuf dl_dbg, dl_masks;
-  const unsigned long long* dl_masks_cur = nullptr;   // masks of the current node list (render_pass)
-  DBuf cull;                      // DevCull: per-scene table for the shadow-ray culling of k_direct_light
   ppm_camera cam;
-  // unsorted records
-  DBuf r_pos, r_dir, r_wl, r_tag, counter;
+  // switches (ppm_option_set; initial values from the environment, read once at ppm_create)
+  int opt_lanes = PPM_DEFAULT_LANES, opt_dl_cull = 1, opt_gather_heavy = 1, opt_dl_stats = 0, opt_graph = 1;
+  // pass state: device copy, host mirror (probe entry points), batch table and per-pass reports
+  PassDev* ps = nullptr;
+  PassDev hps;
+  BatchDev* bt = nullptr;
+  BatchDev* bt_h = nullptr;          // pinned
+  PassOut* out = nullptr;
+  PassOut* out_h = nullptr;          // pinned
+  // unsorted records of the current photon set
+  DBuf r_pos, r_dir, r_wl, r_tag, pmask, pbase;
   uint64_t n_rec = 0;
-  int tag_bits = 38;              // bits of the largest record tag (photon << 4 | depth) of the current photon set
+  bool rec_traced = false;           // records come from k_trace_photons (pmask valid) rather than an import
+  uint64_t rec_nphoton = 0;          // emitted photons of the traced set
   double power = 0.0;
-  // map
-  DBuf keys, keys2, vals, vals2, cub_tmp, cell_start, hist, bbox, axis_hist;
+  // map build
+  DBuf order0, cid, words_p, start_p, key_a, key_b, val_a, val_b, rs_table, tsum_p;
   DBuf m_P, m_D, m_orig;
-  DBuf q_key, q_key2, q_idx, q_idx2, heavy;
-  DBuf knn_lo, knn_hi, knn_thr, knn_cnt;
-  Grid grid;
-  double r2 = 0.0;
+  DBuf bbox, axis_hist;
+  // query sort + gather
+  DBuf qcell, words_q, qcnt, qstart, qrank, qpic, skey, sidx, tsum_q, heavy;
+  DBuf knn_lo, knn_hi, knn_thr, knn_cnt, knn_act;
   // staging for h_or_d arguments
   DBuf st_in0, st_in1, st_out0, st_out1, st_out2, st_out3, st_out4;
   // eye path
-  DBuf e_head, e_prev, e_pos, e_nrm, e_w, e_emit, e_direct, e_photon, e_rays;
-  uint64_t eye_cap = 0;            // capacity of the gather-node pool
-  DBuf pass_img, accum, npass, stats;
+  DBuf e_head, e_prev, e_pos, e_nrm, e_w, e_emit, e_direct, e_photon;
+  DBuf dl_dbg, dl_masks, cull;
+  uint64_t eye_cap = 0;              // capacity of the gather-node pool (probe entry points grow it)
+  uint64_t rec_cap = 0;              // rendered pass: capacity of the record buffers
+  uint64_t pass_eye_cap = 0;         // rendered pass: capacity of the gather-node pool
+  Bounds cal_bounds;                 // rendered pass: grid region (per-scene calibration)
+  int cal_have_bounds = 0;
+  DBuf pass_img, accum;
   uint64_t accum_pixels = 0;
-  // last pass stats
+  // per-scene calibration: grid region, record and node capacities
+  bool cal_valid = false;
+  CalKey cal_key;
+  // the pass as a CUDA graph
+  cudaGraphExec_t gexec = nullptr;
+  GraphKey gkey;
+  uint64_t graph_kernels = 0;
+  enum { EV_FORK, EV_NODES, EV_DL, EV_G0, EV_G1, EV_COUNT };
+  cudaEvent_t ev[EV_COUNT] = {nullptr};
+  // last pass / batch stats
   double ms[8] = {0};
   uint64_t counters[8] = {0};
-  // Two streams: the photon branch (trace -> map build) and the eye branch (expand -> direct
-  // light) of a pass are independent until the gather, so render_pass runs them concurrently.
-  cudaStream_t stream2 = nullptr;
-  DBuf cub_tmp2;
-  enum { EV_A0, EV_A1, EV_A2, EV_A3, EV_A4, EV_A5, EV_A6, EV_A7, EV_A8, EV_B0, EV_B1, EV_B2, EV_B3, EV_COUNT };
-  cudaEvent_t ev[EV_COUNT] = {nullptr};
-  bool timed = false;             // record the phase events (render_pass only)
   uint64_t launches = 0;
-  std::vector<ppm_ctx*> twins;    // further lanes on the same GPU (ppm_render_passes), owned
+  std::vector<ppm_ctx*> twins;       // further lanes on the same GPU (ppm_render_passes), owned
+  void* comm = nullptr;              // ncclComm_t owned by the ctx (ppm_comm_init)
 };
-
-#define PPM_DEFAULT_LANES 2
-#define PPM_MAX_LANES 8
 
 namespace {
 
@@ -115,8 +156,17 @@ namespace {
       return PPM_ERR_CUDA;                                                                 \
     }                                                                                      \
   } while (0)
+#define RC(call) do { int rc__ = (call); if (rc__) return rc__; } while (0)
 
 int fail(ppm_ctx* c, int code, const std::string& m) { if (c) c->err = m; return code; }
+
+// device buffer of at least `bytes`; a reallocation invalidates the captured graph (its nodes hold the old pointers)
+int ens(ppm_ctx* c, DBuf& b, size_t bytes) {
+  if (bytes <= b.cap && b.p) return PPM_OK;
+  c->buf_gen++;
+  CK(c, b.grow(bytes ? bytes : 1));
+  return PPM_OK;
+}
 
 bool is_device_ptr(const void* p) {
   if (!p) return false;
@@ -127,7 +177,7 @@ bool is_device_ptr(const void* p) {
 // input: returns a device pointer holding `bytes` of user data
 int stage_in(ppm_ctx* c, const void* user, size_t bytes, DBuf& scratch, const void** dev) {
   if (is_device_ptr(user)) { *dev = user; return PPM_OK; }
-  CK(c, scratch.ensure(bytes));
+  RC(ens(c, scratch, bytes));
   CK(c, cudaMemcpyAsync(scratch.p, user, bytes, cudaMemcpyHostToDevice, c->stream));
   *dev = scratch.p;
   return PPM_OK;
@@ -136,7 +186,7 @@ int stage_in(ppm_ctx* c, const void* user, size_t bytes, DBuf& scratch, const vo
 int stage_out(ppm_ctx* c, void* user, size_t bytes, DBuf& scratch, void** dev) {
   if (!user) { *dev = nullptr; return PPM_OK; }
   if (is_device_ptr(user)) { *dev = user; return PPM_OK; }
-  CK(c, scratch.ensure(bytes));
+  RC(ens(c, scratch, bytes));
   *dev = scratch.p;
   return PPM_OK;
 }
@@ -145,30 +195,106 @@ int finish_out(ppm_ctx* c, void* user, size_t bytes, void* dev) {
   CK(c, cudaMemcpyAsync(user, dev, bytes, cudaMemcpyDeviceToHost, c->stream));
   return PPM_OK;
 }
-inline unsigned nblk(int64_t n, int b) { return (unsigned)((n + b - 1) / b); }
+inline unsigned nblk(int64_t n, int b) { return (unsigned)std::max<int64_t>(1, (n + b - 1) / b); }
+
+// host mirror <-> device pass state (probe entry points; a rendered pass never does this)
+int push_ps(ppm_ctx* c) {
+  CK(c, cudaMemcpyAsync(c->ps, &c->hps, sizeof(PassDev), cudaMemcpyHostToDevice, c->stream));
+  return PPM_OK;
+}
+int pull_ps(ppm_ctx* c) {
+  CK(c, cudaMemcpyAsync(&c->hps, c->ps, sizeof(PassDev), cudaMemcpyDeviceToHost, c->stream));
+  CK(c, cudaStreamSynchronize(c->stream));
+  return PPM_OK;
+}
 
 RecBuf recbuf(ppm_ctx* c) {
   RecBuf r;
   r.pos3 = c->r_pos.as<double>(); r.dir3 = c->r_dir.as<double>(); r.wl = c->r_wl.as<uint8_t>(); r.tag = c->r_tag.as<uint64_t>();
   return r;
 }
-int ensure_records(ppm_ctx* c, uint64_t cap) {
-  CK(c, c->r_pos.ensure(cap * 24)); CK(c, c->r_dir.ensure(cap * 24));
-  CK(c, c->r_wl.ensure(cap)); CK(c, c->r_tag.ensure(cap * 8));
-  CK(c, c->counter.ensure(64));
-  return PPM_OK;
-}
 MapSoA mapsoa(ppm_ctx* c) {
   MapSoA m;
   m.P = c->m_P.as<double2>(); m.D = c->m_D.as<double2>(); m.orig = c->m_orig.as<uint32_t>();
   return m;
 }
-// bits needed for the tags (index << 4 | depth) of `count` photons; cell bits go above them in the sort key
-int tag_bits_for(uint64_t count) {
-  int b = 1;
-  while (b < 38 && (1ull << b) < count) ++b;
-  return std::min(38, b + 4);
+CellIndex cellindex(ppm_ctx* c) {
+  CellIndex ix;
+  ix.words = c->words_p.as<IdxWord>(); ix.start = c->start_p.as<uint32_t>();
+  return ix;
 }
+EyeNodes eyenodes(ppm_ctx* c) {
+  EyeNodes n = {c->e_pos.as<double>(), c->e_nrm.as<double>(), c->e_w.as<double>(), c->e_prev.as<uint32_t>()};
+  return n;
+}
+unsigned scan_tiles(uint64_t max_n) { return (unsigned)std::max<uint64_t>(1, (max_n + SCAN_TILE - 1) / SCAN_TILE); }
+unsigned rs_blocks(ppm_ctx* c, uint64_t cap) { return (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)c->sm_count * 2, (cap + 1023) / 1024)); }
+int rs_passes(uint64_t cap) {                      // keys are compact cell ranks < number of records <= cap
+  int bits = 1;
+  while (bits < 32 && (1ull << bits) < cap) ++bits;
+  return (bits + RS_BITS - 1) / RS_BITS;
+}
+
+// record buffers (+ per-photon depth masks of a traced set)
+int ensure_records(ppm_ctx* c, uint64_t cap, uint64_t nphoton) {
+  if (cap == 0) cap = 1;
+  RC(ens(c, c->r_pos, cap * 24)); RC(ens(c, c->r_dir, cap * 24));
+  RC(ens(c, c->r_wl, cap)); RC(ens(c, c->r_tag, cap * 8));
+  if (nphoton) { RC(ens(c, c->pmask, nphoton * 4)); RC(ens(c, c->pbase, nphoton * 4)); }
+  return PPM_OK;
+}
+// everything the map build of up to `cap` records (traced from `nphoton` photons) touches
+int ensure_build(ppm_ctx* c, uint64_t cap, uint64_t nphoton) {
+  if (cap == 0) cap = 1;
+  if (cap >= 0xFFFFFFF0ull) return fail(c, PPM_ERR_CAPACITY, "at most 2^32-16 photon records");
+  RC(ens(c, c->order0, cap * 4)); RC(ens(c, c->cid, cap * 4));
+  RC(ens(c, c->words_p, (size_t)PPM_CELL_CAP_WORDS * sizeof(IdxWord)));
+  RC(ens(c, c->start_p, (cap + 2) * 4));
+  RC(ens(c, c->key_a, cap * 4)); RC(ens(c, c->key_b, cap * 4)); RC(ens(c, c->val_a, cap * 4)); RC(ens(c, c->val_b, cap * 4));
+  const size_t table = (size_t)RS_DIGITS * rs_blocks(c, cap);
+  RC(ens(c, c->rs_table, table * 4));
+  const size_t tiles = std::max<size_t>(std::max<size_t>(scan_tiles(table), scan_tiles(PPM_CELL_CAP_WORDS)), scan_tiles(nphoton));
+  RC(ens(c, c->tsum_p, tiles * 4));
+  RC(ens(c, c->m_P, cap * 32)); RC(ens(c, c->m_D, cap * 32)); RC(ens(c, c->m_orig, cap * 4));
+  return PPM_OK;
+}
+// everything the query sort + gather of up to `cap` queries touches
+int ensure_query(ppm_ctx* c, uint64_t cap) {
+  if (cap == 0) cap = 1;
+  if (cap >= 0xFFFFFFF0ull) return fail(c, PPM_ERR_CAPACITY, "at most 2^32-16 gather queries per call");
+  RC(ens(c, c->qcell, cap * 4)); RC(ens(c, c->words_q, (size_t)PPM_CELL_CAP_WORDS * sizeof(IdxWord)));
+  RC(ens(c, c->qcnt, (cap + 2) * 4)); RC(ens(c, c->qstart, (cap + 2) * 4)); RC(ens(c, c->qrank, cap * 4)); RC(ens(c, c->qpic, cap * 4));
+  RC(ens(c, c->skey, cap * 4)); RC(ens(c, c->sidx, cap * 4));
+  RC(ens(c, c->tsum_q, (size_t)std::max(scan_tiles(cap + 1), scan_tiles(PPM_CELL_CAP_WORDS)) * 4));
+  if (c->opt_gather_heavy) {
+    const uint32_t hcap = 1u << 15;                    // parts: 32 MB of partial sums per lane
+    RC(ens(c, c->heavy, (size_t)(hcap / 2) * sizeof(HeavyGroup) + (size_t)hcap * sizeof(HeavyPart) + (size_t)hcap * sizeof(HeavyPartial)));
+  }
+  return PPM_OK;
+}
+int ensure_eye(ppm_ctx* c, uint64_t npix, uint64_t cap) {
+  if (cap >= 0xFFFFFFF0ull) return fail(c, PPM_ERR_CAPACITY, "more than 2^32-16 gather nodes");
+  if (cap == 0) cap = 1;
+  RC(ens(c, c->e_head, npix * 4)); RC(ens(c, c->e_emit, npix * 24));
+  RC(ens(c, c->e_pos, cap * 24)); RC(ens(c, c->e_nrm, cap * 24)); RC(ens(c, c->e_w, cap * 24)); RC(ens(c, c->e_prev, cap * 4));
+  RC(ens(c, c->e_direct, cap * 24)); RC(ens(c, c->e_photon, cap * 24));
+  if (c->scene.nlights > 0) RC(ens(c, c->dl_masks, cap * (size_t)c->scene.nlights * 8));
+  return PPM_OK;
+}
+HeavyList heavylist(ppm_ctx* c) {
+  HeavyList hl;
+  std::memset(&hl, 0, sizeof hl);
+  if (!c->opt_gather_heavy || !c->heavy.p) return hl;
+  const uint32_t hcap = 1u << 15;
+  char* base = c->heavy.as<char>();
+  hl.ctr = c->ps->heavy;                               // device address of PassDev::heavy
+  hl.groups = (HeavyGroup*)base;
+  hl.parts = (HeavyPart*)(base + (size_t)(hcap / 2) * sizeof(HeavyGroup));
+  hl.partials = (HeavyPartial*)(base + (size_t)(hcap / 2) * sizeof(HeavyGroup) + (size_t)hcap * sizeof(HeavyPart));
+  hl.cap_parts = hcap;
+  return hl;
+}
+
 int light_split(ppm_ctx* c, const int64_t* n_per_light, LightSplit* ls, int64_t* total) {
   int64_t acc = 0;
   for (int i = 0; i < c->scene.nlights; ++i) {
@@ -180,370 +306,117 @@ int light_split(ppm_ctx* c, const int64_t* n_per_light, LightSplit* ls, int64_t*
   return PPM_OK;
 }
 
-// Per-scene table for the conservative shadow-ray culling of k_direct_light (kernels_eye.cuh).
-// Everything here is a bound with a 1e-6 safety margin, never a quantity that enters a result.
-void build_cull(const DevScene& sc, DevCull& cu) {
-  std::memset(&cu, 0, sizeof cu);
-  auto len3 = [](const double* a) { return std::sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]); };
-  auto quad_sphere = [&](const double* p0, const double* d1, const double* d2, double* c, double* r) {
-    double s[3], d[3];
-    for (int k = 0; k < 3; ++k) { s[k] = d1[k] + d2[k]; d[k] = d1[k] - d2[k]; c[k] = p0[k] + 0.5 * s[k]; }
-    double rr = 0.5 * std::max(len3(s), len3(d));
-    *r = rr * (1.0 + 1e-6) + 1e-6 * (1.0 + len3(c));
-  };
-  for (int o = 0; o < sc.nprims; ++o) {
-    const ppm_prim& s = sc.prims[o];
-    CullPrim& cp = cu.prim[o];
-    if (s.type == PPM_SHAPE_PLAIN) {
-      cp.kind = 1;
-      double nl = std::max(1.0, len3(s.nvec));
-      double scale = nl * (1.0 + std::fabs(s.scalar));
-      cp.c[0] = 1e-6 * scale;    // D: sign margin on dist + n.p
-      cp.c[1] = 1e-2 * scale;    // gap: the light must be closer to the plane than the node by this much
-    } else if (s.type == PPM_SHAPE_SPHERE) {
-      cp.kind = 2;
-      for (int k = 0; k < 3; ++k) cp.c[k] = s.position[k];
-      cp.r = std::fabs(s.scalar) * (1.0 + 1e-6) + 1e-6 * (1.0 + len3(s.position));
-    } else if (s.type == PPM_SHAPE_POLYGON || s.type == PPM_SHAPE_PARALLELOGRAM) {
-      cp.kind = 2;               // the triangle u + v <= 1 is a subset of its parallelogram
-      quad_sphere(s.position, s.dir1, s.dir2, cp.c, &cp.r);
-      cp.nvtx = 4;
-      for (int j = 0; j < 4; ++j)
-        for (int k = 0; k < 3; ++k)
-          cp.vtx[j][k] = s.position[k] + ((j == 1 || j == 2) ? s.dir1[k] : 0.0) + ((j >= 2) ? s.dir2[k] : 0.0);
-      for (int j = 0; j < 4 && cp.nvtx; ++j)
-        for (int k = 0; k < 3; ++k)
-          if (!(std::fabs(cp.vtx[j][k]) < 1e150)) cp.nvtx = 0;
-    } else {
-      cp.kind = 0;               // Point: calc_distance never yields a root
-    }
-    if (cp.kind == 2 && !(cp.r < 1e150)) cp.kind = 3;   // non-finite geometry: always tested
-  }
-  for (int li = 0; li < sc.nlights; ++li) {
-    const ppm_light& l = sc.lights[li];
-    CullLight& cl = cu.light[li];
-    if (l.type != PPM_LIGHT_PARALLELOGRAM) continue;
-    quad_sphere(l.pos, l.dir1, l.dir2, cl.c, &cl.r);
-    for (int j = 0; j < 4; ++j)
-      for (int k = 0; k < 3; ++k)
-        cl.corner[j][k] = l.pos[k] + ((j == 1 || j == 2) ? l.dir1[k] : 0.0) + ((j >= 2) ? l.dir2[k] : 0.0);
-    if (!(cl.r < 1e150)) { cl.r = 1e300; }              // r^2 overflows -> the cone test is off, planes below stay valid or NaN
-    // unit normal of the light's plane and the polygons / parallelograms lying in it (the emitter's own
-    // geometry): every vertex within 1e-12 (relative to the scene scale) of the plane through the quad
-    {
-      const double cx[3] = {l.dir1[1] * l.dir2[2] - l.dir2[1] * l.dir1[2], l.dir1[2] * l.dir2[0] - l.dir2[2] * l.dir1[0],
-                            l.dir1[0] * l.dir2[1] - l.dir2[0] * l.dir1[1]};
-      const double cn = len3(cx);
-      if (cn > 0.0 && cn < 1e150) {
-        for (int k = 0; k < 3; ++k) cl.nl[k] = cx[k] / cn;
-        for (int o = 0; o < sc.nprims; ++o) {
-          const ppm_prim& s = sc.prims[o];
-          if (s.type != PPM_SHAPE_POLYGON && s.type != PPM_SHAPE_PARALLELOGRAM) continue;
-          bool in_plane = true;
-          double scale = 1.0 + len3(l.pos) + len3(s.position) + len3(s.dir1) + len3(s.dir2);
-          for (int j = 0; j < 4 && in_plane; ++j) {
-            double h = 0.0;
-            for (int k = 0; k < 3; ++k)
-              h += cl.nl[k] * ((s.position[k] + ((j & 1) ? s.dir1[k] : 0.0) + ((j & 2) ? s.dir2[k] : 0.0)) - l.pos[k]);
-            if (!(std::fabs(h) <= 1e-12 * scale)) in_plane = false;
-          }
-          if (in_plane) cl.coplanar |= 1ull << o;
-        }
-      }
-    }
-    for (int o = 0; o < sc.nprims; ++o) {
-      const ppm_prim& s = sc.prims[o];
-      if (s.type != PPM_SHAPE_PLAIN) continue;
-      double hmin = 0.0, hmax = 0.0;
-      for (int j = 0; j < 4; ++j) {
-        double h = s.scalar;
-        for (int k = 0; k < 3; ++k) h += s.nvec[k] * (l.pos[k] + ((j & 1) ? l.dir1[k] : 0.0) + ((j & 2) ? l.dir2[k] : 0.0));
-        if (j == 0 || h < hmin) hmin = h;
-        if (j == 0 || h > hmax) hmax = h;
-        if (!(h == h)) { hmin = -1e300; hmax = 1e300; break; }   // NaN: the plane is always tested
-      }
-      cl.hmin[o] = hmin; cl.hmax[o] = hmax;
-    }
-  }
-}
 int upload_cull(ppm_ctx* c) {
   static_assert(sizeof(DevCull) < (1 << 16), "cull table");
   DevCull cu;
   build_cull(c->scene, cu);
-  CK(c, c->cull.ensure(sizeof cu));
+  RC(ens(c, c->cull, sizeof cu));
   CK(c, cudaMemcpy(c->cull.p, &cu, sizeof cu, cudaMemcpyHostToDevice));
   return PPM_OK;
 }
-// PPM_DL_CULL=0 switches the culling off (parity tests compare both settings bit for bit)
-const DevCull* cull_arg(ppm_ctx* c) {
-  const char* e = std::getenv("PPM_DL_CULL");
-  if (e && e[0] == '0') return nullptr;
-  return c->cull.as<DevCull>();
-}
+// culling is possible when switched on ("dl_cull") and bit 63 of the masks is free for the certificate
+bool cull_on(const ppm_ctx* c) { return c->opt_dl_cull && c->scene.nprims <= 63 && c->scene.nlights > 0; }
 
-// k_dl_classify: per-node culling masks for every light (nullptr result = culling off: PPM_DL_CULL=0 or 64 primitives)
-int launch_dl_classify(ppm_ctx* c, cudaStream_t st, const double* dpos, int64_t n, const unsigned long long** masks_out) {
-  *masks_out = nullptr;
-  const DevCull* cull = cull_arg(c);
-  if (!cull || c->scene.nprims > 63 || c->scene.nlights <= 0 || n <= 0) return PPM_OK;
-  CK(c, c->dl_masks.ensure((size_t)n * (size_t)c->scene.nlights * 8));
-  k_dl_classify<<<nblk(n, 128), 128, 0, st>>>(c->scene, cull, dpos, n, c->dl_masks.as<unsigned long long>());
+// ---- enqueue helpers: launches only, sizes come from PassDev, nothing waits for the host ------------------------
+template <class Op>
+int enq_scan(ppm_ctx* c, cudaStream_t st, Op op, uint64_t max_n, uint32_t* tile_sums) {
+  const unsigned tiles = scan_tiles(max_n);
+  k_scan_tiles<Op><<<tiles, SCAN_THREADS, 0, st>>>(op, tile_sums);
   KCHECK(c);
-  *masks_out = c->dl_masks.as<unsigned long long>();
-  return PPM_OK;
-}
-int launch_direct_light(ppm_ctx* c, cudaStream_t st, const double* dpos, const double* dnrm, int64_t n, double* dout,
-                        const unsigned long long* masks, const uint32_t* order = nullptr) {
-  unsigned long long* dbg = nullptr;
-  const bool stats = std::getenv("PPM_DL_STATS") != nullptr;
-  if (stats) {
-    CK(c, c->dl_dbg.ensure(160));
-    CK(c, cudaMemsetAsync(c->dl_dbg.p, 0, 160, st));
-    dbg = c->dl_dbg.as<unsigned long long>();
-  }
-  k_direct_light<<<nblk(n, 128), 128, 0, st>>>(c->scene, masks, order, dpos, dnrm, n, dout, dbg);
+  k_scan_sums<Op><<<1, 1024, 0, st>>>(op, tile_sums);
   KCHECK(c);
-  if (stats) {
-    unsigned long long h[20];
-    CK(c, cudaMemcpyAsync(h, dbg, 160, cudaMemcpyDeviceToHost, st));
-    CK(c, cudaStreamSynchronize(st));
-    if (h[0]) std::fprintf(stderr, "[ppm direct light] nodes=%llu tested prims/node: own %.3f, warp union %.3f; certificate %.1f%%\n", h[0],
-                           (double)h[1] / h[0], (double)h[2] / h[0], 100.0 * h[3] / h[0]);
-    if (h[0]) {
-      std::fprintf(stderr, "[ppm direct light] nodes by tested prims 0..7+: own");
-      for (int k = 0; k < 8; ++k) std::fprintf(stderr, " %.1f%%", 100.0 * h[4 + k] / h[0]);
-      std::fprintf(stderr, " | warp union");
-      for (int k = 0; k < 8; ++k) std::fprintf(stderr, " %.1f%%", 100.0 * h[12 + k] / h[0]);
-      std::fprintf(stderr, "\n");
-    }
-  }
-  return PPM_OK;
-}
-
-// -- internal (device-resident) building blocks shared by the probes and render_pass --
-int trace_photons_launch(ppm_ctx* c, uint64_t seed, uint32_t pass, int uc, const int64_t* n_per_light, uint64_t* cap_out) {
-  LightSplit ls;
-  int64_t total = 0;
-  int rc = light_split(c, n_per_light, &ls, &total);
-  if (rc) return rc;
-  uint64_t cap = (uint64_t)total * PPM_MAX_TRACE;
-  if (cap == 0) cap = 1;
-  c->tag_bits = tag_bits_for((uint64_t)total);
-  rc = ensure_records(c, cap);
-  if (rc) return rc;
-  CK(c, cudaMemsetAsync(c->counter.p, 0, 16, c->stream));     // [0] record counter, [1] photon ticket
-  if (total > 0) {
-    // persistent grid: enough CTAs to fill every SM (resident CTAs are limited by registers),
-    // never more threads than photons
-    const unsigned blocks = (unsigned)std::min<int64_t>((total + 127) / 128, (int64_t)c->sm_count * 8);
-    k_trace_photons<<<blocks, 128, 0, c->stream>>>(c->scene, ls, seed, pass, uc, total, recbuf(c),
-                                                   c->counter.as<unsigned long long>(), cap,
-                                                   c->counter.as<unsigned long long>() + 1);
-    KCHECK(c);
-  }
-  *cap_out = cap;
-  return PPM_OK;
-}
-int trace_photons_finish(ppm_ctx* c, uint64_t cap, double power) {
-  unsigned long long n = 0;
-  CK(c, cudaMemcpyAsync(&n, c->counter.p, 8, cudaMemcpyDeviceToHost, c->stream));
-  CK(c, cudaStreamSynchronize(c->stream));
-  if (n > cap) return fail(c, PPM_ERR_CAPACITY, "photon record capacity exceeded");
-  c->n_rec = n; c->power = power; c->have_map = false;
-  return PPM_OK;
-}
-int do_trace_photons(ppm_ctx* c, uint64_t seed, uint32_t pass, int uc, const int64_t* n_per_light, double power) {
-  uint64_t cap = 0;
-  int rc = trace_photons_launch(c, seed, pass, uc, n_per_light, &cap);
-  if (rc) return rc;
-  return trace_photons_finish(c, cap, power);
-}
-
-struct HostTrace {
-  bool on; std::chrono::steady_clock::time_point t0; std::string log; cudaStream_t st;
-  explicit HostTrace(cudaStream_t s) : on(std::getenv("PPM_TRACE") != nullptr), t0(std::chrono::steady_clock::now()), st(s) {}
-  void mark(const char* what) {
-    if (!on) return;
-    cudaStreamSynchronize(st);
-    auto t1 = std::chrono::steady_clock::now();
-    char b[96];
-    std::snprintf(b, sizeof b, " %s=%.3f", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
-    log += b; t0 = t1;
-  }
-  ~HostTrace() { if (on) std::fprintf(stderr, "[ppm trace]%s\n", log.c_str()); }
-};
-
-int do_map_build(ppm_ctx* c, double radius2) {
-  HostTrace tr(c->stream);
-  if (!(radius2 > 0.0)) return fail(c, PPM_ERR_ARG, "radius2 must be > 0");
-  const uint64_t n = c->n_rec;
-  c->r2 = radius2;
-  Grid g;
-  std::memset(&g, 0, sizeof g);
-  double cell = std::sqrt(radius2) * (1.0 + 1.0 / 1024.0);   // edge slightly > r: the 27-cell walk can never miss
-  g.nx = g.ny = g.nz = 1; g.inv_cell = 1.0 / cell; g.ncells = 1;
-  if (n > 0) {
-    CK(c, c->bbox.ensure(48));
-    unsigned long long init[6] = {~0ull, ~0ull, ~0ull, 0ull, 0ull, 0ull};
-    CK(c, cudaMemcpyAsync(c->bbox.p, init, 48, cudaMemcpyHostToDevice, c->stream));
-    k_bbox<<<std::min<unsigned>(nblk((int64_t)n, 256), 148 * 8), 256, 0, c->stream>>>(c->r_pos.as<double>(), n,
-                                                                                     c->bbox.as<unsigned long long>());
-    KCHECK(c);
-    unsigned long long mm[6];
-    CK(c, cudaMemcpyAsync(mm, c->bbox.p, 48, cudaMemcpyDeviceToHost, c->stream));
-    CK(c, cudaStreamSynchronize(c->stream));
-    double lo[3], hi[3];
-    for (int k = 0; k < 3; ++k) { lo[k] = dec_ord(mm[k]); hi[k] = dec_ord(mm[3 + k]); }
-    tr.mark("bbox");
-    for (int k = 0; k < 3; ++k)
-      if (!(lo[k] == lo[k]) || !(hi[k] == hi[k]) || std::isinf(lo[k]) || std::isinf(hi[k]))
-        return fail(c, PPM_ERR_ARG, "photon positions are not finite");
-    // Region covered by the dense grid.  The reference leaks a few photons (~1e-4) through
-    // wall corners (a bounce closer than NEARLY0 to the next wall skips it), and those land
-    // tens of metres outside the room on the infinite planes, so the raw bounding box is
-    // erratic and mostly empty.  The grid therefore covers a per-axis TRIMMED range (at most
-    // n/1024 photons cut on each side, found with device histograms); photons and queries
-    // outside are clamped into the boundary cells, which keeps the 27-cell walk exact
-    // (clamping never increases the cell distance of two points).
-    const uint64_t trim = n >= 4096 ? n / 1024 : 0;
-    if (trim > 0) {
-      CK(c, c->axis_hist.ensure(3 * AXIS_BINS * 4));
-      std::vector<uint32_t> hh(3 * AXIS_BINS);
-      for (int iter = 0; iter < 4; ++iter) {
-        AxisRange ar;
-        double w[3];
-        bool fine = true;
-        for (int k = 0; k < 3; ++k) {
-          w[k] = (hi[k] - lo[k]) / (double)AXIS_BINS;
-          if (!(w[k] > 0.0)) w[k] = 1.0;
-          ar.lo[k] = lo[k]; ar.inv_w[k] = 1.0 / w[k];
-          if (w[k] > 0.5 * cell) fine = false;
-        }
-        if (iter > 0 && fine) break;
-        CK(c, cudaMemsetAsync(c->axis_hist.p, 0, 3 * AXIS_BINS * 4, c->stream));
-        k_axis_hist<<<std::min<unsigned>(nblk((int64_t)n, 256 * 8), 148 * 4), 256, 0, c->stream>>>(c->r_pos.as<double>(), n, ar,
-                                                                                              c->axis_hist.as<uint32_t>());
-        KCHECK(c);
-        CK(c, cudaMemcpyAsync(hh.data(), c->axis_hist.p, 3 * AXIS_BINS * 4, cudaMemcpyDeviceToHost, c->stream));
-        CK(c, cudaStreamSynchronize(c->stream));
-        for (int k = 0; k < 3; ++k) {
-          const uint32_t* h = hh.data() + k * AXIS_BINS;
-          uint64_t acc = 0;
-          int a = 0, b = AXIS_BINS - 1;
-          while (a < AXIS_BINS - 1 && acc + h[a] <= trim) acc += h[a++];
-          acc = 0;
-          while (b > a && acc + h[b] <= trim) acc += h[b--];
-          double nlo = lo[k] + (double)a * w[k], nhi = lo[k] + (double)(b + 1) * w[k];
-          lo[k] = std::max(lo[k], nlo); hi[k] = std::min(hi[k], nhi);
-        }
-        if (fine) break;
-      }
-      tr.mark("trim");
-    }
-    // The origin is padded by half a cell: surfaces that bound the photon cloud (the room's
-    // walls) then sit mid-cell, so the +-1 ulp noise of hit points on such a plane cannot
-    // straddle a cell boundary (which would split every warp of queries on that wall).
-    const double CELL_CAP = 67108864.0;   // 2^26 cells
-    for (;;) {
-      double dims[3];
-      for (int k = 0; k < 3; ++k) dims[k] = std::floor((hi[k] - (lo[k] - 0.5 * cell)) / cell) + 2.0;
-      if (dims[0] * dims[1] * dims[2] <= CELL_CAP && dims[0] < 2e9 && dims[1] < 2e9 && dims[2] < 2e9) {
-        g.nx = (int32_t)dims[0]; g.ny = (int32_t)dims[1]; g.nz = (int32_t)dims[2];
-        break;
-      }
-      cell *= 2.0;
-    }
-    for (int k = 0; k < 3; ++k) g.org[k] = lo[k] - 0.5 * cell;
-    g.inv_cell = 1.0 / cell;
-    g.ncells = (uint32_t)g.nx * (uint32_t)g.ny * (uint32_t)g.nz;
-  }
-  c->grid = g;
-  {
-    // cudaFree/cudaMalloc stall for 10-400 ms on this platform: size the cell tables for at
-    // least 2^24 cells up front (64 MB per table) so the shrinking radius does not regrow them every few passes
-    size_t want = std::max<size_t>((size_t)g.ncells + 1, (size_t)1 << 24) * 4;
-    CK(c, c->hist.ensure(want));
-    CK(c, c->cell_start.ensure(want));
-  }
-  tr.mark("alloc_cells");
-  CK(c, cudaMemsetAsync(c->hist.p, 0, ((size_t)g.ncells + 1) * 4, c->stream));
-  tr.mark("memset");
-  size_t nn = n ? n : 1;
-  CK(c, c->keys.ensure(nn * 8)); CK(c, c->keys2.ensure(nn * 8));
-  CK(c, c->vals.ensure(nn * 4)); CK(c, c->vals2.ensure(nn * 4));
-  CK(c, c->m_P.ensure(nn * 32)); CK(c, c->m_D.ensure(nn * 32)); CK(c, c->m_orig.ensure(nn * 4));
-  tr.mark("alloc_map");
-  if (n > 0) {
-    k_cell_key<<<nblk((int64_t)n, 256), 256, 0, c->stream>>>(g, c->r_pos.as<double>(), c->r_tag.as<uint64_t>(), n, c->tag_bits,
-                                                            c->keys.as<uint64_t>(), c->vals.as<uint32_t>(), c->hist.as<uint32_t>());
-    KCHECK(c);
-    int cell_bits = 1;
-    while ((1ull << cell_bits) < (unsigned long long)g.ncells) ++cell_bits;
-    int end_bit = std::min(64, c->tag_bits + cell_bits);
-    size_t tmp = 0;
-    CK(c, cub::DeviceRadixSort::SortPairs(nullptr, tmp, c->keys.as<uint64_t>(), c->keys2.as<uint64_t>(), c->vals.as<uint32_t>(),
-                                          c->vals2.as<uint32_t>(), (int64_t)n, 0, end_bit, c->stream));
-    CK(c, c->cub_tmp.ensure(tmp));
-    tr.mark("key");
-    CK(c, cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp, c->keys.as<uint64_t>(), c->keys2.as<uint64_t>(), c->vals.as<uint32_t>(),
-                                          c->vals2.as<uint32_t>(), (int64_t)n, 0, end_bit, c->stream));
-    tr.mark("sort");
-    k_scatter<<<nblk((int64_t)n, 256), 256, 0, c->stream>>>(recbuf(c), c->vals2.as<uint32_t>(), n, mapsoa(c));
-    KCHECK(c);
-    tr.mark("scatter");
-  }
-  {
-    size_t tmp = 0;
-    CK(c, cub::DeviceScan::ExclusiveSum(nullptr, tmp, c->hist.as<uint32_t>(), c->cell_start.as<uint32_t>(), (int64_t)g.ncells + 1, c->stream));
-    CK(c, c->cub_tmp.ensure(tmp));
-    CK(c, cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tmp, c->hist.as<uint32_t>(), c->cell_start.as<uint32_t>(), (int64_t)g.ncells + 1, c->stream));
-  }
-  tr.mark("scan");
-  c->have_map = true;
-  return PPM_OK;
-}
-
-// key the queries by cell and sort them (stable: ties keep query order -> deterministic)
-int gather_sort_queries(ppm_ctx* c, const double* dpos, int64_t n) {
-  if (n >= (1ll << 32)) return fail(c, PPM_ERR_CAPACITY, "at most 2^32-1 gather queries per call");
-  CK(c, c->q_key.ensure((size_t)n * 4)); CK(c, c->q_key2.ensure((size_t)n * 4));
-  CK(c, c->q_idx.ensure((size_t)n * 4)); CK(c, c->q_idx2.ensure((size_t)n * 4));
-  k_query_key<<<nblk(n, 256), 256, 0, c->stream>>>(c->grid, dpos, n, c->q_key.as<uint32_t>(), c->q_idx.as<uint32_t>());
+  k_scan_apply<Op><<<tiles, SCAN_THREADS, 0, st>>>(op, tile_sums);
   KCHECK(c);
-  unsigned long long maxkey = c->grid.ncells;
-  int bits = 1;
-  while (bits < 32 && (1ull << bits) < maxkey) ++bits;
-  size_t tmp = 0;
-  CK(c, cub::DeviceRadixSort::SortPairs(nullptr, tmp, c->q_key.as<uint32_t>(), c->q_key2.as<uint32_t>(), c->q_idx.as<uint32_t>(),
-                                        c->q_idx2.as<uint32_t>(), n, 0, bits, c->stream));
-  CK(c, c->cub_tmp.ensure(tmp));
-  CK(c, cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp, c->q_key.as<uint32_t>(), c->q_key2.as<uint32_t>(), c->q_idx.as<uint32_t>(),
-                                        c->q_idx2.as<uint32_t>(), n, 0, bits, c->stream));
   return PPM_OK;
 }
-// warp-cooperative gather over the sorted queries; mode 0 fixed radius, 1 per-query radius, 2 count only
-int gather_launch(ppm_ctx* c, const double* dpos, const double* dnrm, int64_t n, int filter, int mode, const double* r2q,
-                  double* drgb, uint32_t* dcounts, unsigned long long* dsumk) {
+int enq_stamp(ppm_ctx* c, cudaStream_t st, int slot) {
+  k_stamp<<<1, 1, 0, st>>>(c->ps, slot);
+  KCHECK(c);
+  return PPM_OK;
+}
+
+// photon tracing of `total` photons; seed / pass / counters are in the pass state
+int enq_trace(ppm_ctx* c, cudaStream_t st, const LightSplit& ls, int64_t total, int uc, uint64_t cap) {
+  if (total <= 0) return PPM_OK;
+  // persistent grid: enough CTAs to fill every SM (resident CTAs are limited by registers), never more threads than photons
+  const unsigned blocks = (unsigned)std::min<int64_t>((total + 127) / 128, (int64_t)c->sm_count * 8);
+  k_trace_photons<<<blocks, 128, 0, st>>>(c->scene, ls, c->ps, uc, total, recbuf(c), (unsigned long long)cap, c->pmask.as<uint32_t>());
+  KCHECK(c);
+  return PPM_OK;
+}
+// photon map of the records in the record buffers: compact cell index, tag order, stable radix sort by cell rank, SoA map.
+// traced: the records come from k_trace_photons (`nphoton` emitted photons; n_map is validated on the device);
+// otherwise they are an imported set in tag order and PassDev::n_map is already set.
+int enq_build(ppm_ctx* c, cudaStream_t st, bool traced, uint64_t nphoton, uint64_t cap) {
+  PassDev* ps = c->ps;
+  IdxWord* words = c->words_p.as<IdxWord>();
+  uint32_t* tsum = c->tsum_p.as<uint32_t>();
+  const unsigned wide = (unsigned)c->sm_count * 8;
+  k_index_clear<<<(unsigned)c->sm_count * 4, 256, 0, st>>>(ps, words);
+  KCHECK(c);
+  if (traced) {
+    ScanMasks sm = {ps, c->pmask.as<uint32_t>(), c->pbase.as<uint32_t>(), (uint32_t)nphoton, (uint32_t)std::min<uint64_t>(cap, 0xFFFFFFF0ull)};
+    RC(enq_scan(c, st, sm, nphoton, tsum));
+    k_photon_place<false><<<wide, 256, 0, st>>>(ps, recbuf(c), c->pmask.as<uint32_t>(), c->pbase.as<uint32_t>(), c->order0.as<uint32_t>(),
+                                                c->cid.as<uint32_t>(), words, -1);
+  } else {
+    k_photon_place<true><<<wide, 256, 0, st>>>(ps, recbuf(c), nullptr, nullptr, c->order0.as<uint32_t>(), c->cid.as<uint32_t>(), words, -1);
+  }
+  KCHECK(c);
+  ScanWords sw = {ps, words, &ps->n_occ_p, nullptr};
+  RC(enq_scan(c, st, sw, PPM_CELL_CAP_WORDS, tsum));
+  const unsigned rsb = rs_blocks(c, cap);
+  const int npass = rs_passes(cap);
+  uint32_t *kin = c->key_a.as<uint32_t>(), *vin = c->val_a.as<uint32_t>(), *kout = c->key_b.as<uint32_t>(), *vout = c->val_b.as<uint32_t>();
+  uint32_t* table = c->rs_table.as<uint32_t>();
+  for (int p = 0; p < npass; ++p) {
+    const int shift = p * RS_BITS;
+    if (p == 0) k_rs_hist<true><<<rsb, RS_THREADS, 0, st>>>(ps, nullptr, shift, table, c->order0.as<uint32_t>(), c->cid.as<uint32_t>(), words, kin, vin);
+    else k_rs_hist<false><<<rsb, RS_THREADS, 0, st>>>(ps, kin, shift, table, nullptr, nullptr, nullptr, nullptr, nullptr);
+    KCHECK(c);
+    ScanFixed sf = {table, (uint32_t)(RS_DIGITS * rsb)};
+    RC(enq_scan(c, st, sf, (uint64_t)RS_DIGITS * rsb, tsum));
+    k_rs_scatter<<<rsb, RS_THREADS, 0, st>>>(ps, kin, vin, shift, table, kout, vout);
+    KCHECK(c);
+    std::swap(kin, kout); std::swap(vin, vout);
+  }
+  k_map_scatter<<<wide, 256, 0, st>>>(ps, recbuf(c), kin, vin, mapsoa(c), c->start_p.as<uint32_t>());
+  KCHECK(c);
+  return PPM_OK;
+}
+// counting sort of the gather queries by grid cell (needs the grid of the pass, not the map)
+int enq_query_sort(ppm_ctx* c, cudaStream_t st, const double* qpos, uint64_t cap) {
+  PassDev* ps = c->ps;
+  IdxWord* words = c->words_q.as<IdxWord>();
+  const unsigned wide = (unsigned)c->sm_count * 8;
+  k_index_clear<<<(unsigned)c->sm_count * 4, 256, 0, st>>>(ps, words);
+  KCHECK(c);
+  k_query_mark<<<wide, 256, 0, st>>>(ps, qpos, (uint32_t)cap, c->qcell.as<uint32_t>(), words, -1);
+  KCHECK(c);
+  ScanWords sw = {ps, words, &ps->n_occ_q, c->qcnt.as<uint32_t>()};
+  RC(enq_scan(c, st, sw, PPM_CELL_CAP_WORDS, c->tsum_q.as<uint32_t>()));
+  k_query_count<<<wide, 256, 0, st>>>(ps, c->qcell.as<uint32_t>(), words, c->qcnt.as<uint32_t>(), c->qrank.as<uint32_t>(), c->qpic.as<uint32_t>());
+  KCHECK(c);
+  ScanU32 su = {&ps->n_occ_q, c->qcnt.as<uint32_t>(), c->qstart.as<uint32_t>()};
+  RC(enq_scan(c, st, su, cap + 1, c->tsum_q.as<uint32_t>()));
+  k_query_scatter<<<wide, 256, 0, st>>>(ps, c->qcell.as<uint32_t>(), c->qrank.as<uint32_t>(), c->qpic.as<uint32_t>(), c->qstart.as<uint32_t>(),
+                                       c->skey.as<uint32_t>(), c->sidx.as<uint32_t>());
+  KCHECK(c);
+  return PPM_OK;
+}
+// warp-cooperative gather over the sorted queries; mode 0 fixed radius, 1 per-query radius, 2 count only.
+// zero_heavy: clear the heavy-part counters first (probe entry points; k_pass_begin does it for a rendered pass)
+int enq_gather(ppm_ctx* c, cudaStream_t st, const double* dpos, const double* dnrm, uint64_t cap, int filter, int mode, const double* r2q,
+               double* drgb, uint32_t* dcounts, bool zero_heavy, int stamp_slot) {
   const int B = GATHER_WARPS * 32;
-  const uint32_t* cs = c->cell_start.as<uint32_t>();
-  const uint32_t* qk = c->q_key2.as<uint32_t>();
-  const uint32_t* qx = c->q_idx2.as<uint32_t>();
-  // heavy groups: warps publish them as parts in a device-side list; k_gather_heavy is launched only if there are any
-  HeavyList hl;
-  std::memset(&hl, 0, sizeof hl);
-  if (!(std::getenv("PPM_GATHER_HEAVY") && std::getenv("PPM_GATHER_HEAVY")[0] == '0')) {
-    const uint32_t cap = 1u << 15;                     // parts: 32 MB of partial sums per context
-    const size_t off_groups = 64, off_parts = off_groups + (size_t)(cap / 2) * sizeof(HeavyGroup),
-                 off_partials = off_parts + (size_t)cap * sizeof(HeavyPart), bytes = off_partials + (size_t)cap * sizeof(HeavyPartial);
-    CK(c, c->heavy.ensure(bytes));
-    char* base = c->heavy.as<char>();
-    hl.ctr = (unsigned int*)base; hl.groups = (HeavyGroup*)(base + off_groups); hl.parts = (HeavyPart*)(base + off_parts);
-    hl.partials = (HeavyPartial*)(base + off_partials);
-    hl.cap_parts = cap;
-    CK(c, cudaMemsetAsync(hl.ctr, 0, 16, c->stream));  // [0] reservations, [1] ticket of k_gather_heavy, [2] groups, [3] parts published
-  }
-  if (c->timed) cudaEventRecord(c->ev[ppm_ctx::EV_A4], c->stream);   // start of k_gather
-#define GATHER_LAUNCH(F, M) k_gather<F, M><<<nblk(n, B), B, 0, c->stream>>>(c->grid, cs, mapsoa(c), qk, qx, dpos, dnrm, n, c->power, c->r2, r2q, drgb, dcounts, dsumk, hl)
+  HeavyList hl = heavylist(c);
+  if (zero_heavy) CK(c, cudaMemsetAsync(c->ps->heavy, 0, 16, st));
+  const unsigned grid = nblk((int64_t)cap, B);
+  const CellIndex ix = cellindex(c);
+  const MapSoA m = mapsoa(c);
+  const uint32_t* qk = c->skey.as<uint32_t>();
+  const uint32_t* qx = c->sidx.as<uint32_t>();
+#define GATHER_LAUNCH(F, M) k_gather<F, M><<<grid, B, 0, st>>>(c->ps, ix, m, qk, qx, dpos, dnrm, r2q, drgb, dcounts, hl, stamp_slot)
   if (mode == 2) GATHER_LAUNCH(PPM_FILTER_NONE, 2);
   else if (mode == 1) {
     switch (filter) {
@@ -560,42 +433,184 @@ int gather_launch(ppm_ctx* c, const double* dpos, const double* dnrm, int64_t n,
   }
 #undef GATHER_LAUNCH
   KCHECK(c);
-  if (c->timed) cudaEventRecord(c->ev[ppm_ctx::EV_A5], c->stream);   // end of k_gather (re-recorded after k_gather_heavy)
   if (hl.ctr) {
-    unsigned int nparts = 0;
-    CK(c, cudaMemcpyAsync(&nparts, hl.ctr + 3, 4, cudaMemcpyDeviceToHost, c->stream));
-    CK(c, cudaStreamSynchronize(c->stream));
-    if (nparts > 0) {
-      const unsigned grid = std::min<unsigned>((nparts + GATHER_WARPS - 1) / GATHER_WARPS, (unsigned)c->sm_count * 16u);
-#define HEAVY_LAUNCH(F, M) k_gather_heavy<F, M><<<grid, B, 0, c->stream>>>(c->grid, cs, mapsoa(c), qx, dpos, dnrm, n, c->power, c->r2, r2q, drgb, dcounts, dsumk, hl)
-      if (mode == 2) HEAVY_LAUNCH(PPM_FILTER_NONE, 2);
-      else if (mode == 1) {
-        switch (filter) {
-          case PPM_FILTER_NONE: HEAVY_LAUNCH(PPM_FILTER_NONE, 1); break;
-          case PPM_FILTER_CONE: HEAVY_LAUNCH(PPM_FILTER_CONE, 1); break;
-          default:              HEAVY_LAUNCH(PPM_FILTER_GAUSS, 1); break;
-        }
-      } else {
-        switch (filter) {
-          case PPM_FILTER_NONE: HEAVY_LAUNCH(PPM_FILTER_NONE, 0); break;
-          case PPM_FILTER_CONE: HEAVY_LAUNCH(PPM_FILTER_CONE, 0); break;
-          default:              HEAVY_LAUNCH(PPM_FILTER_GAUSS, 0); break;
-        }
+    // always launched (fixed sequence): without published parts every warp returns at once
+    const unsigned hgrid = (unsigned)c->sm_count * 16u;
+#define HEAVY_LAUNCH(F, M) k_gather_heavy<F, M><<<hgrid, B, 0, st>>>(c->ps, ix, m, qx, dpos, dnrm, r2q, drgb, dcounts, hl)
+    if (mode == 2) HEAVY_LAUNCH(PPM_FILTER_NONE, 2);
+    else if (mode == 1) {
+      switch (filter) {
+        case PPM_FILTER_NONE: HEAVY_LAUNCH(PPM_FILTER_NONE, 1); break;
+        case PPM_FILTER_CONE: HEAVY_LAUNCH(PPM_FILTER_CONE, 1); break;
+        default:              HEAVY_LAUNCH(PPM_FILTER_GAUSS, 1); break;
       }
-#undef HEAVY_LAUNCH
-      KCHECK(c);
-      if (c->timed) cudaEventRecord(c->ev[ppm_ctx::EV_A5], c->stream);
+    } else {
+      switch (filter) {
+        case PPM_FILTER_NONE: HEAVY_LAUNCH(PPM_FILTER_NONE, 0); break;
+        case PPM_FILTER_CONE: HEAVY_LAUNCH(PPM_FILTER_CONE, 0); break;
+        default:              HEAVY_LAUNCH(PPM_FILTER_GAUSS, 0); break;
+      }
     }
+#undef HEAVY_LAUNCH
+    KCHECK(c);
   }
   return PPM_OK;
 }
-int launch_gather(ppm_ctx* c, const double* dpos, const double* dnrm, int64_t n, int filter, double* drgb, uint32_t* dcounts,
-                  unsigned long long* dsumk) {
+int enq_dl_classify(ppm_ctx* c, cudaStream_t st, const double* dpos, const double* dnrm, uint64_t cap, unsigned long long* masks) {
+  k_dl_classify<<<nblk((int64_t)cap, 128), 128, 0, st>>>(c->scene, c->cull.as<DevCull>(), c->ps, (uint32_t)cap, dpos, dnrm, masks, -1);
+  KCHECK(c);
+  return PPM_OK;
+}
+int enq_direct_light(ppm_ctx* c, cudaStream_t st, const double* dpos, const double* dnrm, uint64_t cap, double* dout,
+                     const unsigned long long* masks, const uint32_t* order, unsigned long long* dbg, int stamp_slot) {
+  k_direct_light<<<nblk((int64_t)cap, 128), 128, 0, st>>>(c->scene, c->ps, (uint32_t)cap, masks, order, dpos, dnrm, dout, dbg, stamp_slot);
+  KCHECK(c);
+  return PPM_OK;
+}
+int dl_stats_begin(ppm_ctx* c, cudaStream_t st, unsigned long long** dbg) {
+  *dbg = nullptr;
+  if (!c->opt_dl_stats) return PPM_OK;
+  RC(ens(c, c->dl_dbg, 160));
+  CK(c, cudaMemsetAsync(c->dl_dbg.p, 0, 160, st));
+  *dbg = c->dl_dbg.as<unsigned long long>();
+  return PPM_OK;
+}
+int dl_stats_print(ppm_ctx* c, cudaStream_t st, unsigned long long* dbg) {
+  if (!dbg) return PPM_OK;
+  unsigned long long h[20];
+  CK(c, cudaMemcpyAsync(h, dbg, 160, cudaMemcpyDeviceToHost, st));
+  CK(c, cudaStreamSynchronize(st));
+  if (h[0]) {
+    std::fprintf(stderr, "[ppm direct light] nodes=%llu tested prims/node: own %.3f, warp union %.3f; certificate %.1f%%\n", h[0],
+                 (double)h[1] / h[0], (double)h[2] / h[0], 100.0 * h[3] / h[0]);
+    std::fprintf(stderr, "[ppm direct light] nodes by tested prims 0..7+: own");
+    for (int k = 0; k < 8; ++k) std::fprintf(stderr, " %.1f%%", 100.0 * h[4 + k] / h[0]);
+    std::fprintf(stderr, " | warp union");
+    for (int k = 0; k < 8; ++k) std::fprintf(stderr, " %.1f%%", 100.0 * h[12 + k] / h[0]);
+    std::fprintf(stderr, "\n");
+  }
+  return PPM_OK;
+}
+
+// ---- probe building blocks (host round trips allowed) ------------------------------------------------------------
+int do_trace_photons(ppm_ctx* c, uint64_t seed, uint32_t pass, int uc, const int64_t* n_per_light, double power) {
+  LightSplit ls;
+  int64_t total = 0;
+  RC(light_split(c, n_per_light, &ls, &total));
+  if ((uint64_t)total >= (1ull << 32) - 16) return fail(c, PPM_ERR_CAPACITY, "at most 2^32-16 photons per pass");
+  uint64_t cap = (uint64_t)total * PPM_MAX_TRACE;
+  if (cap == 0) cap = 1;
+  RC(ensure_records(c, cap, (uint64_t)std::max<int64_t>(total, 1)));
+  c->hps.seed = seed; c->hps.pass = pass; c->hps.power = power;
+  c->hps.n_rec = 0ull; c->hps.ticket = 0ull; c->hps.status = 0u;
+  RC(push_ps(c));
+  RC(enq_trace(c, c->stream, ls, total, uc, cap));
+  RC(pull_ps(c));
+  if (c->hps.n_rec > cap) return fail(c, PPM_ERR_CAPACITY, "photon record capacity exceeded");
+  c->n_rec = c->hps.n_rec; c->power = power; c->have_map = false;
+  c->rec_traced = true; c->rec_nphoton = (uint64_t)total;
+  return PPM_OK;
+}
+
+// Region covered by the grid, from the records in the record buffers.  The reference leaks a few photons (~1e-4)
+// through wall corners (a bounce closer than NEARLY0 to the next wall skips it), and those land tens of metres outside
+// the room on the infinite planes, so the raw bounding box is erratic and mostly empty.  The region is therefore a
+// per-axis TRIMMED range (at most n/1024 photons cut on each side, found with device histograms); photons and queries
+// outside are clamped into the boundary cells, which keeps the 27-cell walk exact (see make_grid).
+int compute_bounds(ppm_ctx* c, uint64_t n, double cell, Bounds* out, int* have) {
+  std::memset(out, 0, sizeof *out);
+  *have = 0;
+  if (n == 0) return PPM_OK;
+  RC(ens(c, c->bbox, 48));
+  unsigned long long init[6] = {~0ull, ~0ull, ~0ull, 0ull, 0ull, 0ull};
+  CK(c, cudaMemcpyAsync(c->bbox.p, init, 48, cudaMemcpyHostToDevice, c->stream));
+  k_bbox<<<std::min<unsigned>(nblk((int64_t)n, 256), (unsigned)c->sm_count * 8), 256, 0, c->stream>>>(c->r_pos.as<double>(), n,
+                                                                                                  c->bbox.as<unsigned long long>());
+  KCHECK(c);
+  unsigned long long mm[6];
+  CK(c, cudaMemcpyAsync(mm, c->bbox.p, 48, cudaMemcpyDeviceToHost, c->stream));
+  CK(c, cudaStreamSynchronize(c->stream));
+  double lo[3], hi[3];
+  for (int k = 0; k < 3; ++k) { lo[k] = dec_ord(mm[k]); hi[k] = dec_ord(mm[3 + k]); }
+  for (int k = 0; k < 3; ++k)
+    if (!(lo[k] == lo[k]) || !(hi[k] == hi[k]) || std::isinf(lo[k]) || std::isinf(hi[k]))
+      return fail(c, PPM_ERR_ARG, "photon positions are not finite");
+  const uint64_t trim = n >= 4096 ? n / 1024 : 0;
+  if (trim > 0) {
+    RC(ens(c, c->axis_hist, 3 * AXIS_BINS * 4));
+    std::vector<uint32_t> hh(3 * AXIS_BINS);
+    for (int iter = 0; iter < 4; ++iter) {
+      AxisRange ar;
+      double w[3];
+      bool fine = true;
+      for (int k = 0; k < 3; ++k) {
+        w[k] = (hi[k] - lo[k]) / (double)AXIS_BINS;
+        if (!(w[k] > 0.0)) w[k] = 1.0;
+        ar.lo[k] = lo[k]; ar.inv_w[k] = 1.0 / w[k];
+        if (w[k] > 0.5 * cell) fine = false;
+      }
+      if (iter > 0 && fine) break;
+      CK(c, cudaMemsetAsync(c->axis_hist.p, 0, 3 * AXIS_BINS * 4, c->stream));
+      k_axis_hist<<<std::min<unsigned>(nblk((int64_t)n, 256 * 8), (unsigned)c->sm_count * 4), 256, 0, c->stream>>>(c->r_pos.as<double>(), n, ar,
+                                                                                                               c->axis_hist.as<uint32_t>());
+      KCHECK(c);
+      CK(c, cudaMemcpyAsync(hh.data(), c->axis_hist.p, 3 * AXIS_BINS * 4, cudaMemcpyDeviceToHost, c->stream));
+      CK(c, cudaStreamSynchronize(c->stream));
+      for (int k = 0; k < 3; ++k) {
+        const uint32_t* h = hh.data() + k * AXIS_BINS;
+        uint64_t acc = 0;
+        int a = 0, b = AXIS_BINS - 1;
+        while (a < AXIS_BINS - 1 && acc + h[a] <= trim) acc += h[a++];
+        acc = 0;
+        while (b > a && acc + h[b] <= trim) acc += h[b--];
+        double nlo = lo[k] + (double)a * w[k], nhi = lo[k] + (double)(b + 1) * w[k];
+        lo[k] = std::max(lo[k], nlo); hi[k] = std::min(hi[k], nhi);
+      }
+      if (fine) break;
+    }
+  }
+  for (int k = 0; k < 3; ++k) { out->lo[k] = lo[k]; out->hi[k] = hi[k]; }
+  *have = 1;
+  return PPM_OK;
+}
+
+// probe: map of the current photon set (records in the record buffers) at squared radius radius2.
+// fresh_bounds: take the grid region from these records (ppm_map_build); otherwise keep the calibrated one.
+int do_map_build(ppm_ctx* c, double radius2, bool fresh_bounds) {
+  if (!(radius2 > 0.0)) return fail(c, PPM_ERR_ARG, "radius2 must be > 0");
+  const uint64_t n = c->n_rec;
+  if (fresh_bounds) {
+    Bounds b; int have = 0;
+    RC(compute_bounds(c, n, std::sqrt(radius2), &b, &have));
+    c->hps.bounds = b; c->hps.have_bounds = have;
+  }
+  c->hps.r2 = radius2; c->hps.power = c->power;
+  c->hps.grid = make_grid(c->hps.bounds, c->hps.have_bounds, radius2);
+  c->hps.n_rec = n; c->hps.n_map = c->rec_traced ? 0u : (uint32_t)n;
+  c->hps.n_occ_p = 0u; c->hps.status = 0u;
+  RC(ensure_build(c, n, c->rec_traced ? c->rec_nphoton : 0));
+  RC(push_ps(c));
+  RC(enq_build(c, c->stream, c->rec_traced, c->rec_nphoton, std::max<uint64_t>(n, 1)));
+  RC(pull_ps(c));
+  if (c->hps.status) return fail(c, PPM_ERR_STATE, "photon records are inconsistent (record count does not match the depth masks)");
+  c->have_map = true;
+  return PPM_OK;
+}
+
+// probe: sort n queries at dpos by cell (the device-side query count is set from the host)
+int probe_sort_queries(ppm_ctx* c, const double* dpos, int64_t n) {
+  RC(ensure_query(c, (uint64_t)n));
+  c->hps.n_nodes = (unsigned long long)n; c->hps.n_query = 0u; c->hps.n_occ_q = 0u;
+  c->hps.sum_k = 0ull; c->hps.cand = 0ull; c->hps.status = 0u;
+  c->hps.heavy[0] = c->hps.heavy[1] = c->hps.heavy[2] = c->hps.heavy[3] = 0u;
+  RC(push_ps(c));
+  return enq_query_sort(c, c->stream, dpos, (uint64_t)n);
+}
+int launch_gather(ppm_ctx* c, const double* dpos, const double* dnrm, int64_t n, int filter, double* drgb, uint32_t* dcounts) {
   if (n <= 0) return PPM_OK;
   if (filter < PPM_FILTER_NONE || filter > PPM_FILTER_GAUSS) return fail(c, PPM_ERR_ARG, "bad filter");
-  int rc = gather_sort_queries(c, dpos, n);
-  if (rc) return rc;
-  return gather_launch(c, dpos, dnrm, n, filter, 0, nullptr, drgb, dcounts, dsumk);
+  RC(probe_sort_queries(c, dpos, n));
+  return enq_gather(c, c->stream, dpos, dnrm, (uint64_t)n, filter, 0, nullptr, drgb, dcounts, true, -1);
 }
 // k-NN estimate (no reference implementation exists: n_sample_photon is dead code, photonmap.rs:18,
 // camera.rs:181; semantics defined in SURVEY.md 8c): for every query the k nearest photons within r;
@@ -605,133 +620,469 @@ int launch_gather(ppm_ctx* c, const double* dpos, const double* dnrm, int64_t n,
 int launch_gather_knn(ppm_ctx* c, const double* dpos, const double* dnrm, int64_t n, uint32_t k, int filter, double* drgb,
                       double* dr2k, uint32_t* dcounts) {
   if (n <= 0) return PPM_OK;
-  int rc = gather_sort_queries(c, dpos, n);
-  if (rc) return rc;
-  CK(c, c->knn_lo.ensure((size_t)n * 8)); CK(c, c->knn_hi.ensure((size_t)n * 8)); CK(c, c->knn_thr.ensure((size_t)n * 8));
-  CK(c, c->knn_cnt.ensure((size_t)n * 4)); CK(c, c->counter.ensure(64));
+  RC(probe_sort_queries(c, dpos, n));
+  RC(ens(c, c->knn_lo, (size_t)n * 8)); RC(ens(c, c->knn_hi, (size_t)n * 8)); RC(ens(c, c->knn_thr, (size_t)n * 8));
+  RC(ens(c, c->knn_cnt, (size_t)n * 4)); RC(ens(c, c->knn_act, 64));
   unsigned long long* lo = c->knn_lo.as<unsigned long long>();
   unsigned long long* hi = c->knn_hi.as<unsigned long long>();
   double* thr = c->knn_thr.as<double>();
   uint32_t* cnt = c->knn_cnt.as<uint32_t>();
-  unsigned int* nact = c->counter.as<unsigned int>() + 8;
+  unsigned int* nact = c->knn_act.as<unsigned int>();
+  const double r2 = c->hps.r2;
   // photons within the fixed radius
-  if ((rc = gather_launch(c, dpos, dnrm, n, PPM_FILTER_NONE, 0, nullptr, drgb, cnt, nullptr))) return rc;
+  RC(enq_gather(c, c->stream, dpos, dnrm, (uint64_t)n, PPM_FILTER_NONE, 0, nullptr, drgb, cnt, true, -1));
   CK(c, cudaMemsetAsync(nact, 0, 4, c->stream));
-  k_knn_init<<<nblk(n, 256), 256, 0, c->stream>>>(n, c->r2, cnt, k, lo, hi, thr, nact);
+  k_knn_init<<<nblk(n, 256), 256, 0, c->stream>>>(n, r2, cnt, k, lo, hi, thr, nact);
   KCHECK(c);
   for (int it = 0; it < 70; ++it) {
     unsigned int active = 0;
     CK(c, cudaMemcpyAsync(&active, nact, 4, cudaMemcpyDeviceToHost, c->stream));
     CK(c, cudaStreamSynchronize(c->stream));
     if (!active) break;
-    if ((rc = gather_launch(c, dpos, dnrm, n, PPM_FILTER_NONE, 2, thr, nullptr, cnt, nullptr))) return rc;
+    RC(enq_gather(c, c->stream, dpos, dnrm, (uint64_t)n, PPM_FILTER_NONE, 2, thr, nullptr, cnt, true, -1));
     CK(c, cudaMemsetAsync(nact, 0, 4, c->stream));
     k_knn_step<<<nblk(n, 256), 256, 0, c->stream>>>(n, cnt, k, lo, hi, thr, nact);
     KCHECK(c);
   }
-  k_knn_finish<<<nblk(n, 256), 256, 0, c->stream>>>(n, c->r2, thr);
+  k_knn_finish<<<nblk(n, 256), 256, 0, c->stream>>>(n, r2, thr);
   KCHECK(c);
-  if ((rc = gather_launch(c, dpos, dnrm, n, filter, 1, thr, drgb, dcounts, nullptr))) return rc;
+  RC(enq_gather(c, c->stream, dpos, dnrm, (uint64_t)n, filter, 1, thr, drgb, dcounts, true, -1));
   if (dr2k) CK(c, cudaMemcpyAsync(dr2k, thr, (size_t)n * 8, cudaMemcpyDeviceToDevice, c->stream));
   return PPM_OK;
 }
 
-// Eye branch, part 1 (stream `st`): expand the eye paths into the gather-node list and
-// compute the classic direct light at every node.  drays == NULL generates camera rays.
-int eye_front(ppm_ctx* c, cudaStream_t st, DBuf& tmpbuf, const double* drays, int64_t n, int64_t first_pixel, uint64_t seed,
-              uint32_t pass, int uc, uint32_t* nn_out, int classic = 0, bool defer_direct = false) {
-  (void)tmpbuf;
-  CK(c, c->e_head.ensure((size_t)n * 4));
-  CK(c, c->e_emit.ensure((size_t)n * 24)); CK(c, c->stats.ensure(64));
-  unsigned long long* dstats = c->stats.as<unsigned long long>();
+// probe: expand the eye paths of n rays (drays == NULL: camera rays) into the gather-node pool, growing it as needed
+int probe_eye_expand(ppm_ctx* c, const double* drays, int64_t n, int64_t first_pixel, uint64_t seed, uint32_t pass, int classic, uint32_t* nn_out) {
   if (c->eye_cap < (uint64_t)n * 2) c->eye_cap = (uint64_t)n * 2;      // first guess: two gather nodes per pixel
-  if (c->timed) cudaEventRecord(c->ev[ppm_ctx::EV_B0], st);
-  uint32_t nn = 0;
   for (int attempt = 0;; ++attempt) {
-    const size_t cap = (size_t)c->eye_cap;
-    if (cap >= 0xFFFFFFFFull) return fail(c, PPM_ERR_CAPACITY, "more than 2^32-1 gather nodes");
-    CK(c, c->e_pos.ensure(cap * 24)); CK(c, c->e_nrm.ensure(cap * 24)); CK(c, c->e_w.ensure(cap * 24));
-    CK(c, c->e_prev.ensure(cap * 4));
-    CK(c, c->e_direct.ensure(cap * 24)); CK(c, c->e_photon.ensure(cap * 24));
-    CK(c, cudaMemsetAsync(c->stats.p, 0, 64, st));
-    EyeNodes nodes = {c->e_pos.as<double>(), c->e_nrm.as<double>(), c->e_w.as<double>(), c->e_prev.as<uint32_t>()};
-    k_eye_expand<<<nblk(n, 128), 128, 0, st>>>(c->scene, c->cam, drays, n, first_pixel, seed, pass, nodes, (uint32_t)cap,
-                                              c->e_head.as<uint32_t>(), c->e_emit.as<double>(), dstats + 2, dstats, classic);
+    RC(ensure_eye(c, (uint64_t)n, c->eye_cap));
+    c->hps.seed = seed; c->hps.pass = pass; c->hps.n_nodes = 0ull; c->hps.n_visited = 0ull; c->hps.status = 0u;
+    RC(push_ps(c));
+    k_eye_expand<<<nblk(n, 128), 128, 0, c->stream>>>(c->scene, c->cam, drays, n, first_pixel, c->ps, eyenodes(c), (uint32_t)c->eye_cap,
+                                                     c->e_head.as<uint32_t>(), c->e_emit.as<double>(), classic, -1);
     KCHECK(c);
-    unsigned long long made = 0;
-    CK(c, cudaMemcpyAsync(&made, dstats + 2, 8, cudaMemcpyDeviceToHost, st));
-    CK(c, cudaStreamSynchronize(st));
-    if (made <= cap) { nn = (uint32_t)made; break; }
+    RC(pull_ps(c));
+    if (c->hps.n_nodes <= c->eye_cap) break;
     if (attempt >= 2) return fail(c, PPM_ERR_CAPACITY, "gather-node pool keeps overflowing");
-    c->eye_cap = made + made / 4;                           // pool overflow: grow and walk again
+    c->eye_cap = c->hps.n_nodes + c->hps.n_nodes / 4;                 // pool overflow: grow and walk again
   }
-  EyeNodes nodes = {c->e_pos.as<double>(), c->e_nrm.as<double>(), c->e_w.as<double>(), c->e_prev.as<uint32_t>()};
-  cudaEventRecord(c->ev[ppm_ctx::EV_B1], st);
-  *nn_out = nn;
-  c->dl_masks_cur = nullptr;
-  if (uc && nn) {                                            // culling masks: right after the expansion, beside the photon branch
-    int rc = launch_dl_classify(c, st, nodes.pos3, nn, &c->dl_masks_cur);
-    if (rc) return rc;
-  }
-  if (defer_direct) return PPM_OK;                           // render_pass launches the direct light in cell-sorted order
-  cudaEventRecord(c->ev[ppm_ctx::EV_B3], st);
-  if (uc && nn) {
-    int rc = launch_direct_light(c, st, nodes.pos3, nodes.nrm3, nn, c->e_direct.as<double>(), c->dl_masks_cur);
-    if (rc) return rc;
-  }
-  cudaEventRecord(c->ev[ppm_ctx::EV_B2], st);
+  *nn_out = (uint32_t)c->hps.n_nodes;
   return PPM_OK;
 }
-// Eye branch, part 2 (main stream; the photon map must be built): gather at every node.
-// Needs the node list (event EV_B1) but not the direct light, so in render_pass it runs
-// concurrently with k_direct_light.
-int eye_gather(ppm_ctx* c, uint32_t nn, int uc_sorted_direct = 0) {
-  if (c->timed) cudaEventRecord(c->ev[ppm_ctx::EV_A3], c->stream);
-  if (nn) {
-    if (c->cam.pfilter < PPM_FILTER_NONE || c->cam.pfilter > PPM_FILTER_GAUSS) return fail(c, PPM_ERR_ARG, "bad filter");
-    int rc = gather_sort_queries(c, c->e_pos.as<double>(), nn);
-    if (rc) return rc;
-    if (uc_sorted_direct) {
-      // direct light on stream2, over the nodes in the cell-sorted order the gather uses (coherent culling masks);
-      // it runs concurrently with k_gather on the main stream
-      cudaEventRecord(c->ev[ppm_ctx::EV_A8], c->stream);
-      cudaStreamWaitEvent(c->stream2, c->ev[ppm_ctx::EV_A8], 0);
-      cudaEventRecord(c->ev[ppm_ctx::EV_B3], c->stream2);
-      rc = launch_direct_light(c, c->stream2, c->e_pos.as<double>(), c->e_nrm.as<double>(), nn, c->e_direct.as<double>(),
-                               c->dl_masks_cur, c->q_idx2.as<uint32_t>());
-      if (rc) return rc;
-      cudaEventRecord(c->ev[ppm_ctx::EV_B2], c->stream2);
-    }
-    rc = gather_launch(c, c->e_pos.as<double>(), c->e_nrm.as<double>(), nn, c->cam.pfilter, 0, nullptr, c->e_photon.as<double>(), nullptr,
-                       c->stats.as<unsigned long long>() + 1);
-    if (rc) return rc;
-  } else if (uc_sorted_direct) {
-    cudaEventRecord(c->ev[ppm_ctx::EV_B3], c->stream2);
-    cudaEventRecord(c->ev[ppm_ctx::EV_B2], c->stream2);
+// probe: classic direct light at nn points in the given order (NULL = as they are)
+int probe_direct_light(ppm_ctx* c, const double* dpos, const double* dnrm, int64_t nn, double* dout) {
+  if (nn <= 0) return PPM_OK;
+  const unsigned long long* masks = nullptr;
+  c->hps.n_nodes = (unsigned long long)nn;
+  RC(push_ps(c));
+  if (cull_on(c)) {
+    RC(ens(c, c->dl_masks, (size_t)nn * (size_t)c->scene.nlights * 8));
+    RC(enq_dl_classify(c, c->stream, dpos, dnrm, (uint64_t)nn, c->dl_masks.as<unsigned long long>()));
+    masks = c->dl_masks.as<unsigned long long>();
   }
-  c->counters[3] = nn;
-  return PPM_OK;
+  unsigned long long* dbg = nullptr;
+  RC(dl_stats_begin(c, c->stream, &dbg));
+  RC(enq_direct_light(c, c->stream, dpos, dnrm, (uint64_t)nn, dout, masks, nullptr, dbg, -1));
+  return dl_stats_print(c, c->stream, dbg);
 }
-// Eye branch, part 3 (main stream, after direct light AND gather): combine per pixel,
-// optionally add into the accumulator.
-int eye_combine(ppm_ctx* c, int64_t n, int64_t first_pixel, int uc, double* dout, double* daccum, int classic = 0) {
+int enq_combine(ppm_ctx* c, int64_t n, int64_t first_pixel, bool with_direct, bool classic, double* dout, double* daccum, int stamp_slot) {
   const D3 amb = {c->cam.ambient[0], c->cam.ambient[1], c->cam.ambient[2]};
-  k_combine<<<nblk(n, 256), 256, 0, c->stream>>>(c->e_head.as<uint32_t>(), c->e_prev.as<uint32_t>(), c->e_w.as<double>(),
-                                                (uc || classic) ? c->e_direct.as<double>() : nullptr,
+  k_combine<<<nblk(n, 256), 256, 0, c->stream>>>(c->ps, c->e_head.as<uint32_t>(), c->e_prev.as<uint32_t>(), c->e_w.as<double>(),
+                                                (with_direct || classic) ? c->e_direct.as<double>() : nullptr,
                                                 classic ? nullptr : c->e_photon.as<double>(), c->e_emit.as<double>(), n, dout, daccum,
-                                                first_pixel, amb);
+                                                first_pixel, amb, stamp_slot);
   KCHECK(c);
   return PPM_OK;
 }
-// serial version on the main stream (ppm_trace_rays)
-int do_trace_rays(ppm_ctx* c, const double* drays, int64_t n, int64_t first_pixel, uint64_t seed, uint32_t pass, int uc,
-                  double* dout, double* daccum, int classic = 0) {
+// serial eye path on the main stream (ppm_trace_rays / ppm_trace_rays_classic)
+int do_trace_rays(ppm_ctx* c, const double* drays, int64_t n, int64_t first_pixel, uint64_t seed, uint32_t pass, int uc, double* dout, int classic) {
   if (n <= 0) return PPM_OK;
   uint32_t nn = 0;
-  int rc = eye_front(c, c->stream, c->cub_tmp, drays, n, first_pixel, seed, pass, classic ? 1 : uc, &nn, classic);
-  if (rc) return rc;
-  if (!classic && (rc = eye_gather(c, nn))) return rc;
-  return eye_combine(c, n, first_pixel, uc, dout, daccum, classic);
+  RC(probe_eye_expand(c, drays, n, first_pixel, seed, pass, classic, &nn));
+  const bool direct = classic || uc;
+  if (direct && nn) RC(probe_direct_light(c, c->e_pos.as<double>(), c->e_nrm.as<double>(), nn, c->e_direct.as<double>()));
+  if (!classic && nn) {
+    if (c->cam.pfilter < PPM_FILTER_NONE || c->cam.pfilter > PPM_FILTER_GAUSS) return fail(c, PPM_ERR_ARG, "bad filter");
+    RC(launch_gather(c, c->e_pos.as<double>(), c->e_nrm.as<double>(), nn, c->cam.pfilter, c->e_photon.as<double>(), nullptr));
+  }
+  c->hps.status = 0u;
+  RC(push_ps(c));
+  return enq_combine(c, n, first_pixel, uc != 0, classic != 0, dout, nullptr, -1);
+}
+
+// ---- a rendered pass ------------------------------------------------------------------------------------------------
+int ensure_accum(ppm_ctx* c) {
+  uint64_t npix = (uint64_t)c->cam.xreso * (uint64_t)c->cam.yreso;
+  if (c->accum_pixels == npix && c->accum.p) return PPM_OK;
+  // sum image and pass counter live in ONE allocation so a single reduce covers both
+  RC(ens(c, c->accum, (size_t)(npix * 3 + 1) * 8));
+  CK(c, cudaMemsetAsync(c->accum.p, 0, (size_t)(npix * 3 + 1) * 8, c->stream));
+  c->accum_pixels = npix;
+  return PPM_OK;
+}
+
+// Per-scene calibration (once per scene / camera / seed / photon budget): the grid region and the buffer capacities of
+// a pass come from a small calibration pass with its own Philox pass id, so they do not depend on which passes a
+// context renders -- every rank of a multi-GPU frame derives the same grid and therefore the same summation order.
+int calibrate(ppm_ctx* c, uint64_t seed, int64_t nphoton, int uc) {
+  CalKey k;
+  k.scene_ver = c->scene_ver; k.cam_ver = c->cam_ver; k.seed = seed; k.nphoton = nphoton; k.uc = uc;
+  if (c->cal_valid && k == c->cal_key) return PPM_OK;
+  c->cal_valid = false;
+  double pw = 0.0, pw_cal = 0.0;
+  int64_t ns[PPM_MAX_LIGHTS], ns_cal[PPM_MAX_LIGHTS];
+  int rc;
+  if ((rc = ppm_photon_budget(c->scene.lights, c->scene.nlights, nphoton, &pw, ns))) return fail(c, rc, "photon budget");
+  const int64_t ncal = std::min<int64_t>(nphoton, PPM_CAL_PHOTONS);
+  if ((rc = ppm_photon_budget(c->scene.lights, c->scene.nlights, ncal, &pw_cal, ns_cal))) return fail(c, rc, "photon budget");
+  int64_t total = 0, total_cal = 0;
+  for (int i = 0; i < c->scene.nlights; ++i) { total += ns[i]; total_cal += ns_cal[i]; }
+  RC(do_trace_photons(c, seed, PPM_CAL_PASS, uc, ns_cal, pw_cal));
+  Bounds b; int have = 0;
+  RC(compute_bounds(c, c->n_rec, 0.01, &b, &have));
+  c->cal_bounds = b; c->cal_have_bounds = have;
+  const double per = total_cal > 0 ? (double)c->n_rec / (double)total_cal : 1.0;
+  uint64_t rec_cap = (uint64_t)(per * (double)total * 1.25) + 65536;
+  rec_cap = std::min<uint64_t>(rec_cap, (uint64_t)std::max<int64_t>(total, 1) * PPM_MAX_TRACE);
+  c->rec_cap = std::max<uint64_t>(rec_cap, 1);
+  const int64_t npix = (int64_t)c->cam.xreso * c->cam.yreso;
+  uint32_t nn = 0;
+  RC(probe_eye_expand(c, nullptr, npix, 0, seed, PPM_CAL_PASS, 0, &nn));
+  c->pass_eye_cap = (uint64_t)nn + (uint64_t)nn / 12 + 16384;
+  c->have_map = false; c->n_rec = 0;
+  c->cal_key = k; c->cal_valid = true;
+  return PPM_OK;
+}
+// buffers of a rendered pass at the calibrated capacities
+int ensure_pass(ppm_ctx* c, int64_t total) {
+  const uint64_t npix = (uint64_t)c->cam.xreso * (uint64_t)c->cam.yreso;
+  RC(ensure_records(c, c->rec_cap, (uint64_t)total));
+  RC(ensure_build(c, c->rec_cap, (uint64_t)total));
+  RC(ensure_eye(c, npix, c->pass_eye_cap));
+  RC(ensure_query(c, c->pass_eye_cap));
+  RC(ens(c, c->pass_img, (size_t)npix * 24));
+  RC(ensure_accum(c));
+  return PPM_OK;
+}
+
+// The launch sequence of ONE pass: photon branch on `stream`, eye branch on `stream2`, joined before the gather (needs
+// map + sorted queries) and before the combine (needs direct light + estimates).  Pure enqueue: runs as is in stream
+// mode and is what the graph capture records.
+int enq_pass(ppm_ctx* c, const LightSplit& ls, int64_t total, int uc, bool accumulate, unsigned long long* dl_dbg) {
+  typedef ppm_ctx E;
+  cudaStream_t sa = c->stream, sb = c->stream2;
+  const int64_t npix = (int64_t)c->cam.xreso * c->cam.yreso;
+  const uint64_t ecap = c->pass_eye_cap;
+  const bool cull = uc && cull_on(c);
+  k_pass_begin<<<1, 32, 0, sa>>>(c->ps, c->bt);
+  KCHECK(c);
+  CK(c, cudaEventRecord(c->ev[E::EV_FORK], sa));
+  CK(c, cudaStreamWaitEvent(sb, c->ev[E::EV_FORK], 0));
+  // photon branch
+  RC(enq_trace(c, sa, ls, total, uc, c->rec_cap));
+  RC(enq_stamp(c, sa, ST_TRACE_END));
+  RC(enq_build(c, sa, true, (uint64_t)total, c->rec_cap));
+  RC(enq_stamp(c, sa, ST_BUILD_END));
+  // eye branch
+  k_eye_expand<<<nblk(npix, 128), 128, 0, sb>>>(c->scene, c->cam, nullptr, npix, 0, c->ps, eyenodes(c), (uint32_t)ecap, c->e_head.as<uint32_t>(),
+                                               c->e_emit.as<double>(), 0, ST_EXPAND_BEGIN);
+  KCHECK(c);
+  RC(enq_stamp(c, sb, ST_EXPAND_END));
+  if (cull) RC(enq_dl_classify(c, sb, c->e_pos.as<double>(), c->e_nrm.as<double>(), ecap, c->dl_masks.as<unsigned long long>()));
+  RC(enq_stamp(c, sb, ST_CLASSIFY_END));
+  RC(enq_query_sort(c, sb, c->e_pos.as<double>(), ecap));
+  RC(enq_stamp(c, sb, ST_QSORT_END));
+  CK(c, cudaEventRecord(c->ev[E::EV_NODES], sb));
+  if (uc) {
+    // direct light over the nodes in the cell-sorted order of the gather (coherent culling masks), beside k_gather
+    RC(enq_direct_light(c, sb, c->e_pos.as<double>(), c->e_nrm.as<double>(), ecap, c->e_direct.as<double>(),
+                        cull ? c->dl_masks.as<unsigned long long>() : nullptr, c->sidx.as<uint32_t>(), dl_dbg, ST_DL_BEGIN));
+    RC(enq_stamp(c, sb, ST_DL_END));
+  }
+  CK(c, cudaEventRecord(c->ev[E::EV_DL], sb));
+  // gather
+  CK(c, cudaStreamWaitEvent(sa, c->ev[E::EV_NODES], 0));
+  if (!c->opt_graph) CK(c, cudaEventRecord(c->ev[E::EV_G0], sa));
+  RC(enq_gather(c, sa, c->e_pos.as<double>(), c->e_nrm.as<double>(), ecap, c->cam.pfilter, 0, nullptr, c->e_photon.as<double>(), nullptr, false,
+                ST_GATHER_BEGIN));
+  RC(enq_stamp(c, sa, ST_GATHER_END));
+  if (!c->opt_graph) CK(c, cudaEventRecord(c->ev[E::EV_G1], sa));
+  // combine + accumulate
+  CK(c, cudaStreamWaitEvent(sa, c->ev[E::EV_DL], 0));
+  RC(enq_combine(c, npix, 0, uc != 0, false, c->pass_img.as<double>(), accumulate ? c->accum.as<double>() : nullptr, ST_COMBINE_BEGIN));
+  k_pass_end<<<1, 32, 0, sa>>>(c->ps, c->out, accumulate ? c->accum.as<double>() + (size_t)npix * 3 : nullptr);
+  KCHECK(c);
+  return PPM_OK;
+}
+
+int build_graph(ppm_ctx* c, const LightSplit& ls, int64_t total, int uc) {
+  GraphKey k;
+  k.scene_ver = c->scene_ver; k.cam_ver = c->cam_ver; k.buf_gen = c->buf_gen; k.rec_cap = c->rec_cap; k.eye_cap = c->pass_eye_cap;
+  k.nphoton = total; k.uc = uc; k.cull = c->opt_dl_cull; k.heavy = c->opt_gather_heavy; k.accumulate = 1;
+  if (c->gexec && k == c->gkey) return PPM_OK;
+  if (c->gexec) { cudaGraphExecDestroy(c->gexec); c->gexec = nullptr; }
+  CK(c, cudaStreamSynchronize(c->stream));
+  CK(c, cudaStreamSynchronize(c->stream2));
+  const uint64_t l0 = c->launches;
+  CK(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+  int rc = enq_pass(c, ls, total, uc, true, nullptr);
+  cudaGraph_t g = nullptr;
+  cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+  if (rc) { if (g) cudaGraphDestroy(g); cudaGetLastError(); return rc; }
+  if (e != cudaSuccess) { c->err = std::string("graph capture: ") + cudaGetErrorString(e); cudaGetLastError(); return PPM_ERR_CUDA; }
+  e = cudaGraphInstantiate(&c->gexec, g, 0);
+  cudaGraphDestroy(g);
+  if (e != cudaSuccess) { c->gexec = nullptr; c->err = std::string("graph instantiate: ") + cudaGetErrorString(e); return PPM_ERR_CUDA; }
+  c->graph_kernels = c->launches - l0;
+  c->launches = l0;
+  c->gkey = k;
+  return PPM_OK;
+}
+
+struct BatchStats {
+  double ms[8] = {0};
+  uint64_t ct[8] = {0};
+};
+void add_pass_stats(BatchStats& s, const PassOut& o, int64_t emitted, uint64_t launches) {
+  auto d = [&](int a, int b) { return (o.stamp[a] && o.stamp[b] && o.stamp[b] >= o.stamp[a]) ? (double)(o.stamp[b] - o.stamp[a]) * 1e-6 : 0.0; };
+  s.ms[0] += d(ST_BEGIN, ST_TRACE_END);
+  s.ms[1] += d(ST_TRACE_END, ST_BUILD_END);
+  s.ms[2] += d(ST_EXPAND_BEGIN, ST_EXPAND_END);
+  s.ms[3] += d(ST_DL_BEGIN, ST_DL_END);
+  s.ms[4] += d(ST_CLASSIFY_END, ST_QSORT_END) + d(ST_GATHER_BEGIN, ST_GATHER_END);
+  s.ms[5] += d(ST_COMBINE_BEGIN, ST_END);
+  s.ms[6] += d(ST_BEGIN, ST_END);
+  s.ms[7] += d(ST_GATHER_BEGIN, ST_GATHER_END);
+  s.ct[0] += (uint64_t)emitted; s.ct[1] += o.n_rec; s.ct[2] += o.n_visited; s.ct[3] += o.n_nodes; s.ct[4] += o.sum_k;
+  s.ct[5] += launches; s.ct[6] += o.cand;
+}
+
+// the lanes of a context: itself + twins, all with the same scene, camera, switches, calibration
+int sync_twin(ppm_ctx* c, ppm_ctx* t) {
+  if (t->scene_ver != c->scene_ver || !t->have_scene) {
+    t->scene = c->scene; t->scene_ver = c->scene_ver; t->have_scene = true;
+    int rc = upload_cull(t);
+    if (rc) return fail(c, rc, "lane: " + t->err);
+  }
+  t->cam = c->cam; t->cam_ver = c->cam_ver; t->have_camera = true;
+  t->opt_dl_cull = c->opt_dl_cull; t->opt_gather_heavy = c->opt_gather_heavy; t->opt_dl_stats = c->opt_dl_stats; t->opt_graph = c->opt_graph;
+  t->cal_bounds = c->cal_bounds; t->cal_have_bounds = c->cal_have_bounds;
+  t->rec_cap = c->rec_cap; t->pass_eye_cap = c->pass_eye_cap;
+  return PPM_OK;
+}
+
+// Renders the passes idx[0..n) of a batch (pass id = first + idx*stride, radius2[idx]) on `lanes` lanes; returns the
+// reports in outs[idx].  One host thread: a pass is one graph launch (or, in stream mode, one enqueue sequence).
+int run_passes(ppm_ctx* c, std::vector<ppm_ctx*>& lane, const std::vector<int32_t>& idx, uint64_t seed, uint32_t first_pass, uint32_t stride,
+               const double* radius2, double power, const LightSplit& ls, int64_t total, int uc, std::vector<PassOut>& outs) {
+  const int lanes = (int)lane.size();
+  size_t done = 0;
+  while (done < idx.size()) {
+    const size_t chunk = std::min(idx.size() - done, (size_t)PPM_BATCH_MAX * (size_t)lanes);
+    // batch tables
+    std::vector<int> cnt(lanes, 0);
+    for (size_t k = 0; k < chunk; ++k) {
+      const int j = (int)(k % (size_t)lanes);
+      ppm_ctx* x = lane[j];
+      const int32_t i = idx[done + k];
+      x->bt_h->pass[cnt[j]] = first_pass + (uint32_t)i * stride;
+      x->bt_h->r2[cnt[j]] = radius2[i];
+      ++cnt[j];
+    }
+    for (int j = 0; j < lanes; ++j) {
+      ppm_ctx* x = lane[j];
+      if (!cnt[j]) continue;
+      x->bt_h->seed = seed; x->bt_h->power = power;
+      CK(c, cudaMemcpyAsync(x->bt, x->bt_h, sizeof(BatchDev), cudaMemcpyHostToDevice, x->stream));
+      // bounds + cursor: the grid region of the pass state and the table position
+      x->hps.cursor = 0u;
+      x->hps.bounds = x->cal_bounds; x->hps.have_bounds = x->cal_have_bounds;
+      CK(c, cudaMemcpyAsync(x->ps, &x->hps, sizeof(PassDev), cudaMemcpyHostToDevice, x->stream));
+    }
+    // the passes, alternating over the lanes
+    for (size_t k = 0; k < chunk; ++k) {
+      ppm_ctx* x = lane[k % (size_t)lanes];
+      if (x->opt_graph && x->gexec) {
+        cudaError_t e = cudaGraphLaunch(x->gexec, x->stream);
+        if (e != cudaSuccess) return fail(c, PPM_ERR_CUDA, std::string("graph launch: ") + cudaGetErrorString(e));
+      } else {
+        unsigned long long* dbg = nullptr;
+        int rc = dl_stats_begin(x, x->stream2, &dbg);
+        if (!rc) rc = enq_pass(x, ls, total, uc, true, dbg);
+        if (!rc && dbg) { cudaStreamSynchronize(x->stream); rc = dl_stats_print(x, x->stream2, dbg); }
+        if (rc) return x == c ? rc : fail(c, rc, "lane: " + x->err);
+        if (!x->opt_graph) {                               // stream mode: CUDA events around k_gather (+ heavy parts) as a cross-check of the stamps
+          cudaStreamSynchronize(x->stream);
+          float f = 0.f;
+          if (cudaEventElapsedTime(&f, x->ev[ppm_ctx::EV_G0], x->ev[ppm_ctx::EV_G1]) == cudaSuccess) x->ms[7] += (double)f; else cudaGetLastError();
+        }
+      }
+    }
+    // reports
+    for (int j = 0; j < lanes; ++j) {
+      ppm_ctx* x = lane[j];
+      if (!cnt[j]) continue;
+      CK(c, cudaMemcpyAsync(x->out_h, x->out, sizeof(PassOut) * (size_t)cnt[j], cudaMemcpyDeviceToHost, x->stream));
+    }
+    for (int j = 0; j < lanes; ++j) {
+      if (!cnt[j]) continue;
+      cudaError_t e = cudaStreamSynchronize(lane[j]->stream);
+      if (e != cudaSuccess) return fail(c, PPM_ERR_CUDA, std::string("pass batch: ") + cudaGetErrorString(e));
+    }
+    std::vector<int> pos(lanes, 0);
+    for (size_t k = 0; k < chunk; ++k) {
+      const int j = (int)(k % (size_t)lanes);
+      outs[(size_t)idx[done + k]] = lane[j]->out_h[pos[j]++];
+    }
+    done += chunk;
+  }
+  return PPM_OK;
+}
+
+int render_batch(ppm_ctx* c, uint64_t seed, uint32_t first_pass, uint32_t stride, int32_t npass, int64_t nphoton, const double* radius2,
+                 int uc, int lanes_wanted) {
+  if (!c->have_scene || c->scene.nlights == 0) return fail(c, PPM_ERR_STATE, "scene with lights not set");
+  if (!c->have_camera) return fail(c, PPM_ERR_STATE, "camera not set");
+  if (nphoton <= 0) return fail(c, PPM_ERR_ARG, "nphoton must be positive");
+  if (c->cam.pfilter < PPM_FILTER_NONE || c->cam.pfilter > PPM_FILTER_GAUSS) return fail(c, PPM_ERR_ARG, "bad filter");
+  for (int32_t i = 0; i < npass; ++i)
+    if (!(radius2[i] > 0.0)) return fail(c, PPM_ERR_ARG, "radius2 must be positive");
+  CK(c, cudaSetDevice(c->device));
+  int rc;
+  double power;
+  int64_t ns[PPM_MAX_LIGHTS];
+  if ((rc = ppm_photon_budget(c->scene.lights, c->scene.nlights, nphoton, &power, ns))) return fail(c, rc, "photon budget");
+  LightSplit ls;
+  int64_t total = 0;
+  RC(light_split(c, ns, &ls, &total));
+  if ((uint64_t)total >= (1ull << 32) - 16) return fail(c, PPM_ERR_CAPACITY, "at most 2^32-16 photons per pass");
+  RC(calibrate(c, seed, nphoton, uc));
+  int lanes = std::max(1, std::min(lanes_wanted, (int)PPM_MAX_LANES));
+  lanes = std::min<int>(lanes, npass);
+  std::vector<ppm_ctx*> lane(lanes, nullptr);
+  lane[0] = c;
+  for (int j = 1; j < lanes; ++j) {
+    if ((int)c->twins.size() < j) {
+      ppm_ctx* t = nullptr;
+      rc = ppm_create(c->device, &t);
+      if (rc) return fail(c, rc, "cannot create another lane");
+      c->twins.push_back(t);
+    }
+    lane[j] = c->twins[j - 1];
+  }
+  std::vector<int32_t> todo(npass);
+  for (int32_t i = 0; i < npass; ++i) todo[i] = i;
+  std::vector<PassOut> outs((size_t)npass);
+  BatchStats st;
+  uint64_t retried = 0, stream_launches = 0;
+  int last_lane = 0;
+  for (int attempt = 0; !todo.empty(); ++attempt) {
+    for (size_t k = 0; k < todo.size(); ++k)
+      if (todo[k] == npass - 1) last_lane = (int)(k % (size_t)lanes);
+    uint64_t l0 = 0;
+    for (int j = 0; j < lanes; ++j) l0 += lane[j]->launches;
+    for (int j = 0; j < lanes; ++j) {
+      ppm_ctx* x = lane[j];
+      if (j > 0) RC(sync_twin(c, x));
+      if ((rc = ensure_pass(x, total))) return x == c ? rc : fail(c, rc, "lane: " + x->err);
+      x->ms[7] = 0.0;
+      if (x->opt_graph && !x->opt_dl_stats) {
+        if ((rc = build_graph(x, ls, total, uc))) return x == c ? rc : fail(c, rc, "lane: " + x->err);
+      } else if (x->gexec) { cudaGraphExecDestroy(x->gexec); x->gexec = nullptr; }
+    }
+    RC(run_passes(c, lane, todo, seed, first_pass, stride, radius2, power, ls, total, uc, outs));
+    for (int j = 0; j < lanes; ++j) stream_launches += lane[j]->launches;
+    stream_launches -= l0;
+    // passes that overflowed a buffer did not count: grow and render them again
+    std::vector<int32_t> again;
+    uint64_t need_rec = 0, need_nodes = 0;
+    for (int32_t i : todo) {
+      const PassOut& o = outs[(size_t)i];
+      if (o.status) {
+        again.push_back(i);
+        if (o.status & PPM_ST_REC_OVERFLOW) need_rec = std::max<uint64_t>(need_rec, o.n_rec);
+        if (o.status & PPM_ST_NODE_OVERFLOW) need_nodes = std::max<uint64_t>(need_nodes, o.n_nodes);
+      } else {
+        add_pass_stats(st, o, total, c->opt_graph && !c->opt_dl_stats ? c->graph_kernels : 0);
+      }
+    }
+    if (!again.empty()) {
+      if (attempt >= 3) return fail(c, PPM_ERR_CAPACITY, "pass buffers keep overflowing");
+      if (need_rec) c->rec_cap = std::min<uint64_t>(need_rec + need_rec / 4 + 65536, (uint64_t)total * PPM_MAX_TRACE);
+      if (need_nodes) c->pass_eye_cap = need_nodes + need_nodes / 8 + 16384;
+      if (!need_rec && !need_nodes) return fail(c, PPM_ERR_STATE, "a pass reported an inconsistent state");
+      retried += again.size();
+    }
+    todo.swap(again);
+  }
+  // merge the twins' accumulators (and pass counters) into ours; the last pass image follows the last pass
+  const int64_t nacc = (int64_t)c->accum_pixels * 3 + 1;
+  for (int j = 1; j < lanes; ++j) {
+    k_accum_merge<<<nblk(nacc, 256), 256, 0, c->stream>>>(c->accum.as<double>(), lane[j]->accum.as<double>(), nacc);
+    KCHECK(c);
+  }
+  if (last_lane != 0)
+    CK(c, cudaMemcpyAsync(c->pass_img.p, lane[last_lane]->pass_img.p, (size_t)c->accum_pixels * 24, cudaMemcpyDeviceToDevice, c->stream));
+  CK(c, cudaStreamSynchronize(c->stream));
+  if (!c->opt_graph) {                                    // stream mode: k_gather by CUDA events
+    double g = 0.0;
+    for (int j = 0; j < lanes; ++j) g += lane[j]->ms[7];
+    st.ms[7] = g;
+  }
+  st.ct[5] += stream_launches;                            // (graph mode: the graph's kernel nodes were counted per pass above)
+  st.ct[7] = retried;
+  std::memcpy(c->ms, st.ms, sizeof st.ms);
+  std::memcpy(c->counters, st.ct, sizeof st.ct);
+  // the photon set and the map of this lane's last pass stay current for the probe entry points
+  RC(pull_ps(c));
+  c->n_rec = c->hps.n_map; c->power = power; c->rec_traced = true; c->rec_nphoton = (uint64_t)total;
+  c->have_map = c->hps.status == 0u;
+  return PPM_OK;
+}
+
+// ---- NCCL, loaded at run time -------------------------------------------------------------------------------------------
+struct NcclUid { char internal[128]; };
+struct NcclApi {
+  void* h = nullptr;
+  int (*GetUniqueId)(NcclUid*) = nullptr;
+  int (*CommInitRank)(void**, int, NcclUid, int) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  int (*Reduce)(const void*, void*, size_t, int, int, int, void*, cudaStream_t) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  std::string why;
+};
+NcclApi* nccl_api() {
+  static NcclApi api;
+  static bool tried = false;
+  if (tried) return &api;
+  tried = true;
+  // the copy already mapped into the process (e.g. PyTorch's) is found first by its soname
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* n : names) {
+    api.h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (api.h) break;
+  }
+  if (!api.h) { api.why = std::string("cannot load libnccl.so.2: ") + (dlerror() ? dlerror() : "?"); return &api; }
+  api.GetUniqueId = (int (*)(NcclUid*))dlsym(api.h, "ncclGetUniqueId");
+  api.CommInitRank = (int (*)(void**, int, NcclUid, int))dlsym(api.h, "ncclCommInitRank");
+  api.CommDestroy = (int (*)(void*))dlsym(api.h, "ncclCommDestroy");
+  api.Reduce = (int (*)(const void*, void*, size_t, int, int, int, void*, cudaStream_t))dlsym(api.h, "ncclReduce");
+  api.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(api.h, "ncclAllReduce");
+  api.GetErrorString = (const char* (*)(int))dlsym(api.h, "ncclGetErrorString");
+  if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.Reduce || !api.AllReduce) {
+    api.why = "libnccl.so.2 lacks an expected symbol";
+    api.h = nullptr;
+  }
+  return &api;
+}
+std::string nccl_err(NcclApi* a, int r) { return a->GetErrorString ? std::string(a->GetErrorString(r)) : ("nccl error " + std::to_string(r)); }
+const int kNcclFloat64 = 8, kNcclSum = 0;
+
+int opt_from_env(const char* name, int dflt) {
+  const char* e = std::getenv(name);
+  if (!e || !e[0]) return dflt;
+  return std::atoi(e);
 }
 
 }  // namespace
@@ -752,15 +1103,31 @@ int ppm_create(int device, ppm_ctx** out) {
   c->device = device;
   cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
   if (c->sm_count <= 0) c->sm_count = 148;
-  // The main stream gets the highest priority: in render_pass its small photon-branch kernels
-  // must be dispatched ahead of the remaining blocks of the long eye-branch kernels on stream2.
+  // The main stream gets the highest priority: its small photon-branch kernels must be dispatched ahead of the
+  // remaining blocks of the long eye-branch kernels on stream2.
   int prio_lo = 0, prio_hi = 0;
   cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
-  if (cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess) { delete c; return PPM_ERR_CUDA; }
-  if (cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, prio_lo) != cudaSuccess) { cudaStreamDestroy(c->stream); delete c; return PPM_ERR_CUDA; }
-  for (int i = 0; i < ppm_ctx::EV_COUNT; ++i) cudaEventCreate(&c->ev[i]);
+  bool ok = cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_hi) == cudaSuccess;
+  ok = ok && cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, prio_lo) == cudaSuccess;
+  for (int i = 0; ok && i < ppm_ctx::EV_COUNT; ++i)
+    ok = cudaEventCreateWithFlags(&c->ev[i], (i == ppm_ctx::EV_G0 || i == ppm_ctx::EV_G1) ? cudaEventDefault : cudaEventDisableTiming) == cudaSuccess;
+  ok = ok && cudaMalloc((void**)&c->ps, sizeof(PassDev)) == cudaSuccess;
+  ok = ok && cudaMalloc((void**)&c->bt, sizeof(BatchDev)) == cudaSuccess;
+  ok = ok && cudaMalloc((void**)&c->out, sizeof(PassOut) * PPM_BATCH_MAX) == cudaSuccess;
+  ok = ok && cudaMallocHost((void**)&c->bt_h, sizeof(BatchDev)) == cudaSuccess;
+  ok = ok && cudaMallocHost((void**)&c->out_h, sizeof(PassOut) * PPM_BATCH_MAX) == cudaSuccess;
+  if (!ok) { cudaGetLastError(); ppm_destroy(c); return PPM_ERR_CUDA; }
+  std::memset(&c->hps, 0, sizeof c->hps);
+  c->hps.grid.nx = c->hps.grid.ny = c->hps.grid.nz = 1; c->hps.grid.ncells = 1; c->hps.grid.inv_cell = 1.0;
+  cudaMemcpy(c->ps, &c->hps, sizeof(PassDev), cudaMemcpyHostToDevice);
   std::memset(&c->scene, 0, sizeof c->scene);
   ppm_camera_default(&c->cam);
+  // switches: the environment is read once, here
+  c->opt_lanes = std::max(1, std::min(opt_from_env("PPM_LANES", PPM_DEFAULT_LANES), (int)PPM_MAX_LANES));
+  c->opt_dl_cull = opt_from_env("PPM_DL_CULL", 1) != 0;
+  c->opt_gather_heavy = opt_from_env("PPM_GATHER_HEAVY", 1) != 0;
+  c->opt_dl_stats = opt_from_env("PPM_DL_STATS", 0) != 0;
+  c->opt_graph = opt_from_env("PPM_GRAPH", 1) != 0;
   *out = c;
   return PPM_OK;
 }
@@ -770,34 +1137,74 @@ void ppm_destroy(ppm_ctx* c) {
   for (ppm_ctx* t : c->twins) ppm_destroy(t);
   c->twins.clear();
   cudaSetDevice(c->device);
-  cudaStreamSynchronize(c->stream);
-  DBuf* all[] = {&c->r_pos, &c->r_dir, &c->r_wl, &c->r_tag, &c->counter, &c->keys, &c->keys2, &c->vals, &c->vals2, &c->cub_tmp,
-                 &c->cell_start, &c->hist, &c->bbox, &c->axis_hist, &c->m_P, &c->m_D, &c->m_orig, &c->q_key, &c->q_key2, &c->q_idx, &c->q_idx2, &c->knn_lo, &c->knn_hi, &c->knn_thr, &c->knn_cnt,
-                 &c->st_in0, &c->st_in1, &c->st_out0, &c->st_out1, &c->st_out2, &c->st_out3, &c->st_out4,
-                 &c->e_head, &c->e_prev, &c->e_pos, &c->e_nrm, &c->e_w, &c->e_emit, &c->e_direct, &c->e_photon, &c->e_rays,
-                 &c->pass_img, &c->accum, &c->npass, &c->stats, &c->cub_tmp2, &c->cull, &c->dl_dbg, &c->dl_masks, &c->heavy};
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->stream2) cudaStreamSynchronize(c->stream2);
+  if (c->comm) { NcclApi* a = nccl_api(); if (a->h) a->CommDestroy(c->comm); c->comm = nullptr; }
+  if (c->gexec) cudaGraphExecDestroy(c->gexec);
+  DBuf* all[] = {&c->r_pos, &c->r_dir, &c->r_wl, &c->r_tag, &c->pmask, &c->pbase, &c->order0, &c->cid, &c->words_p, &c->start_p, &c->key_a, &c->key_b,
+                 &c->val_a, &c->val_b, &c->rs_table, &c->tsum_p, &c->m_P, &c->m_D, &c->m_orig, &c->bbox, &c->axis_hist, &c->qcell, &c->words_q,
+                 &c->qcnt, &c->qstart, &c->qrank, &c->qpic, &c->skey, &c->sidx, &c->tsum_q, &c->heavy, &c->knn_lo, &c->knn_hi, &c->knn_thr,
+                 &c->knn_cnt, &c->knn_act, &c->st_in0, &c->st_in1, &c->st_out0, &c->st_out1, &c->st_out2, &c->st_out3, &c->st_out4, &c->e_head,
+                 &c->e_prev, &c->e_pos, &c->e_nrm, &c->e_w, &c->e_emit, &c->e_direct, &c->e_photon, &c->dl_dbg, &c->dl_masks, &c->cull,
+                 &c->pass_img, &c->accum};
   for (DBuf* b : all) b->release();
+  if (c->ps) cudaFree(c->ps);
+  if (c->bt) cudaFree(c->bt);
+  if (c->out) cudaFree(c->out);
+  if (c->bt_h) cudaFreeHost(c->bt_h);
+  if (c->out_h) cudaFreeHost(c->out_h);
   for (int i = 0; i < ppm_ctx::EV_COUNT; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
-  cudaStreamSynchronize(c->stream2);
-  cudaStreamDestroy(c->stream2);
-  cudaStreamDestroy(c->stream);
+  if (c->stream2) cudaStreamDestroy(c->stream2);
+  if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
 
 const char* ppm_last_error(const ppm_ctx* c) { return c ? c->err.c_str() : "null context"; }
 void* ppm_stream(ppm_ctx* c) { return c ? (void*)c->stream : nullptr; }
 
+static int* opt_slot(ppm_ctx* c, const char* name) {
+  if (!name) return nullptr;
+  if (!std::strcmp(name, "lanes")) return &c->opt_lanes;
+  if (!std::strcmp(name, "dl_cull")) return &c->opt_dl_cull;
+  if (!std::strcmp(name, "gather_heavy")) return &c->opt_gather_heavy;
+  if (!std::strcmp(name, "dl_stats")) return &c->opt_dl_stats;
+  if (!std::strcmp(name, "graph")) return &c->opt_graph;
+  return nullptr;
+}
+int ppm_option_set(ppm_ctx* c, const char* name, int64_t value) {
+  if (!c) return PPM_ERR_ARG;
+  int* s = opt_slot(c, name);
+  if (!s) return fail(c, PPM_ERR_ARG, std::string("unknown option ") + (name ? name : "(null)"));
+  if (s == &c->opt_lanes) {
+    if (value < 1 || value > PPM_MAX_LANES) return fail(c, PPM_ERR_ARG, "lanes must be 1..8");
+    *s = (int)value;
+  } else {
+    *s = value != 0;
+  }
+  return PPM_OK;
+}
+int ppm_option_get(ppm_ctx* c, const char* name, int64_t* value) {
+  if (!c || !value) return PPM_ERR_ARG;
+  int* s = opt_slot(c, name);
+  if (!s) return fail(c, PPM_ERR_ARG, std::string("unknown option ") + (name ? name : "(null)"));
+  *value = *s;
+  return PPM_OK;
+}
+
 int ppm_scene_set(ppm_ctx* c, const ppm_prim* prims, int32_t nprims, const ppm_material* mats, int32_t nmats,
                   const ppm_light* lights, int32_t nlights) {
   if (!c) return PPM_ERR_ARG;
   if (!prims || !mats || nprims <= 0 || nmats <= 0 || nlights < 0 || (nlights > 0 && !lights)) return fail(c, PPM_ERR_ARG, "null/empty scene arrays");
-  if (nprims > PPM_MAX_PRIMS || nmats > PPM_MAX_MATS || nlights > PPM_MAX_LIGHTS) return fail(c, PPM_ERR_CAPACITY, "scene exceeds 64 prims / 48 materials / 8 lights");
+  if (nprims > PPM_MAX_PRIMS || nmats > PPM_MAX_MATS || nlights > PPM_MAX_LIGHTS)
+    return fail(c, PPM_ERR_CAPACITY, "scene exceeds 64 primitives / 48 materials / 8 lights (the hit test walks every primitive; no BVH)");
   for (int i = 0; i < nprims; ++i) {
     if (prims[i].material < 0 || prims[i].material >= nmats) return fail(c, PPM_ERR_ARG, "primitive material index out of range");
     if (prims[i].type < PPM_SHAPE_POINT || prims[i].type > PPM_SHAPE_PARALLELOGRAM) return fail(c, PPM_ERR_ARG, "bad shape type");
   }
   for (int i = 0; i < nlights; ++i)
     if (lights[i].type < PPM_LIGHT_POINT || lights[i].type > PPM_LIGHT_SUN) return fail(c, PPM_ERR_ARG, "bad light type");
+  CK(c, cudaSetDevice(c->device));
+  CK(c, cudaStreamSynchronize(c->stream));
   std::memset(&c->scene, 0, sizeof c->scene);
   c->scene.nprims = nprims; c->scene.nmats = nmats; c->scene.nlights = nlights;
   std::memcpy(c->scene.prims, prims, sizeof(ppm_prim) * nprims);
@@ -811,10 +1218,9 @@ int ppm_scene_set(ppm_ctx* c, const ppm_prim* prims, int32_t nprims, const ppm_m
     else if (prims[o].type == PPM_SHAPE_POLYGON) c->scene.types.poly |= bit;
     else if (prims[o].type == PPM_SHAPE_PARALLELOGRAM) c->scene.types.para |= bit;
   }
-  CK(c, cudaSetDevice(c->device));
-  int rc = upload_cull(c);
-  if (rc) return rc;
+  RC(upload_cull(c));
   c->have_scene = true;
+  c->scene_ver++;
   return PPM_OK;
 }
 
@@ -824,6 +1230,7 @@ int ppm_camera_set(ppm_ctx* c, const ppm_camera* cam) {
   if (cam->pfilter < PPM_FILTER_NONE || cam->pfilter > PPM_FILTER_GAUSS) return fail(c, PPM_ERR_ARG, "bad photon filter");
   c->cam = *cam;
   c->have_camera = true;
+  c->cam_ver++;
   return PPM_OK;
 }
 
@@ -834,21 +1241,20 @@ int ppm_intersect(ppm_ctx* c, const double* rays6, int64_t n, int32_t* hit_idx, 
   if (n == 0) return PPM_OK;
   CK(c, cudaSetDevice(c->device));
   const void* drays; void *dh, *dt, *dp, *dn, *di;
-  int rc;
-  if ((rc = stage_in(c, rays6, (size_t)n * 48, c->st_in0, &drays))) return rc;
-  if ((rc = stage_out(c, hit_idx, (size_t)n * 4, c->st_out0, &dh))) return rc;
-  if ((rc = stage_out(c, t, (size_t)n * 8, c->st_out1, &dt))) return rc;
-  if ((rc = stage_out(c, pos3, (size_t)n * 24, c->st_out2, &dp))) return rc;
-  if ((rc = stage_out(c, nrm3, (size_t)n * 24, c->st_out3, &dn))) return rc;
-  if ((rc = stage_out(c, io, (size_t)n * 4, c->st_out4, &di))) return rc;
+  RC(stage_in(c, rays6, (size_t)n * 48, c->st_in0, &drays));
+  RC(stage_out(c, hit_idx, (size_t)n * 4, c->st_out0, &dh));
+  RC(stage_out(c, t, (size_t)n * 8, c->st_out1, &dt));
+  RC(stage_out(c, pos3, (size_t)n * 24, c->st_out2, &dp));
+  RC(stage_out(c, nrm3, (size_t)n * 24, c->st_out3, &dn));
+  RC(stage_out(c, io, (size_t)n * 4, c->st_out4, &di));
   k_intersect<<<nblk(n, 128), 128, 0, c->stream>>>(c->scene, (const double*)drays, n, (int32_t*)dh, (double*)dt, (double*)dp,
                                                   (double*)dn, (int32_t*)di);
   KCHECK(c);
-  if ((rc = finish_out(c, hit_idx, (size_t)n * 4, dh))) return rc;
-  if ((rc = finish_out(c, t, (size_t)n * 8, dt))) return rc;
-  if ((rc = finish_out(c, pos3, (size_t)n * 24, dp))) return rc;
-  if ((rc = finish_out(c, nrm3, (size_t)n * 24, dn))) return rc;
-  if ((rc = finish_out(c, io, (size_t)n * 4, di))) return rc;
+  RC(finish_out(c, hit_idx, (size_t)n * 4, dh));
+  RC(finish_out(c, t, (size_t)n * 8, dt));
+  RC(finish_out(c, pos3, (size_t)n * 24, dp));
+  RC(finish_out(c, nrm3, (size_t)n * 24, dn));
+  RC(finish_out(c, io, (size_t)n * 4, di));
   CK(c, cudaStreamSynchronize(c->stream));
   return PPM_OK;
 }
@@ -859,14 +1265,13 @@ int ppm_emit_photons(ppm_ctx* c, uint64_t seed, uint32_t pass, const int64_t* n_
   if (!n_per_light || !out) return fail(c, PPM_ERR_ARG, "null argument");
   CK(c, cudaSetDevice(c->device));
   LightSplit ls; int64_t total;
-  int rc = light_split(c, n_per_light, &ls, &total);
-  if (rc) return rc;
+  RC(light_split(c, n_per_light, &ls, &total));
   if (total == 0) return PPM_OK;
   void* d;
-  if ((rc = stage_out(c, out, (size_t)total * sizeof(ppm_photon), c->st_out0, &d))) return rc;
+  RC(stage_out(c, out, (size_t)total * sizeof(ppm_photon), c->st_out0, &d));
   k_emit<<<nblk(total, 128), 128, 0, c->stream>>>(c->scene, ls, seed, pass, total, (ppm_photon*)d);
   KCHECK(c);
-  if ((rc = finish_out(c, out, (size_t)total * sizeof(ppm_photon), d))) return rc;
+  RC(finish_out(c, out, (size_t)total * sizeof(ppm_photon), d));
   CK(c, cudaStreamSynchronize(c->stream));
   return PPM_OK;
 }
@@ -876,8 +1281,7 @@ int ppm_trace_photons(ppm_ctx* c, uint64_t seed, uint32_t pass, int uc, const in
   if (!c->have_scene || c->scene.nlights == 0) return fail(c, PPM_ERR_STATE, "scene with lights not set");
   if (!n_per_light) return fail(c, PPM_ERR_ARG, "null n_per_light");
   CK(c, cudaSetDevice(c->device));
-  int rc = do_trace_photons(c, seed, pass, uc, n_per_light, power);
-  if (rc) return rc;
+  RC(do_trace_photons(c, seed, pass, uc, n_per_light, power));
   if (n_stored) *n_stored = c->n_rec;
   return PPM_OK;
 }
@@ -895,12 +1299,12 @@ int ppm_photons_export(ppm_ctx* c, ppm_photon* out, uint64_t cap, uint64_t* tags
   if (!out) return fail(c, PPM_ERR_ARG, "null output");
   if (cap < c->n_rec) return fail(c, PPM_ERR_CAPACITY, "export buffer too small");
   CK(c, cudaSetDevice(c->device));
-  void* d; int rc;
+  void* d;
   size_t bytes = (size_t)c->n_rec * sizeof(ppm_photon);
-  if ((rc = stage_out(c, out, bytes, c->st_out0, &d))) return rc;
+  RC(stage_out(c, out, bytes, c->st_out0, &d));
   k_export<<<nblk((int64_t)c->n_rec, 256), 256, 0, c->stream>>>(recbuf(c), c->n_rec, (ppm_photon*)d);
   KCHECK(c);
-  if ((rc = finish_out(c, out, bytes, d))) return rc;
+  RC(finish_out(c, out, bytes, d));
   if (tags) CK(c, cudaMemcpyAsync(tags, c->r_tag.p, (size_t)c->n_rec * 8, is_device_ptr(tags) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->stream));
   CK(c, cudaStreamSynchronize(c->stream));
   return PPM_OK;
@@ -909,29 +1313,25 @@ int ppm_photons_export(ppm_ctx* c, ppm_photon* out, uint64_t cap, uint64_t* tags
 int ppm_photons_import(ppm_ctx* c, const ppm_photon* in, uint64_t n, double power) {
   if (!c) return PPM_ERR_ARG;
   if (n > 0 && !in) return fail(c, PPM_ERR_ARG, "null input");
-  if (n >= (1ull << 32)) return fail(c, PPM_ERR_CAPACITY, "at most 2^32-1 photon records");
+  if (n >= (1ull << 32) - 16) return fail(c, PPM_ERR_CAPACITY, "at most 2^32-16 photon records");
   CK(c, cudaSetDevice(c->device));
-  int rc = ensure_records(c, n ? n : 1);
-  if (rc) return rc;
+  RC(ensure_records(c, n ? n : 1, 0));
   if (n) {
     const void* d;
-    if ((rc = stage_in(c, in, (size_t)n * sizeof(ppm_photon), c->st_in0, &d))) return rc;
+    RC(stage_in(c, in, (size_t)n * sizeof(ppm_photon), c->st_in0, &d));
     k_import<<<nblk((int64_t)n, 256), 256, 0, c->stream>>>((const ppm_photon*)d, n, recbuf(c));
     KCHECK(c);
     CK(c, cudaStreamSynchronize(c->stream));
   }
   c->n_rec = n; c->power = power; c->have_map = false;
-  c->tag_bits = tag_bits_for(n);
+  c->rec_traced = false; c->rec_nphoton = 0;
   return PPM_OK;
 }
 
 int ppm_map_build(ppm_ctx* c, double radius2) {
   if (!c) return PPM_ERR_ARG;
   CK(c, cudaSetDevice(c->device));
-  int rc = do_map_build(c, radius2);
-  if (rc) return rc;
-  CK(c, cudaStreamSynchronize(c->stream));
-  return PPM_OK;
+  return do_map_build(c, radius2, true);
 }
 
 int ppm_within(ppm_ctx* c, const double* q3, int64_t nq, uint32_t* idx, uint32_t* count, uint32_t cap) {
@@ -940,17 +1340,16 @@ int ppm_within(ppm_ctx* c, const double* q3, int64_t nq, uint32_t* idx, uint32_t
   if (nq < 0 || (nq > 0 && (!q3 || !count || (cap > 0 && !idx)))) return fail(c, PPM_ERR_ARG, "null argument");
   if (nq == 0) return PPM_OK;
   CK(c, cudaSetDevice(c->device));
-  const void* dq; void *di, *dc; int rc;
+  const void* dq; void *di, *dc;
   size_t ib = (size_t)nq * (cap ? cap : 1) * 4;
-  if ((rc = stage_in(c, q3, (size_t)nq * 24, c->st_in0, &dq))) return rc;
-  CK(c, c->st_out0.ensure(ib));
+  RC(stage_in(c, q3, (size_t)nq * 24, c->st_in0, &dq));
+  RC(ens(c, c->st_out0, ib));
   di = c->st_out0.p;
   CK(c, cudaMemsetAsync(di, 0, ib, c->stream));      // slots beyond a query's count stay 0
-  if ((rc = stage_out(c, count, (size_t)nq * 4, c->st_out1, &dc))) return rc;
-  k_within<<<nblk(nq, 128), 128, 0, c->stream>>>(c->grid, c->cell_start.as<uint32_t>(), mapsoa(c), (const double*)dq, nq, c->r2,
-                                                (uint32_t*)di, (uint32_t*)dc, cap);
+  RC(stage_out(c, count, (size_t)nq * 4, c->st_out1, &dc));
+  k_within<<<nblk(nq, 128), 128, 0, c->stream>>>(c->ps, cellindex(c), mapsoa(c), (const double*)dq, nq, (uint32_t*)di, (uint32_t*)dc, cap);
   KCHECK(c);
-  if ((rc = finish_out(c, count, (size_t)nq * 4, dc))) return rc;
+  RC(finish_out(c, count, (size_t)nq * 4, dc));
   if (cap) {
     // sort each neighbour list ascending by photon index on the host (probe only)
     std::vector<uint32_t> h((size_t)nq * cap), hc((size_t)nq);
@@ -975,14 +1374,14 @@ int ppm_gather(ppm_ctx* c, const double* pos3, const double* nrm3, int64_t n, in
   if (filter < PPM_FILTER_NONE || filter > PPM_FILTER_GAUSS) return fail(c, PPM_ERR_ARG, "bad filter");
   if (n == 0) return PPM_OK;
   CK(c, cudaSetDevice(c->device));
-  const void *dp, *dn; void *dr, *dc; int rc;
-  if ((rc = stage_in(c, pos3, (size_t)n * 24, c->st_in0, &dp))) return rc;
-  if ((rc = stage_in(c, nrm3, (size_t)n * 24, c->st_in1, &dn))) return rc;
-  if ((rc = stage_out(c, rgb3, (size_t)n * 24, c->st_out0, &dr))) return rc;
-  if ((rc = stage_out(c, counts, (size_t)n * 4, c->st_out1, &dc))) return rc;
-  if ((rc = launch_gather(c, (const double*)dp, (const double*)dn, n, filter, (double*)dr, (uint32_t*)dc, nullptr))) return rc;
-  if ((rc = finish_out(c, rgb3, (size_t)n * 24, dr))) return rc;
-  if ((rc = finish_out(c, counts, (size_t)n * 4, dc))) return rc;
+  const void *dp, *dn; void *dr, *dc;
+  RC(stage_in(c, pos3, (size_t)n * 24, c->st_in0, &dp));
+  RC(stage_in(c, nrm3, (size_t)n * 24, c->st_in1, &dn));
+  RC(stage_out(c, rgb3, (size_t)n * 24, c->st_out0, &dr));
+  RC(stage_out(c, counts, (size_t)n * 4, c->st_out1, &dc));
+  RC(launch_gather(c, (const double*)dp, (const double*)dn, n, filter, (double*)dr, (uint32_t*)dc));
+  RC(finish_out(c, rgb3, (size_t)n * 24, dr));
+  RC(finish_out(c, counts, (size_t)n * 4, dc));
   CK(c, cudaStreamSynchronize(c->stream));
   return PPM_OK;
 }
@@ -995,16 +1394,16 @@ int ppm_gather_knn(ppm_ctx* c, const double* pos3, const double* nrm3, int64_t n
   if (filter < PPM_FILTER_NONE || filter > PPM_FILTER_GAUSS) return fail(c, PPM_ERR_ARG, "bad filter");
   if (n == 0) return PPM_OK;
   CK(c, cudaSetDevice(c->device));
-  const void *dp, *dn; void *dr, *dk, *dc; int rc;
-  if ((rc = stage_in(c, pos3, (size_t)n * 24, c->st_in0, &dp))) return rc;
-  if ((rc = stage_in(c, nrm3, (size_t)n * 24, c->st_in1, &dn))) return rc;
-  if ((rc = stage_out(c, rgb3, (size_t)n * 24, c->st_out0, &dr))) return rc;
-  if ((rc = stage_out(c, r2k, (size_t)n * 8, c->st_out1, &dk))) return rc;
-  if ((rc = stage_out(c, counts, (size_t)n * 4, c->st_out2, &dc))) return rc;
-  if ((rc = launch_gather_knn(c, (const double*)dp, (const double*)dn, n, k, filter, (double*)dr, (double*)dk, (uint32_t*)dc))) return rc;
-  if ((rc = finish_out(c, rgb3, (size_t)n * 24, dr))) return rc;
-  if ((rc = finish_out(c, r2k, (size_t)n * 8, dk))) return rc;
-  if ((rc = finish_out(c, counts, (size_t)n * 4, dc))) return rc;
+  const void *dp, *dn; void *dr, *dk, *dc;
+  RC(stage_in(c, pos3, (size_t)n * 24, c->st_in0, &dp));
+  RC(stage_in(c, nrm3, (size_t)n * 24, c->st_in1, &dn));
+  RC(stage_out(c, rgb3, (size_t)n * 24, c->st_out0, &dr));
+  RC(stage_out(c, r2k, (size_t)n * 8, c->st_out1, &dk));
+  RC(stage_out(c, counts, (size_t)n * 4, c->st_out2, &dc));
+  RC(launch_gather_knn(c, (const double*)dp, (const double*)dn, n, k, filter, (double*)dr, (double*)dk, (uint32_t*)dc));
+  RC(finish_out(c, rgb3, (size_t)n * 24, dr));
+  RC(finish_out(c, r2k, (size_t)n * 8, dk));
+  RC(finish_out(c, counts, (size_t)n * 4, dc));
   CK(c, cudaStreamSynchronize(c->stream));
   return PPM_OK;
 }
@@ -1015,14 +1414,12 @@ int ppm_direct_light(ppm_ctx* c, const double* pos3, const double* nrm3, int64_t
   if (n < 0 || (n > 0 && (!pos3 || !nrm3 || !rgb3))) return fail(c, PPM_ERR_ARG, "null argument");
   if (n == 0) return PPM_OK;
   CK(c, cudaSetDevice(c->device));
-  const void *dp, *dn; void* dr; int rc;
-  if ((rc = stage_in(c, pos3, (size_t)n * 24, c->st_in0, &dp))) return rc;
-  if ((rc = stage_in(c, nrm3, (size_t)n * 24, c->st_in1, &dn))) return rc;
-  if ((rc = stage_out(c, rgb3, (size_t)n * 24, c->st_out0, &dr))) return rc;
-  const unsigned long long* masks = nullptr;
-  if ((rc = launch_dl_classify(c, c->stream, (const double*)dp, n, &masks))) return rc;
-  if ((rc = launch_direct_light(c, c->stream, (const double*)dp, (const double*)dn, n, (double*)dr, masks))) return rc;
-  if ((rc = finish_out(c, rgb3, (size_t)n * 24, dr))) return rc;
+  const void *dp, *dn; void* dr;
+  RC(stage_in(c, pos3, (size_t)n * 24, c->st_in0, &dp));
+  RC(stage_in(c, nrm3, (size_t)n * 24, c->st_in1, &dn));
+  RC(stage_out(c, rgb3, (size_t)n * 24, c->st_out0, &dr));
+  RC(probe_direct_light(c, (const double*)dp, (const double*)dn, n, (double*)dr));
+  RC(finish_out(c, rgb3, (size_t)n * 24, dr));
   CK(c, cudaStreamSynchronize(c->stream));
   return PPM_OK;
 }
@@ -1033,11 +1430,11 @@ int ppm_generate_rays(ppm_ctx* c, uint64_t seed, uint32_t pass, double* rays6) {
   if (!rays6) return fail(c, PPM_ERR_ARG, "null output");
   CK(c, cudaSetDevice(c->device));
   int64_t n = (int64_t)c->cam.xreso * c->cam.yreso;
-  void* d; int rc;
-  if ((rc = stage_out(c, rays6, (size_t)n * 48, c->st_out0, &d))) return rc;
+  void* d;
+  RC(stage_out(c, rays6, (size_t)n * 48, c->st_out0, &d));
   k_gen_rays<<<nblk(n, 128), 128, 0, c->stream>>>(c->cam, seed, pass, n, (double*)d);
   KCHECK(c);
-  if ((rc = finish_out(c, rays6, (size_t)n * 48, d))) return rc;
+  RC(finish_out(c, rays6, (size_t)n * 48, d));
   CK(c, cudaStreamSynchronize(c->stream));
   return PPM_OK;
 }
@@ -1048,11 +1445,11 @@ int ppm_trace_rays_classic(ppm_ctx* c, const double* rays6, int64_t n, int64_t f
   if (n < 0 || first_pixel < 0 || (n > 0 && (!rays6 || !rgb3))) return fail(c, PPM_ERR_ARG, "null argument");
   if (n == 0) return PPM_OK;
   CK(c, cudaSetDevice(c->device));
-  const void* dr; void* dout; int rc;
-  if ((rc = stage_in(c, rays6, (size_t)n * 48, c->st_in0, &dr))) return rc;
-  if ((rc = stage_out(c, rgb3, (size_t)n * 24, c->st_out0, &dout))) return rc;
-  if ((rc = do_trace_rays(c, (const double*)dr, n, first_pixel, seed, pass, 1, (double*)dout, nullptr, 1))) return rc;
-  if ((rc = finish_out(c, rgb3, (size_t)n * 24, dout))) return rc;
+  const void* dr; void* dout;
+  RC(stage_in(c, rays6, (size_t)n * 48, c->st_in0, &dr));
+  RC(stage_out(c, rgb3, (size_t)n * 24, c->st_out0, &dout));
+  RC(do_trace_rays(c, (const double*)dr, n, first_pixel, seed, pass, 1, (double*)dout, 1));
+  RC(finish_out(c, rgb3, (size_t)n * 24, dout));
   CK(c, cudaStreamSynchronize(c->stream));
   return PPM_OK;
 }
@@ -1064,167 +1461,47 @@ int ppm_trace_rays(ppm_ctx* c, const double* rays6, int64_t n, int64_t first_pix
   if (n < 0 || first_pixel < 0 || (n > 0 && (!rays6 || !rgb3))) return fail(c, PPM_ERR_ARG, "null argument");
   if (n == 0) return PPM_OK;
   CK(c, cudaSetDevice(c->device));
-  const void* dr; void* dout; int rc;
-  if ((rc = stage_in(c, rays6, (size_t)n * 48, c->st_in0, &dr))) return rc;
-  if ((rc = stage_out(c, rgb3, (size_t)n * 24, c->st_out0, &dout))) return rc;
-  if ((rc = do_trace_rays(c, (const double*)dr, n, first_pixel, seed, pass, uc, (double*)dout, nullptr))) return rc;
-  if ((rc = finish_out(c, rgb3, (size_t)n * 24, dout))) return rc;
+  const void* dr; void* dout;
+  // the eye-path buffers must not alias the staging of the rays / the output
+  RC(stage_in(c, rays6, (size_t)n * 48, c->st_in1, &dr));
+  RC(stage_out(c, rgb3, (size_t)n * 24, c->st_out4, &dout));
+  RC(do_trace_rays(c, (const double*)dr, n, first_pixel, seed, pass, uc, (double*)dout, 0));
+  RC(finish_out(c, rgb3, (size_t)n * 24, dout));
   CK(c, cudaStreamSynchronize(c->stream));
-  return PPM_OK;
-}
-
-static int ensure_accum(ppm_ctx* c) {
-  uint64_t npix = (uint64_t)c->cam.xreso * (uint64_t)c->cam.yreso;
-  if (c->accum_pixels == npix && c->accum.p) return PPM_OK;
-  // sum image and pass counter live in ONE allocation so a single reduce covers both
-  CK(c, c->accum.ensure((size_t)(npix * 3 + 1) * 8));
-  CK(c, cudaMemsetAsync(c->accum.p, 0, (size_t)(npix * 3 + 1) * 8, c->stream));
-  c->accum_pixels = npix;
   return PPM_OK;
 }
 
 int ppm_render_pass(ppm_ctx* c, uint64_t seed, uint32_t pass, int64_t nphoton, double radius2, int uc) {
   if (!c) return PPM_ERR_ARG;
-  if (!c->have_scene || c->scene.nlights == 0) return fail(c, PPM_ERR_STATE, "scene with lights not set");
-  if (!c->have_camera) return fail(c, PPM_ERR_STATE, "camera not set");
-  if (nphoton <= 0 || !(radius2 > 0.0)) return fail(c, PPM_ERR_ARG, "nphoton and radius2 must be positive");
-  CK(c, cudaSetDevice(c->device));
-  int rc;
-  double power;
-  int64_t ns[PPM_MAX_LIGHTS];
-  if ((rc = ppm_photon_budget(c->scene.lights, c->scene.nlights, nphoton, &power, ns))) return fail(c, rc, "photon budget");
-  if ((rc = ensure_accum(c))) return rc;
-  const int64_t npix = (int64_t)c->cam.xreso * c->cam.yreso;
-  CK(c, c->pass_img.ensure((size_t)npix * 24));
-  const uint64_t l0 = c->launches;
-  typedef ppm_ctx E;
-  c->timed = true;
-  // photon branch on the main stream (async), eye branch on stream2, joined before the gather
-  cudaEventRecord(c->ev[E::EV_A0], c->stream);
-  CK(c, cudaStreamWaitEvent(c->stream2, c->ev[E::EV_A0], 0));
-  uint64_t cap = 0;
-  uint32_t nn = 0;
-  rc = trace_photons_launch(c, seed, pass, uc, ns, &cap);
-  cudaEventRecord(c->ev[E::EV_A1], c->stream);
-  if (!rc) rc = eye_front(c, c->stream2, c->cub_tmp2, nullptr, npix, 0, seed, pass, uc, &nn, 0, /*defer_direct=*/uc != 0);
-  if (!rc) rc = trace_photons_finish(c, cap, power);
-  if (!rc) rc = do_map_build(c, radius2);
-  cudaEventRecord(c->ev[E::EV_A2], c->stream);
-  if (!rc) {
-    cudaStreamWaitEvent(c->stream, c->ev[E::EV_B1], 0);      // node list ready
-    rc = eye_gather(c, nn, uc);                               // k_gather runs concurrently with k_direct_light (stream2)
-  }
-  if (!rc) {
-    cudaStreamWaitEvent(c->stream, c->ev[E::EV_B2], 0);      // direct light done
-    if (c->timed) cudaEventRecord(c->ev[E::EV_A7], c->stream);
-    rc = eye_combine(c, npix, 0, uc, c->pass_img.as<double>(), c->accum.as<double>());
-  }
-  c->timed = false;
-  if (rc) { cudaStreamSynchronize(c->stream2); cudaStreamSynchronize(c->stream); return rc; }
-  k_bump<<<1, 1, 0, c->stream>>>(c->accum.as<double>() + (size_t)npix * 3);
-  KCHECK(c);
-  cudaEventRecord(c->ev[E::EV_A6], c->stream);
-  unsigned long long st[2];
-  CK(c, cudaMemcpyAsync(st, c->stats.p, 16, cudaMemcpyDeviceToHost, c->stream));
-  CK(c, cudaStreamSynchronize(c->stream));
-  auto el = [&](int a, int b) { float f = 0.f; cudaEventElapsedTime(&f, c->ev[a], c->ev[b]); return (double)f; };
-  c->ms[0] = el(E::EV_A0, E::EV_A1);                 // photon trace
-  c->ms[1] = el(E::EV_A1, E::EV_A2);                 // map build (includes waiting for host readbacks)
-  c->ms[2] = el(E::EV_B0, E::EV_B1);                 // eye expand (stream2, concurrent with the photon branch)
-  c->ms[3] = el(E::EV_B3, E::EV_B2);                 // direct light (stream2)
-  c->ms[4] = el(E::EV_A3, E::EV_A5);                 // gather: query sort + kernel
-  c->ms[5] = el(E::EV_A7, E::EV_A6);                 // combine + accumulate
-  c->ms[6] = el(E::EV_A0, E::EV_A6);                 // whole pass
-  c->ms[7] = nn ? el(E::EV_A4, E::EV_A5) : 0.0;      // k_gather alone
-  if (std::getenv("PPM_TRACE"))
-    std::fprintf(stderr, "[ppm timeline ms since A0] A1=%.3f A2=%.3f B0=%.3f B1=%.3f B2=%.3f A3=%.3f A4=%.3f A5=%.3f A7=%.3f A6=%.3f\n",
-                 el(E::EV_A0, E::EV_A1), el(E::EV_A0, E::EV_A2), el(E::EV_A0, E::EV_B0), el(E::EV_A0, E::EV_B1), el(E::EV_A0, E::EV_B2),
-                 el(E::EV_A0, E::EV_A3), nn ? el(E::EV_A0, E::EV_A4) : 0.0, el(E::EV_A0, E::EV_A5), el(E::EV_A0, E::EV_A7), el(E::EV_A0, E::EV_A6));
-  int64_t emitted = 0;
-  for (int i = 0; i < c->scene.nlights; ++i) emitted += ns[i];
-  c->counters[0] = (uint64_t)emitted; c->counters[1] = c->n_rec; c->counters[2] = st[0];
-  c->counters[4] = st[1]; c->counters[5] = c->launches - l0;
-  return PPM_OK;
+  return render_batch(c, seed, pass, 1, 1, nphoton, &radius2, uc, 1);
 }
 
-// A batch of passes with cross-pass overlap.  Passes are independent, and within one pass the
-// FP64-bound kernels (direct light, gather) and the latency-bound ones (photon tracing, eye-path
-// expansion, map build) cannot fill the GPU together.  Two lanes -- this context and an internal
-// twin on the same GPU, each with its own streams and buffers, each driven by its own host
-// thread -- render alternating passes so that different phases of two passes co-schedule.  The
-// twin's accumulator is merged afterwards, so ppm_accum_read / ppm_image_mean see every pass.
+// A batch of passes with cross-pass overlap.  Passes are independent, and within one pass the FP64-bound kernels
+// (direct light, gather) and the latency-bound ones (photon tracing, eye-path expansion, map build) cannot fill the
+// GPU together.  Lanes -- this context and internal twins on the same GPU, each with its own streams, buffers and
+// pass graph -- render alternating passes so that different phases of different passes co-schedule.  One host thread
+// launches everything; nothing waits for the host until the batch ends.  The twins' accumulators are merged
+// afterwards, so ppm_accum_read / ppm_image_mean see every pass.
 int ppm_render_passes(ppm_ctx* c, uint64_t seed, uint32_t first_pass, uint32_t pass_stride, int32_t npass, int64_t nphoton,
                       const double* radius2, int uc) {
   if (!c) return PPM_ERR_ARG;
   if (npass < 0 || (npass > 0 && !radius2)) return fail(c, PPM_ERR_ARG, "bad pass batch");
   if (npass == 0) return PPM_OK;
   if (!c->have_scene || !c->have_camera) return fail(c, PPM_ERR_STATE, "scene and camera must be set");
-  // lanes: this context plus (lanes - 1) internal twins on the same GPU; PPM_LANES overrides the default
-  int lanes = PPM_DEFAULT_LANES;
-  if (const char* e = std::getenv("PPM_LANES")) lanes = std::atoi(e);
-  lanes = std::max(1, std::min(lanes, (int)PPM_MAX_LANES));
-  lanes = std::min<int>(lanes, npass);
-  double ms_sum[8] = {0}; uint64_t ct_sum[8] = {0};
-  if (lanes == 1) {
-    for (int32_t i = 0; i < npass; ++i) {
-      int rc = ppm_render_pass(c, seed, first_pass + (uint32_t)i * pass_stride, nphoton, radius2[i], uc);
-      if (rc) return rc;
-      for (int k = 0; k < 8; ++k) { ms_sum[k] += c->ms[k]; ct_sum[k] += c->counters[k]; }
-    }
-  } else {
-    std::vector<ppm_ctx*> lane(lanes, nullptr);
-    lane[0] = c;
-    for (int j = 1; j < lanes; ++j) {
-      if ((int)c->twins.size() < j) {
-        ppm_ctx* t = nullptr;
-        int rc = ppm_create(c->device, &t);
-        if (rc) return fail(c, rc, "cannot create another lane");
-        c->twins.push_back(t);
-      }
-      ppm_ctx* t = c->twins[j - 1];
-      t->scene = c->scene; t->cam = c->cam; t->have_camera = true;
-      { int rc = upload_cull(t); if (rc) return fail(c, rc, "lane: " + t->err); }
-      t->have_scene = true;
-      lane[j] = t;
-    }
-    std::vector<int> rcs(lanes, PPM_OK);
-    std::vector<std::array<double, 8>> lms(lanes);
-    std::vector<std::array<uint64_t, 8>> lct(lanes);
-    auto run_lane = [&](int j) {
-      ppm_ctx* x = lane[j];
-      cudaSetDevice(x->device);
-      lms[j].fill(0.0); lct[j].fill(0);
-      for (int32_t i = j; i < npass; i += lanes) {
-        rcs[j] = ppm_render_pass(x, seed, first_pass + (uint32_t)i * pass_stride, nphoton, radius2[i], uc);
-        if (rcs[j]) return;
-        for (int k = 0; k < 8; ++k) { lms[j][k] += x->ms[k]; lct[j][k] += x->counters[k]; }
-      }
-    };
-    std::vector<std::thread> workers;
-    for (int j = 1; j < lanes; ++j) workers.emplace_back(run_lane, j);
-    run_lane(0);
-    for (auto& w : workers) w.join();
-    if (rcs[0]) return rcs[0];
-    for (int j = 1; j < lanes; ++j)
-      if (rcs[j]) return fail(c, rcs[j], std::string("lane: ") + lane[j]->err);
-    for (int j = 0; j < lanes; ++j)
-      for (int k = 0; k < 8; ++k) { ms_sum[k] += lms[j][k]; ct_sum[k] += lct[j][k]; }
-    // merge the twins' accumulators (and pass counters) into ours; last pass image follows the last pass
-    CK(c, cudaSetDevice(c->device));
+  int rc = render_batch(c, seed, first_pass, pass_stride, npass, nphoton, radius2, uc, c->opt_lanes);
+  if (rc) {
+    // a failed batch leaves no half-summed twin behind: fold whatever the lanes accumulated into the parent
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    cudaGetLastError();
     const int64_t nacc = (int64_t)c->accum_pixels * 3 + 1;
-    for (int j = 1; j < lanes; ++j) {
-      CK(c, cudaStreamSynchronize(lane[j]->stream));
-      k_accum_merge<<<nblk(nacc, 256), 256, 0, c->stream>>>(c->accum.as<double>(), lane[j]->accum.as<double>(), nacc);
-      KCHECK(c);
-    }
-    const int last_lane = (npass - 1) % lanes;
-    if (last_lane != 0)
-      CK(c, cudaMemcpyAsync(c->pass_img.p, lane[last_lane]->pass_img.p, (size_t)c->accum_pixels * 24, cudaMemcpyDeviceToDevice, c->stream));
-    CK(c, cudaStreamSynchronize(c->stream));
+    for (ppm_ctx* t : c->twins)
+      if (t->accum.p && t->accum_pixels == c->accum_pixels && c->accum.p)
+        k_accum_merge<<<nblk(nacc, 256), 256, 0, c->stream>>>(c->accum.as<double>(), t->accum.as<double>(), nacc);
+    cudaStreamSynchronize(c->stream);
+    cudaGetLastError();
   }
-  std::memcpy(c->ms, ms_sum, sizeof ms_sum);          // batch totals (sum over the passes of all lanes)
-  std::memcpy(c->counters, ct_sum, sizeof ct_sum);
-  return PPM_OK;
+  return rc;
 }
 
 int ppm_last_pass_stats(ppm_ctx* c, double ms[8], uint64_t counters[8]) {
@@ -1250,8 +1527,11 @@ int ppm_pass_image_read(ppm_ctx* c, double* rgb3) {
 int ppm_accum_reset(ppm_ctx* c) {
   if (!c) return PPM_ERR_ARG;
   CK(c, cudaSetDevice(c->device));
-  c->accum_pixels = 0;
-  if (c->have_camera) return ensure_accum(c);
+  for (ppm_ctx* t : c->twins)                           // the lanes' partial sums go too
+    if (t->accum.p && t->accum_pixels) CK(c, cudaMemsetAsync(t->accum.p, 0, (size_t)(t->accum_pixels * 3 + 1) * 8, c->stream));
+  if (c->accum.p && c->accum_pixels) CK(c, cudaMemsetAsync(c->accum.p, 0, (size_t)(c->accum_pixels * 3 + 1) * 8, c->stream));
+  if (c->have_camera) RC(ensure_accum(c));
+  CK(c, cudaStreamSynchronize(c->stream));
   return PPM_OK;
 }
 
@@ -1259,7 +1539,7 @@ int ppm_accum_read(ppm_ctx* c, double* rgb3, uint32_t* n_pass) {
   if (!c) return PPM_ERR_ARG;
   if (!c->accum.p || !c->accum_pixels) return fail(c, PPM_ERR_STATE, "no accumulator yet");
   CK(c, cudaSetDevice(c->device));
-  if (rgb3) { int rc = copy_out(c, rgb3, c->accum.p, (size_t)c->accum_pixels * 24); if (rc) return rc; }
+  if (rgb3) RC(copy_out(c, rgb3, c->accum.p, (size_t)c->accum_pixels * 24));
   if (n_pass) {
     double np = 0.0;
     CK(c, cudaMemcpyAsync(&np, c->accum.as<double>() + c->accum_pixels * 3, 8, cudaMemcpyDeviceToHost, c->stream));
@@ -1273,8 +1553,7 @@ int ppm_accum_device(ppm_ctx* c, void** sum_dev, void** npass_dev, uint64_t* n_d
   if (!c) return PPM_ERR_ARG;
   CK(c, cudaSetDevice(c->device));
   if (!c->have_camera) return fail(c, PPM_ERR_STATE, "camera not set");
-  int rc = ensure_accum(c);
-  if (rc) return rc;
+  RC(ensure_accum(c));
   CK(c, cudaStreamSynchronize(c->stream));
   if (sum_dev) *sum_dev = c->accum.p;
   if (npass_dev) *npass_dev = c->accum.as<double>() + c->accum_pixels * 3;
@@ -1287,11 +1566,66 @@ int ppm_image_mean(ppm_ctx* c, double* rgb3) {
   if (!c->accum.p || !c->accum_pixels) return fail(c, PPM_ERR_STATE, "no accumulator yet");
   CK(c, cudaSetDevice(c->device));
   int64_t n = (int64_t)c->accum_pixels * 3;
-  void* d; int rc;
-  if ((rc = stage_out(c, rgb3, (size_t)n * 8, c->st_out0, &d))) return rc;
+  double np = 0.0;
+  CK(c, cudaMemcpyAsync(&np, c->accum.as<double>() + n, 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(c, cudaStreamSynchronize(c->stream));
+  if (!(np > 0.0)) return fail(c, PPM_ERR_STATE, "no pass has been accumulated");
+  void* d;
+  RC(stage_out(c, rgb3, (size_t)n * 8, c->st_out0, &d));
   k_scale<<<nblk(n, 256), 256, 0, c->stream>>>(c->accum.as<double>(), c->accum.as<double>() + n, n, (double*)d);
   KCHECK(c);
-  if ((rc = finish_out(c, rgb3, (size_t)n * 8, d))) return rc;
+  RC(finish_out(c, rgb3, (size_t)n * 8, d));
+  CK(c, cudaStreamSynchronize(c->stream));
+  return PPM_OK;
+}
+
+// ---- multi-GPU frame: one NCCL sum-reduce of [3*W*H sums | pass count] (util/averager2.rb:49-62,86) --------------------
+int ppm_comm_unique_id(void* id128) {
+  if (!id128) return PPM_ERR_ARG;
+  NcclApi* a = nccl_api();
+  if (!a->h) return PPM_ERR_STATE;
+  NcclUid id;
+  std::memset(&id, 0, sizeof id);
+  if (a->GetUniqueId(&id) != 0) return PPM_ERR_CUDA;
+  std::memcpy(id128, &id, sizeof id);
+  return PPM_OK;
+}
+int ppm_comm_init(ppm_ctx* c, int32_t nranks, int32_t rank, const void* id128) {
+  if (!c || !id128 || nranks <= 0 || rank < 0 || rank >= nranks) return c ? fail(c, PPM_ERR_ARG, "bad communicator arguments") : PPM_ERR_ARG;
+  NcclApi* a = nccl_api();
+  if (!a->h) return fail(c, PPM_ERR_STATE, a->why);
+  CK(c, cudaSetDevice(c->device));
+  if (c->comm) { a->CommDestroy(c->comm); c->comm = nullptr; }
+  NcclUid id;
+  std::memcpy(&id, id128, sizeof id);
+  int r = a->CommInitRank(&c->comm, nranks, id, rank);
+  if (r != 0) { c->comm = nullptr; return fail(c, PPM_ERR_CUDA, "ncclCommInitRank: " + nccl_err(a, r)); }
+  return PPM_OK;
+}
+int ppm_comm_destroy(ppm_ctx* c) {
+  if (!c) return PPM_ERR_ARG;
+  if (c->comm) {
+    NcclApi* a = nccl_api();
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    if (a->h) a->CommDestroy(c->comm);
+    c->comm = nullptr;
+  }
+  return PPM_OK;
+}
+int ppm_accum_reduce(ppm_ctx* c, void* nccl_comm, int32_t root) {
+  if (!c) return PPM_ERR_ARG;
+  NcclApi* a = nccl_api();
+  if (!a->h) return fail(c, PPM_ERR_STATE, a->why);
+  void* comm = nccl_comm ? nccl_comm : c->comm;
+  if (!comm) return fail(c, PPM_ERR_STATE, "no communicator: call ppm_comm_init or pass an ncclComm_t");
+  if (!c->have_camera) return fail(c, PPM_ERR_STATE, "camera not set");
+  CK(c, cudaSetDevice(c->device));
+  RC(ensure_accum(c));
+  const size_t n = (size_t)c->accum_pixels * 3 + 1;
+  int r = root < 0 ? a->AllReduce(c->accum.p, c->accum.p, n, kNcclFloat64, kNcclSum, comm, c->stream)
+                   : a->Reduce(c->accum.p, c->accum.p, n, kNcclFloat64, kNcclSum, root, comm, c->stream);
+  if (r != 0) return fail(c, PPM_ERR_CUDA, "nccl reduce: " + nccl_err(a, r));
   CK(c, cudaStreamSynchronize(c->stream));
   return PPM_OK;
 }

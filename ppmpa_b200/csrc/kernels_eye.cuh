@@ -4,6 +4,7 @@
 #define PPM_KERNELS_EYE_CUH_
 
 #include "dev_core.cuh"
+#include "pass_state.cuh"
 
 // ---- camera ---------------------------------------------------------------------
 __device__ __forceinline__ void camera_ray(const ppm_camera& cam, int64_t pix, uint64_t seed, uint32_t pass, D3& pos, D3& dir) {
@@ -56,11 +57,15 @@ struct EyeStack {
 #endif
 __global__ void __launch_bounds__(128, PPM_EYE_MINB)
 k_eye_expand(const __grid_constant__ DevScene sc, const __grid_constant__ ppm_camera cam, const double* __restrict__ rays6,
-             int64_t n, int64_t first_pixel, uint64_t seed, uint32_t pass, EyeNodes nodes, uint32_t cap,
-             uint32_t* __restrict__ head, double* __restrict__ emit3, unsigned long long* __restrict__ pool_counter,
-             unsigned long long* __restrict__ n_visited, int classic) {
+             int64_t n, int64_t first_pixel, PassDev* ps, EyeNodes nodes, uint32_t cap,
+             uint32_t* __restrict__ head, double* __restrict__ emit3, int classic, int stamp_slot) {
+  stamp(ps, stamp_slot);
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  const uint64_t seed = ps->seed;                       // RNG keys and the node counter live in the pass state
+  const uint32_t pass = ps->pass;
+  unsigned long long* const pool_counter = &ps->n_nodes;
+  unsigned long long* const n_visited = &ps->n_visited;
   const unsigned lane = threadIdx.x & 31u;
   const unsigned lt_mask = (1u << lane) - 1u;
   const int64_t pix = first_pixel + i;
@@ -183,6 +188,8 @@ struct CullLight {
   double corner[4][3];                              // the quad's corners in cyclic order: pos, +dir1, +dir1+dir2, +dir2
   unsigned long long coplanar;                      // polygons / parallelograms lying in that plane
   double hmin[PPM_MAX_PRIMS], hmax[PPM_MAX_PRIMS];  // planes: min / max of dist + n.corner over the quad's corners
+  double side_e;                                    // |nvec.dir1| + |nvec.dir2|: spread of nvec.(sample - p) over the 25 samples
+  double ext, ln1;                                  // |pos|_1 + |dir1|_1 + |dir2|_1 and |nvec|_1 (rounding scale of that test)
 };
 struct DevCull {
   CullPrim prim[PPM_MAX_PRIMS];
@@ -282,30 +289,47 @@ __device__ __forceinline__ unsigned long long cull_classify(const DevScene& sc, 
   return mask;
 }
 
-// One thread per node: the conservative classification above, for every area light.  masks[li * n + node] = the
+#define PPM_CULL_CERT (1ull << 63)
+// Conservative "no sample of this light can ever reach the hit test" for a node: every sample fails
+// `dot(lnv, d) < 0` (light.rs:112) or every sample has cos0 < 0 (tracer.rs:277-278).  The bands are > 1000 x the
+// rounding of the reference's own tests, so this only fires when each of the 25 reference decisions is certain.
+__device__ __forceinline__ bool light_never_tested(const ppm_light& l, const CullLight& cl, D3 p, D3 nv) {
+  const D3 lp = ld3(l.pos) - p;
+  const double p1 = fabs(p.x) + fabs(p.y) + fabs(p.z);
+  const double a0 = dot(ld3(l.nvec), lp);
+  if (a0 > 4.0 * (cl.side_e + 1e-12 * (cl.ln1 * (1.0 + cl.ext + p1)))) return true;
+  const double x = dot(nv, ld3(l.dir1)), y = dot(nv, ld3(l.dir2));
+  const double bmax = (dot(nv, lp) + fmax(0.1 * x, 0.9 * x)) + fmax(0.1 * y, 0.9 * y);
+  const double n1 = fabs(nv.x) + fabs(nv.y) + fabs(nv.z);
+  return bmax < -1e-11 * (n1 * (1.0 + cl.ext + p1));
+}
+// One thread per node: the conservative classification above, for every area light.  masks[li * cap + node] = the
 // primitives the node's shadow rays towards light li must test, bit 63 = the node has a certificate.  A separate
 // kernel so that it has its own register budget (k_direct_light is compiled for 64 registers) and can run right after
-// the eye-path expansion, concurrently with the photon branch.
-#define PPM_CULL_CERT (1ull << 63)
+// the eye-path expansion, concurrently with the photon branch.  The node count comes from the pass state.
 #ifdef PPM_CLS_MINB                                   // tuning builds (tools/build_variants.sh): 5 / 6 / 8 CTAs per SM are all slower
 __global__ void __launch_bounds__(128, PPM_CLS_MINB)
 #else
 __global__ void __launch_bounds__(128)
 #endif
-k_dl_classify(const __grid_constant__ DevScene sc, const DevCull* __restrict__ cull, const double* __restrict__ pos3, int64_t n,
-              unsigned long long* __restrict__ masks) {
+k_dl_classify(const __grid_constant__ DevScene sc, const DevCull* __restrict__ cull, PassDev* ps, uint32_t cap,
+              const double* __restrict__ pos3, const double* __restrict__ nrm3, unsigned long long* __restrict__ masks, int stamp_slot) {
+  stamp(ps, stamp_slot);
+  const unsigned long long made = ps->n_nodes;
+  const int64_t n = made > (unsigned long long)cap ? (int64_t)cap : (int64_t)made;
   const int64_t node = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (node >= n) return;
   const D3 p = ld3(pos3 + node * 3);
+  const D3 nv = ld3(nrm3 + node * 3);
   const unsigned long long all = (1ull << sc.nprims) - 1ull;       // nprims <= 63 here (bit 63 is the certificate)
   for (int li = 0; li < sc.nlights; ++li) {
     unsigned long long m = 0;
-    if (sc.lights[li].type == PPM_LIGHT_PARALLELOGRAM) {
+    if (sc.lights[li].type == PPM_LIGHT_PARALLELOGRAM && !light_never_tested(sc.lights[li], cull->light[li], p, nv)) {
       bool cert;
       m = cull_classify(sc, cull, li, p, all, cert);
       if (cert) m |= PPM_CULL_CERT;
     }
-    masks[(int64_t)li * n + node] = m;
+    masks[(int64_t)li * cap + node] = m;
   }
 }
 
@@ -314,22 +338,39 @@ __device__ __forceinline__ double ts5(unsigned i) {   // the literals 0.1, 0.3, 
 }
 // 64 registers (8 CTAs per SM): the kernel is latency bound, so occupancy beats the ~100 bytes of spills
 // (96 registers / 5 CTAs: 2.1 ms, 64 / 8: 1.35 ms on config 2).
+//
+// Arithmetic (tolerance tier, 1e-12 held by the tests).  The reference evaluates, per surviving sample i,
+//   rad += (color * (lnum / (4 pi |d_{i-1}|^2))) * cos0_i^2,   cos0_i = nvec . normalize(d_i)
+// which costs a square root, a reciprocal, a division and nine multiplications per sample.  Here
+//   rad = (color * lnum / (4 pi)) * sum_i (1 / |d_{i-1}|^2) * cos0_i^2,   cos0_i^2 = (nvec . d_i)^2 / |d_i|^2
+// with ONE reciprocal per sample: no square root and no normalised direction unless the node has primitives to test
+// (then the shadow ray needs the reference's exact direction, and cos0 is taken from it as the reference does).  The
+// DECISIONS stay the reference's: `dot(lnv, d) < 0` is evaluated per sample unless the node is far enough from the
+// light's plane that all 25 outcomes are certain (band > 1000 x the rounding), and the sign of nvec . d stands for
+// the sign of cos0 only when |nvec . d| is 10^7 roundings away from zero; anything closer takes the exact path.
 #ifndef PPM_DL_MINB
 #define PPM_DL_MINB 8
 #endif
 __global__ void __launch_bounds__(128, PPM_DL_MINB)
-k_direct_light(const __grid_constant__ DevScene sc, const unsigned long long* __restrict__ masks, const uint32_t* __restrict__ order,
-               const double* __restrict__ pos3, const double* __restrict__ nrm3, int64_t n, double* __restrict__ out3,
-               unsigned long long* __restrict__ dbg) {
+k_direct_light(const __grid_constant__ DevScene sc, PassDev* ps, uint32_t cap, const unsigned long long* __restrict__ masks,
+               const uint32_t* __restrict__ order, const double* __restrict__ pos3, const double* __restrict__ nrm3,
+               double* __restrict__ out3, unsigned long long* __restrict__ dbg, int stamp_slot) {
   __shared__ double s_gp[25][3];
+  __shared__ double s_lc[3];
+  stamp(ps, stamp_slot);
+  const unsigned long long made = ps->n_nodes;
+  const int64_t n = made > (unsigned long long)cap ? (int64_t)cap : (int64_t)made;
+  if ((int64_t)blockIdx.x * blockDim.x >= n) return;     // block-uniform: grids are sized for the capacity
   const int64_t node0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = node0 < n;
-  // `order` (optional): visit the nodes in this order -- ppm_render_pass passes the cell-sorted query order of the
-  // gather, so the 32 nodes of a warp lie in the same or adjacent grid cells and have (almost) the same culling
-  // mask: the warp-wide OR then costs nothing (2.35 -> 1.6 tested primitives per node on config 2).
+  // `order` (optional): visit the nodes in this order -- a pass hands in the cell-sorted query order of the gather, so
+  // the 32 nodes of a warp lie in the same or adjacent grid cells and have (almost) the same culling mask: the
+  // warp-wide OR then costs nothing (2.35 -> 0.87 tested primitives per node on config 2).
   const int64_t slot = live ? node0 : n - 1;           // idle lanes of the last block shadow the last node (no store)
   const int64_t node = order ? (int64_t)order[slot] : slot;
   const D3 p = ld3(pos3 + node * 3), nv = ld3(nrm3 + node * 3);
+  const double p1 = fabs(p.x) + fabs(p.y) + fabs(p.z);
+  const double nn_thr = 1e-28 * dot(nv, nv);
   const unsigned long long all = sc.nprims >= 64 ? ~0ull : ((1ull << sc.nprims) - 1ull);
   const PrimMasks tmask = sc.types;
   D3 total = mk3(0.0, 0.0, 0.0);
@@ -342,58 +383,84 @@ k_direct_light(const __grid_constant__ DevScene sc, const unsigned long long* __
       const unsigned s = threadIdx.x;
       const D3 gp = (ld3(l.pos) + ts5(s / 5) * ld3(l.dir1)) + ts5(s % 5) * ld3(l.dir2);   // gen_pos, light.rs:152-154
       s_gp[s][0] = gp.x; s_gp[s][1] = gp.y; s_gp[s][2] = gp.z;
+    } else if (threadIdx.x == 32) {
+      const D3 d1 = ld3(l.dir1), d2 = ld3(l.dir2);
+      s_lc[0] = fabs(dot(lnv, d1)) + fabs(dot(lnv, d2));
+      s_lc[1] = (fabs(l.pos[0]) + fabs(l.pos[1]) + fabs(l.pos[2])) + (fabs(d1.x) + fabs(d1.y) + fabs(d1.z)) + (fabs(d2.x) + fabs(d2.y) + fabs(d2.z));
+      s_lc[2] = fabs(lnv.x) + fabs(lnv.y) + fabs(lnv.z);
     }
     __syncthreads();
-    bool cert = false;
+    bool cert = false, own_none = false;
     unsigned long long mask = all;
     if (masks) {
-      const unsigned long long own = masks[(int64_t)li * n + node];     // k_dl_classify
+      const unsigned long long own = masks[(int64_t)li * cap + node];   // k_dl_classify
       cert = (own & PPM_CULL_CERT) != 0ull;
       mask = own & ~PPM_CULL_CERT;
+      own_none = mask == 0ull;                                // a property of the node alone (the OR below is not)
       const unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)mask);
       const unsigned hi = __reduce_or_sync(0xffffffffu, (unsigned)(mask >> 32));
       mask = ((unsigned long long)hi << 32) | lo;
-      if (dbg && live) {                                      // diagnostic (PPM_DL_STATS): primitives tested per node
+      if (dbg && live) {                                      // diagnostic ("dl_stats"): primitives tested per node
         const unsigned long long o1 = own & ~PPM_CULL_CERT;
         atomicAdd(dbg, 1ull); atomicAdd(dbg + 1, (unsigned long long)__popcll(o1));
         atomicAdd(dbg + 2, (unsigned long long)__popcll(mask)); atomicAdd(dbg + 3, cert ? 1ull : 0ull);
         atomicAdd(dbg + 4 + min(__popcll(o1), 7), 1ull); atomicAdd(dbg + 12 + min(__popcll(mask), 7), 1ull);
       }
     }
-    PrimMasks pm;
-    pm.plain = mask & tmask.plain; pm.sphere = mask & tmask.sphere; pm.poly = mask & tmask.poly; pm.para = mask & tmask.para;
-    pm.nwords = tmask.nwords; pm._pad = 0;
-    const double PI4 = PPM_PI * 4.0;
-    const double lnum = 2.0 * l.flux * 0.2 * 0.2;           // 2 * flux * PARA_DIV * PARA_DIV, light.rs:142
-    D3 rad = mk3(0.0, 0.0, 0.0);
-    bool have_prev = false;
-    double dprev = 0.0;
-    for (unsigned s = 0; s < 25; ++s) {
-      const D3 gp = mk3(s_gp[s][0], s_gp[s][1], s_gp[s][2]);
-      const D3 d = gp - p;
-      if (!(dot(lnv, d) < 0.0)) continue;                   // light.rs:112
-      D3 ld;
-      if (!normalize(d, ld)) continue;                      // tracer.rs:275-276
-      const double cos0 = dot(nv, ld);
-      if (cos0 < 0.0) continue;
-      const double sq_ldist = dot(d, d);
-      D3 hp;
-      const int hit = nearest_hit_masked(sc, p, ld, pm, hp);
-      if (hit == 1) {
-        const D3 po = hp - p;
-        if (sq_ldist - dot(po, po) > 0.002) continue;
-      } else if (hit == 2 || !cert) {
-        continue;                                           // no hit counts as occluded, tracer.rs:282
-      }                                                     // hit == 0 with a certificate: nearest hit beyond the light
-      if (have_prev) {
-        const double l0 = lnum / (PI4 * dprev);
-        const double cc = cos0 * cos0;
-        rad = rad + mk3((l.color[0] * l0) * cc, (l.color[1] * l0) * cc, (l.color[2] * l0) * cc);
+    // which side of the light's plane: +1 = every sample passes `dot(lnv, d) < 0` (light.rs:112), -1 = none does,
+    // 0 = too close to the plane to say, evaluate per sample
+    const double a0 = dot(lnv, ld3(l.pos) - p);
+    const double band = s_lc[0] + 1e-12 * (s_lc[2] * (1.0 + s_lc[1] + p1));
+    const int side = a0 < -band ? 1 : (a0 > band ? -1 : 0);
+    if (side >= 0) {
+      PrimMasks pm;
+      pm.plain = mask & tmask.plain; pm.sphere = mask & tmask.sphere; pm.poly = mask & tmask.poly; pm.para = mask & tmask.para;
+      pm.nwords = tmask.nwords; pm._pad = 0;
+      const bool need_ld = mask != 0ull;                      // warp-uniform (masks are OR-ed across the warp)
+      const double C = (2.0 * l.flux * 0.2 * 0.2) / (PPM_PI * 4.0);   // 2 * flux * PARA_DIV^2 / (4 pi), light.rs:142
+      double acc = 0.0, inv_prev = 0.0;
+      bool have_prev = false;
+      for (unsigned s = 0; s < 25; ++s) {
+        const D3 gp = mk3(s_gp[s][0], s_gp[s][1], s_gp[s][2]);
+        const D3 d = gp - p;
+        if (side == 0 && !(dot(lnv, d) < 0.0)) continue;      // light.rs:112
+        const double dd = dot(d, d);                          // sq_ldist
+        if (dd == 0.0) continue;                              // normalize(d) is None exactly when |d|^2 == 0, tracer.rs:275-276
+        const double inv = 1.0 / dd;
+        const double b = dot(nv, d);
+        double cc;
+        D3 ld = d;
+        // Which arithmetic a node gets depends on the node alone (own_none), never on the warp it sits in, so the
+        // result is reproducible whatever order the nodes come in; the warp-uniform need_ld only decides whether the
+        // normalised direction has to exist for the hit test.
+        const bool lean = own_none && b * b > nn_thr * dd;
+        if (need_ld || !lean) normalize(d, ld);
+        if (lean) {
+          if (b < 0.0) continue;
+          cc = (b * b) * inv;
+        } else {
+          const double cos0 = dot(nv, ld);
+          if (cos0 < 0.0) continue;
+          cc = cos0 * cos0;
+        }
+        if (need_ld) {
+          D3 hp;
+          const int hit = nearest_hit_masked(sc, p, ld, pm, hp);
+          if (hit == 1) {
+            const D3 po = hp - p;
+            if (dd - dot(po, po) > 0.002) continue;
+          } else if (hit == 2 || !cert) {
+            continue;                                         // no hit counts as occluded, tracer.rs:282
+          }                                                   // hit == 0 with a certificate: nearest hit beyond the light
+        } else if (!cert) {
+          continue;
+        }
+        if (have_prev) acc = acc + inv_prev * cc;             // the off-by-one pairing [0, L(d0), ...] . [c0, c1, ...]
+        have_prev = true;
+        inv_prev = inv;
       }
-      have_prev = true;
-      dprev = sq_ldist;
+      total = total + mk3((l.color[0] * C) * acc, (l.color[1] * C) * acc, (l.color[2] * C) * acc);
     }
-    total = total + rad;
   }
   if (live) st3(out3 + node * 3, total);
 }
@@ -401,10 +468,12 @@ k_direct_light(const __grid_constant__ DevScene sc, const unsigned long long* __
 // ---- combine + accumulate ------------------------------------------------------------
 // pixel = sum_nodes W(.)kd (.) (direct + photon estimate) + sum emittance terms;
 // then the pass image is added to the running sum (util/averager2.rb:49-62).
-__global__ void k_combine(const uint32_t* __restrict__ head, const uint32_t* __restrict__ prev, const double* __restrict__ w3,
+__global__ void k_combine(PassDev* ps, const uint32_t* __restrict__ head, const uint32_t* __restrict__ prev, const double* __restrict__ w3,
                           const double* __restrict__ direct3, const double* __restrict__ photon3,
                           const double* __restrict__ emit3, int64_t n, double* __restrict__ out3,
-                          double* __restrict__ accum3, int64_t accum_first, D3 ambient) {
+                          double* __restrict__ accum3, int64_t accum_first, D3 ambient, int stamp_slot) {
+  stamp(ps, stamp_slot);
+  if (accum3 && ps->status != 0u) accum3 = nullptr;      // a pass that overflowed a buffer does not count: the host re-renders it
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   D3 rad = ld3(emit3 + i * 3);
@@ -424,7 +493,6 @@ __global__ void k_combine(const uint32_t* __restrict__ head, const uint32_t* __r
     a[0] += rad.x; a[1] += rad.y; a[2] += rad.z;
   }
 }
-__global__ void k_bump(double* npass) { npass[0] += 1.0; }
 // acc += other; other = 0   (merging the twin lane's accumulator, incl. the pass counter)
 __global__ void k_accum_merge(double* __restrict__ acc, double* __restrict__ other, int64_t n) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -20,18 +20,8 @@ __device__ __forceinline__ double filter_gauss(double d, double rmax) {
   return e_r > E_BETA ? 0.0 : ALPHA * (1.0 - e_r / E_BETA) + CORR;
 }
 
-// Queries are keyed by their (padded) grid cell and radix sorted, so that the 32
-// lanes of a warp hold queries of the same cell (or of a few cells).
-__global__ void k_query_key(Grid g, const double* __restrict__ qpos3, int64_t n, uint32_t* __restrict__ keys,
-                            uint32_t* __restrict__ vals) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  int cx = cell_coord(g, qpos3[i * 3], 0), cy = cell_coord(g, qpos3[i * 3 + 1], 1), cz = cell_coord(g, qpos3[i * 3 + 2], 2);
-  uint32_t key = ((uint32_t)cz * (uint32_t)g.ny + (uint32_t)cy) * (uint32_t)g.nx + (uint32_t)cx;
-  keys[i] = key;
-  vals[i] = (uint32_t)i;
-}
-
+// Queries are ordered by grid cell (counting sort, kernels_map.cuh), so that the 32 lanes of a warp hold
+// queries of the same cell (or of a few cells).
 // v2: warp-cooperative gather.  A warp owns 32 cell-sorted queries (one per lane).
 // For each distinct cell among them, the photons of the 3x3x3 neighbourhood -- nine
 // x-contiguous runs of the sorted map (cell edge >= r) -- form one virtual candidate stream;
@@ -60,7 +50,7 @@ struct HeavyGroup { uint32_t s_base, grp, ck, klast, nparts, part0, done, _pad; 
 struct HeavyPart { uint32_t group; };
 struct HeavyPartial { double rgb[3][32]; uint32_t cnt[32]; };                      // one part's partial sums, one column per lane
 struct HeavyList {
-  unsigned int* ctr;        // [0] reservation counter, [1] ticket of k_gather_heavy, [2] groups, [3] parts published
+  unsigned int* ctr;        // = PassDev::heavy: [0] reservation counter, [1] ticket of k_gather_heavy, [2] groups, [3] parts published
   HeavyGroup* groups;       // [cap_parts / 2]
   HeavyPart* parts;         // [cap_parts]
   HeavyPartial* partials;   // [cap_parts]
@@ -69,7 +59,7 @@ struct HeavyList {
 
 // lanes 0..8 look up the nine runs of the group's neighbourhood; returns the length of the candidate stream and
 // leaves, per run, its cumulative end (sEnd) and start minus exclusive prefix (sOff) in the warp's shared arrays
-__device__ __forceinline__ uint32_t gather_group_runs(const Grid& g, const uint32_t* __restrict__ cell_start, uint32_t ck, uint32_t klast,
+__device__ __forceinline__ uint32_t gather_group_runs(const Grid& g, const CellIndex& ix, uint32_t ck, uint32_t klast,
                                                       int lane, uint32_t* sEnd, uint32_t* sOff) {
   constexpr int REACH = 1, W = 2 * REACH + 1, ROWS = W * W;
   const unsigned FULL = 0xffffffffu;
@@ -81,8 +71,8 @@ __device__ __forceinline__ uint32_t gather_group_runs(const Grid& g, const uint3
     const int z = cz + lane / W - REACH, y = cy + lane % W - REACH;
     if (z >= 0 && z < g.nz && y >= 0 && y < g.ny) {
       const uint32_t row = ((uint32_t)z * (uint32_t)g.ny + (uint32_t)y) * (uint32_t)g.nx;
-      rbeg = cell_start[row + x0];
-      rlen = cell_start[row + x1 + 1] - rbeg;
+      rbeg = cell_begin(ix, row + (uint32_t)x0);
+      rlen = cell_begin(ix, row + (uint32_t)x1 + 1u) - rbeg;
     }
   }
   uint32_t pre = rlen;                               // inclusive prefix of the run lengths
@@ -99,11 +89,13 @@ __device__ __forceinline__ uint32_t gather_group_runs(const Grid& g, const uint3
   return total;
 }
 // chunks base = first, first + stride, ... of the candidate stream: stage 32 candidates, test them against the lane's query
+// returns the number of candidates staged (warp-uniform)
 template <int FILTER, int MODE>
-__device__ __forceinline__ void gather_chunks(const MapSoA& m, uint32_t total, uint32_t first, uint32_t stride, int lane, bool act,
+__device__ __forceinline__ uint32_t gather_chunks(const MapSoA& m, uint32_t total, uint32_t first, uint32_t stride, int lane, bool act,
                                               const uint32_t* sEnd, const uint32_t* sOff, double2 (*sP)[2], double2 (*sD)[2],
                                               double qx, double qy, double qz, D3 nv, double r2, double power,
                                               double& rr, double& rg, double& rb, uint32_t& cnt) {
+  uint32_t staged = 0;
   for (uint32_t base = first; base < total; base += stride) {
     const uint32_t v = base + lane;
     if (v < total) {
@@ -118,6 +110,7 @@ __device__ __forceinline__ void gather_chunks(const MapSoA& m, uint32_t total, u
     }
     __syncwarp();
     const int mcount = (int)min(32u, total - base);
+    staged += (uint32_t)mcount;
     if (act) {
       for (int t = 0; t < mcount; ++t) {
         const double2 a = sP[t][0], b = sP[t][1];
@@ -139,22 +132,28 @@ __device__ __forceinline__ void gather_chunks(const MapSoA& m, uint32_t total, u
     }
     __syncwarp();
   }
+  return staged;
 }
 // MODE 0: fixed radius r2 (estimate_radiance).  MODE 1: per-query squared radius r2q[] (k-NN estimate:
 // membership, filter rmax and normaliser all use the query's own radius).  MODE 2: count only,
 // members are d2 <= r2q[] (the bisection steps of the k-NN radius search).
+// The number of queries, the grid, the radius and the photon power come from the pass state.
 template <int FILTER, int MODE>
 __global__ void __launch_bounds__(GATHER_WARPS * 32)
-k_gather(Grid g, const uint32_t* __restrict__ cell_start, MapSoA m, const uint32_t* __restrict__ qkey,
-         const uint32_t* __restrict__ qidx, const double* __restrict__ qpos3, const double* __restrict__ qnrm3, int64_t n,
-         double power, double r2_fixed, const double* __restrict__ r2q, double* __restrict__ rgb3, uint32_t* __restrict__ counts,
-         unsigned long long* __restrict__ sum_k, HeavyList hl) {
+k_gather(PassDev* ps, CellIndex ix, MapSoA m, const uint32_t* __restrict__ qkey,
+         const uint32_t* __restrict__ qidx, const double* __restrict__ qpos3, const double* __restrict__ qnrm3,
+         const double* __restrict__ r2q, double* __restrict__ rgb3, uint32_t* __restrict__ counts, HeavyList hl, int stamp_slot) {
   __shared__ double2 sP[GATHER_WARPS][32][2];
   __shared__ double2 sD[GATHER_WARPS][32][2];
   __shared__ uint32_t sEnd[GATHER_WARPS][32], sOff[GATHER_WARPS][32];   // per run: cumulative end, start - exclusive prefix
+  stamp(ps, stamp_slot);
   const unsigned FULL = 0xffffffffu;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t n = (int64_t)ps->n_query;
   const int64_t s_base = ((int64_t)blockIdx.x * GATHER_WARPS + warp) * 32;
+  if (s_base >= n) return;                             // whole warp beyond the query list (grids are sized for the capacity)
+  const Grid g = ps->grid;
+  const double power = ps->power, r2_fixed = ps->r2;
   const int64_t s = s_base + lane;
   const bool valid = s < n;
   const uint32_t key = valid ? qkey[s] : 0xFFFFFFFFu;
@@ -170,6 +169,7 @@ k_gather(Grid g, const uint32_t* __restrict__ cell_start, MapSoA m, const uint32
   double rr = 0.0, rg = 0.0, rb = 0.0;
   uint32_t cnt = 0;
   bool deferred = false;                               // this lane's query was handed to k_gather_heavy
+  unsigned long long tests = 0;                        // (candidates staged) x (lanes of the group): distance tests done
   const uint32_t nxp = (uint32_t)g.nx;
   unsigned pending = __ballot_sync(FULL, valid);
   while (pending) {
@@ -179,11 +179,21 @@ k_gather(Grid g, const uint32_t* __restrict__ cell_start, MapSoA m, const uint32
     // GATHER_SPAN cells to the right of the leader's cell (keys are sorted, x fastest).  They
     // share ONE candidate stream covering [cx_leader - R, cx_last + R]: a superset of every
     // lane's own neighbourhood, so the extra candidates simply fail the distance test.
-    const bool act = valid && key >= ck && key - ck <= (uint32_t)GATHER_SPAN && key / nxp == ck / nxp;
-    const unsigned grp = __ballot_sync(FULL, act);
+    bool act = valid && key >= ck && key - ck <= (uint32_t)GATHER_SPAN && key / nxp == ck / nxp;
+    unsigned grp = __ballot_sync(FULL, act);
+    uint32_t klast = __shfl_sync(FULL, key, 31 - __clz((int)grp));
+    uint32_t total = gather_group_runs(g, ix, ck, klast, lane, sEnd[warp], sOff[warp]);
+    if (hl.ctr && total > GATHER_HEAVY_MIN && klast != ck) {
+      // A heavy stream is split into parts by its length, and the parts fix the order in which a query's photons are
+      // summed.  Narrow the group to the leader's cell alone: the stream, its split and therefore every sum then
+      // depend on the query's cell only, not on which other queries happen to share the warp (bit-reproducible
+      // whatever order the counting sort left inside a cell).  The other lanes stay pending.
+      act = valid && key == ck;
+      grp = __ballot_sync(FULL, act);
+      klast = ck;
+      total = gather_group_runs(g, ix, ck, klast, lane, sEnd[warp], sOff[warp]);
+    }
     pending &= ~grp;
-    const uint32_t klast = __shfl_sync(FULL, key, 31 - __clz((int)grp));
-    const uint32_t total = gather_group_runs(g, cell_start, ck, klast, lane, sEnd[warp], sOff[warp]);
     if (hl.ctr && total > GATHER_HEAVY_MIN) {
       const uint32_t nparts = min(GATHER_HEAVY_MAXPARTS, (total + GATHER_HEAVY_MIN - 1u) / GATHER_HEAVY_MIN);
       uint32_t part0 = 0xFFFFFFFFu;
@@ -208,8 +218,9 @@ k_gather(Grid g, const uint32_t* __restrict__ cell_start, MapSoA m, const uint32
         continue;
       }
     }
-    gather_chunks<FILTER, MODE>(m, total, 0u, 32u, lane, act, sEnd[warp], sOff[warp], sP[warp], sD[warp], qx, qy, qz, nv, r2, power,
-                                rr, rg, rb, cnt);
+    const uint32_t staged = gather_chunks<FILTER, MODE>(m, total, 0u, 32u, lane, act, sEnd[warp], sOff[warp], sP[warp], sD[warp], qx, qy, qz,
+                                                        nv, r2, power, rr, rg, rb, cnt);
+    tests += (unsigned long long)staged * (unsigned)__popc(grp);
   }
   if (valid && !deferred) {
     if (MODE != 2) {
@@ -218,27 +229,30 @@ k_gather(Grid g, const uint32_t* __restrict__ cell_start, MapSoA m, const uint32
     }
     if (counts) counts[qi] = cnt;
   }
-  if (sum_k) {
-    unsigned long long c = cnt;
-    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(FULL, c, o);
-    if (lane == 0 && c) atomicAdd(sum_k, c);
+  {
+    const unsigned c = __reduce_add_sync(FULL, cnt);
+    if (lane == 0 && c) atomicAdd(&ps->sum_k, (unsigned long long)c);
+    if (lane == 0 && tests) atomicAdd(&ps->cand, tests);
   }
 }
 
 // Heavy parts: every warp claims parts by ticket (ctr[1]) until the list (ctr[3] parts, all published before this
-// kernel starts) is exhausted.
+// kernel starts) is exhausted.  Launched after every k_gather with a fixed grid; without parts it returns at once.
 template <int FILTER, int MODE>
 __global__ void __launch_bounds__(GATHER_WARPS * 32)
-k_gather_heavy(Grid g, const uint32_t* __restrict__ cell_start, MapSoA m, const uint32_t* __restrict__ qidx,
-               const double* __restrict__ qpos3, const double* __restrict__ qnrm3, int64_t n, double power, double r2_fixed,
-               const double* __restrict__ r2q, double* __restrict__ rgb3, uint32_t* __restrict__ counts,
-               unsigned long long* __restrict__ sum_k, HeavyList hl) {
+k_gather_heavy(PassDev* ps, CellIndex ix, MapSoA m, const uint32_t* __restrict__ qidx,
+               const double* __restrict__ qpos3, const double* __restrict__ qnrm3,
+               const double* __restrict__ r2q, double* __restrict__ rgb3, uint32_t* __restrict__ counts, HeavyList hl) {
   __shared__ double2 sP[GATHER_WARPS][32][2];
   __shared__ double2 sD[GATHER_WARPS][32][2];
   __shared__ uint32_t sEnd[GATHER_WARPS][32], sOff[GATHER_WARPS][32];
+  const unsigned int nparts_total = hl.ctr[3];
+  if (nparts_total == 0u) return;
   const unsigned FULL = 0xffffffffu;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const unsigned int nparts_total = hl.ctr[3];
+  const Grid g = ps->grid;
+  const int64_t n = (int64_t)ps->n_query;
+  const double power = ps->power, r2_fixed = ps->r2;
   for (;;) {
     unsigned int t = 0xFFFFFFFFu;
     if (lane == 0) { t = atomicAdd(hl.ctr + 1, 1u); if (t >= nparts_total) t = 0xFFFFFFFFu; }
@@ -259,11 +273,12 @@ k_gather_heavy(Grid g, const uint32_t* __restrict__ cell_start, MapSoA m, const 
       if (MODE != 2) hnv = ld3(qnrm3 + (uint64_t)hqi * 3);
       if (MODE != 0) hr2 = r2q[hqi];
     }
-    const uint32_t total = gather_group_runs(g, cell_start, h_ck, h_klast, lane, sEnd[warp], sOff[warp]);
+    const uint32_t total = gather_group_runs(g, ix, h_ck, h_klast, lane, sEnd[warp], sOff[warp]);
     double ar = 0.0, ag = 0.0, ab = 0.0;
     uint32_t ac = 0;
-    gather_chunks<FILTER, MODE>(m, total, (t - h_p0) * 32u, h_np * 32u, lane, hact, sEnd[warp], sOff[warp], sP[warp], sD[warp],
-                                hx, hy, hz, hnv, hr2, power, ar, ag, ab, ac);
+    const uint32_t staged = gather_chunks<FILTER, MODE>(m, total, (t - h_p0) * 32u, h_np * 32u, lane, hact, sEnd[warp], sOff[warp], sP[warp],
+                                                        sD[warp], hx, hy, hz, hnv, hr2, power, ar, ag, ab, ac);
+    if (lane == 0 && staged) atomicAdd(&ps->cand, (unsigned long long)staged * (unsigned)__popc(h_grp));
     HeavyPartial* hp = hl.partials + t;
     __stcg(&hp->rgb[0][lane], ar); __stcg(&hp->rgb[1][lane], ag); __stcg(&hp->rgb[2][lane], ab); __stcg(&hp->cnt[lane], ac);
     __threadfence();
@@ -286,10 +301,9 @@ k_gather_heavy(Grid g, const uint32_t* __restrict__ cell_start, MapSoA m, const 
       }
       if (counts) counts[hqi] = tc;
     }
-    if (sum_k) {
-      unsigned long long c = hact ? tc : 0u;
-      for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(FULL, c, o);
-      if (lane == 0 && c) atomicAdd(sum_k, c);
+    {
+      const unsigned c = __reduce_add_sync(FULL, hact ? tc : 0u);
+      if (lane == 0 && c) atomicAdd(&ps->sum_k, (unsigned long long)c);
     }
   }
 }
@@ -325,10 +339,12 @@ __global__ void k_knn_finish(int64_t n, double r2, double* __restrict__ thr) {
   if (i < n && !(thr[i] > 0.0)) thr[i] = r2;
 }
 
-__global__ void k_within(Grid g, const uint32_t* __restrict__ cell_start, MapSoA m, const double* __restrict__ qpos3,
-                         int64_t n, double r2, uint32_t* __restrict__ idx, uint32_t* __restrict__ counts, uint32_t cap) {
+__global__ void k_within(const PassDev* __restrict__ ps, CellIndex ix, MapSoA m, const double* __restrict__ qpos3,
+                         int64_t n, uint32_t* __restrict__ idx, uint32_t* __restrict__ counts, uint32_t cap) {
   int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= n) return;
+  const Grid g = ps->grid;
+  const double r2 = ps->r2;
   const double qx = qpos3[q * 3], qy = qpos3[q * 3 + 1], qz = qpos3[q * 3 + 2];
   uint32_t cnt = 0;
   int cx = cell_coord(g, qx, 0), cy = cell_coord(g, qy, 1), cz = cell_coord(g, qz, 2);
@@ -338,10 +354,10 @@ __global__ void k_within(Grid g, const uint32_t* __restrict__ cell_start, MapSoA
     for (int z = max(cz - R, 0); z <= min(cz + R, g.nz - 1); ++z)
       for (int y = max(cy - R, 0); y <= min(cy + R, g.ny - 1); ++y) {
         uint32_t row = ((uint32_t)z * (uint32_t)g.ny + (uint32_t)y) * (uint32_t)g.nx;
-        uint32_t b = cell_start[row + x0], e = cell_start[row + x1 + 1];
+        uint32_t b = cell_begin(ix, row + (uint32_t)x0), e = cell_begin(ix, row + (uint32_t)x1 + 1u);
         for (uint32_t j = b; j < e; ++j) {
-          const double2 a = m.P[(uint64_t)j * 2], b = m.P[(uint64_t)j * 2 + 1];
-          double ax = qx - a.x, ay = qy - a.y, az = qz - b.x;
+          const double2 a = m.P[(uint64_t)j * 2], b2 = m.P[(uint64_t)j * 2 + 1];
+          double ax = qx - a.x, ay = qy - a.y, az = qz - b2.x;
           double d2 = (ax * ax + ay * ay) + az * az;
           if (d2 <= r2) {
             if (cnt < cap) idx[(uint64_t)q * cap + cnt] = m.orig[j];

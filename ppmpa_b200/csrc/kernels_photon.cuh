@@ -4,6 +4,7 @@
 #define PPM_KERNELS_PHOTON_CUH_
 
 #include "dev_core.cuh"
+#include "pass_state.cuh"
 
 
 __global__ void k_intersect(const __grid_constant__ DevScene sc, const double* __restrict__ rays6, int64_t n,
@@ -55,19 +56,26 @@ struct RecBuf {
 // from a global ticket counter (one atomic per warp per refill) instead of idling until the
 // longest path of its warp ends.  One loop iteration = (optional) emission + one bounce.
 // Records are appended with one atomic per warp (warp-aggregated compaction).
+// seed / pass come from the device-resident pass state, the record counter and the ticket live there too: the
+// kernel is launched with the same arguments every pass (CUDA graph).  Every photon leaves the set of depths at which
+// it stored a record in pmask[photon] (kernels_map.cuh: the tag order of the records then costs one scan).
 #ifndef PPM_TRACE_MINB
 #define PPM_TRACE_MINB 6
 #endif
 __global__ void __launch_bounds__(128, PPM_TRACE_MINB)
-k_trace_photons(const __grid_constant__ DevScene sc, const __grid_constant__ LightSplit ls, uint64_t seed, uint32_t pass,
-                int uc, int64_t n, RecBuf rec, unsigned long long* __restrict__ counter, unsigned long long cap,
-                unsigned long long* __restrict__ ticket) {
+k_trace_photons(const __grid_constant__ DevScene sc, const __grid_constant__ LightSplit ls, PassDev* ps,
+                int uc, int64_t n, RecBuf rec, unsigned long long cap, uint32_t* __restrict__ pmask) {
   const unsigned FULL = 0xffffffffu;
   const unsigned lane = threadIdx.x & 31u;
   const unsigned lt_mask = (1u << lane) - 1u;
+  const uint64_t seed = ps->seed;
+  const uint32_t pass = ps->pass;
+  unsigned long long* const counter = &ps->n_rec;
+  unsigned long long* const ticket = &ps->ticket;
   bool alive = false, exhausted = false, need_dir = false;
   int64_t idx = 0;
   int wl = 0, medium = -1, depth = 0;
+  uint32_t stored = 0;                                   // depths at which this photon stored a record
   D3 pos = mk3(0, 0, 0), dir = mk3(1, 0, 0);
   Philox rng(seed, pass, PPM_DOMAIN_PHOTON, 0, 0);
   for (;;) {
@@ -84,7 +92,7 @@ k_trace_photons(const __grid_constant__ DevScene sc, const __grid_constant__ Lig
           idx = i;
           rng = Philox(seed, pass, PPM_DOMAIN_PHOTON, (uint64_t)i, 0);
           need_dir = generate_photon_t<true>(sc.lights[light_of(ls, sc.nlights, i)], rng, wl, pos, dir);   // dir = normal if deferred
-          medium = -1; depth = 0; alive = true;
+          medium = -1; depth = 0; alive = true; stored = 0u;
         } else {
           exhausted = true;
         }
@@ -97,6 +105,7 @@ k_trace_photons(const __grid_constant__ DevScene sc, const __grid_constant__ Lig
     // ---- one bounce ----------------------------------------------------------------------
     Isect is;
     bool store = false;
+    const bool was_alive = alive;
     const D3 in_dir = dir;
     const int l = depth;
     if (alive) {
@@ -127,8 +136,10 @@ k_trace_photons(const __grid_constant__ DevScene sc, const __grid_constant__ Lig
           rec.wl[slot] = (uint8_t)wl;
           rec.tag[slot] = ((uint64_t)idx << 4) | (uint64_t)l;
         }
+        stored |= 1u << l;
       }
     }
+    if (was_alive && !alive && pmask) pmask[idx] = stored;                // the path has ended: publish its depth set
   }
 }
 

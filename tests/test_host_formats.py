@@ -25,7 +25,7 @@ def test_cabi_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(K.lib, name), f"{name} is declared in ppm.h but not exported"
     assert declared == set(K.SIGNATURES), declared ^ set(K.SIGNATURES)
-    assert K.lib.ppm_abi_version() == 1
+    assert K.lib.ppm_abi_version() == 2
 
 
 def test_no_device_is_a_loud_error():

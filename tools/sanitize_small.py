@@ -27,9 +27,9 @@ eng.estimate_radiance_knn(q, nrm, 20, 1)
 eng.within(q, 64)
 eng.set_scene(P.read_scene(os.path.join(EX, "sample1.scene")))
 eng.direct_light(q, nrm)                              # culled shadow rays (spheres, planes, emitter quad)
-os.environ["PPM_DL_CULL"] = "0"
+eng.set_option("dl_cull", 0)
 eng.direct_light(q, nrm)
-del os.environ["PPM_DL_CULL"]
+eng.set_option("dl_cull", 1)
 # heavy gather groups: 6000 photons in one cell neighbourhood -> parts + k_gather_heavy, all modes
 rng = np.random.default_rng(3)
 hp = np.zeros(6000, K.PHOTON_DTYPE)
