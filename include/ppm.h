@@ -340,6 +340,11 @@ int  ppm_accum_reduce(ppm_ctx* ctx, void* nccl_comm, int32_t root);
  * [4] sum of K (photons within r over all gather nodes), [5] kernel launches,
  * [6] candidate distance tests of k_gather, [7] passes rendered again after a buffer overflow */
 int  ppm_last_pass_stats(ppm_ctx* ctx, double ms[8], uint64_t counters[8]);
+/* phase boundaries of the LAST pass of the last call, ms since the pass began (0 = not reached):
+ * [0] begin, [1] photon trace end, [2] map build end, [3] eye expand begin, [4] eye expand end, [5] shadow-ray
+ * classification end, [6] query sort end, [7] direct light begin, [8] direct light end, [9] gather begin,
+ * [10] gather end, [11] combine begin, [12] end */
+int  ppm_last_pass_timeline(ppm_ctx* ctx, double ms_since_begin[16]);
 
 /* ---- output formats (host) -------------------------------------------- */
 /* Rust `{}` / `{:e}` f64 formatting (shortest round-trip digits) */

@@ -1288,4 +1288,22 @@ int orc_render_passes_parallel(const ppm_prim* prims, int np, const ppm_material
   return 0;
 }
 
+// The same, with a row band PER THREAD (row0s[t] .. row1s[t]): bench.py spreads the bands evenly over the image so
+// that the extrapolated pass time is a stratified sample of the image, not its centre rows.
+int orc_render_passes_bands(const ppm_prim* prims, int np, const ppm_material* mats, int nm, const ppm_light* lights, int nl,
+                            const ppm_camera* cam, uint64_t seed, const uint32_t* pass_ids, int nthreads, int64_t nphoton,
+                            const double* radius2_per_pass, int uc, const int* row0s, const int* row1s, double* times_s, uint64_t* stats) {
+  std::vector<std::thread> th;
+  std::vector<std::vector<double>> img((size_t)nthreads);
+  for (int t = 0; t < nthreads; ++t) {
+    img[(size_t)t].resize((size_t)(row1s[t] - row0s[t]) * cam->xreso * 3);
+    th.emplace_back([=, &img]() {
+      orc_render_pass(prims, np, mats, nm, lights, nl, cam, seed, pass_ids[t], nphoton, radius2_per_pass[t], uc,
+                      row0s[t], row1s[t], img[(size_t)t].data(), times_s ? times_s + t * 3 : nullptr, stats ? stats + t * 4 : nullptr);
+    });
+  }
+  for (auto& x : th) x.join();
+  return 0;
+}
+
 }  // extern "C"

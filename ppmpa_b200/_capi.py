@@ -128,6 +128,7 @@ SIGNATURES = {
     "ppm_comm_init": (C.c_int, [vp, i32, i32, vp]),
     "ppm_comm_destroy": (C.c_int, [vp]),
     "ppm_accum_reduce": (C.c_int, [vp, vp, i32]),
+    "ppm_last_pass_timeline": (C.c_int, [vp, P(dbl)]),
     "ppm_last_pass_stats": (C.c_int, [vp, P(dbl), P(u64)]),
     "ppm_format_f64": (C.c_int, [dbl, C.c_int, C.c_char_p, C.c_size_t]),
     "ppm_radiance_to_rgb": (None, [dbl, D3, P(i32)]),

@@ -127,11 +127,15 @@ struct ppm_ctx {
   cudaGraphExec_t gexec = nullptr;
   GraphKey gkey;
   uint64_t graph_kernels = 0;
+  int prio_hi = 0, prio_lo = 0;      // stream priorities (main stream = highest)
+  bool capturing = false;            // enq_pass is being recorded into a graph
+  std::vector<cudaGraphNode_t> seg_before, hi_nodes;   // capture bookkeeping: nodes recorded from the main stream
   enum { EV_FORK, EV_NODES, EV_DL, EV_G0, EV_G1, EV_COUNT };
   cudaEvent_t ev[EV_COUNT] = {nullptr};
   // last pass / batch stats
   double ms[8] = {0};
   uint64_t counters[8] = {0};
+  double timeline[PPM_NSTAMP] = {0};  // last pass of the last batch: stamps in ms since its begin
   uint64_t launches = 0;
   std::vector<ppm_ctx*> twins;       // further lanes on the same GPU (ppm_render_passes), owned
   void* comm = nullptr;              // ncclComm_t owned by the ctx (ppm_comm_init)
@@ -765,6 +769,34 @@ int ensure_pass(ppm_ctx* c, int64_t total) {
   return PPM_OK;
 }
 
+// Stream priorities are not carried into captured kernel nodes, and without them the few-CTA kernels of the photon
+// branch queue behind the 16 k CTAs of the eye-path expansion.  While capturing, the nodes recorded from the main
+// stream are collected segment by segment (set difference of the graph's node list) and get the high priority as a
+// node attribute afterwards.
+std::vector<cudaGraphNode_t> capture_nodes(ppm_ctx* c) {
+  std::vector<cudaGraphNode_t> v;
+  cudaStreamCaptureStatus stt = cudaStreamCaptureStatusNone;
+  cudaGraph_t g = nullptr;
+  if (cudaStreamGetCaptureInfo(c->stream, &stt, nullptr, &g, nullptr, nullptr) != cudaSuccess || stt != cudaStreamCaptureStatusActive || !g) {
+    cudaGetLastError();
+    return v;
+  }
+  size_t n = 0;
+  if (cudaGraphGetNodes(g, nullptr, &n) != cudaSuccess || n == 0) { cudaGetLastError(); return v; }
+  v.resize(n);
+  if (cudaGraphGetNodes(g, v.data(), &n) != cudaSuccess) { cudaGetLastError(); v.clear(); return v; }
+  v.resize(n);
+  std::sort(v.begin(), v.end());
+  return v;
+}
+void seg_begin(ppm_ctx* c) { if (c->capturing) c->seg_before = capture_nodes(c); }
+void seg_end(ppm_ctx* c) {
+  if (!c->capturing) return;
+  std::vector<cudaGraphNode_t> now = capture_nodes(c);
+  for (cudaGraphNode_t n : now)
+    if (!std::binary_search(c->seg_before.begin(), c->seg_before.end(), n)) c->hi_nodes.push_back(n);
+}
+
 // The launch sequence of ONE pass: photon branch on `stream`, eye branch on `stream2`, joined before the gather (needs
 // map + sorted queries) and before the combine (needs direct light + estimates).  Pure enqueue: runs as is in stream
 // mode and is what the graph capture records.
@@ -774,6 +806,7 @@ int enq_pass(ppm_ctx* c, const LightSplit& ls, int64_t total, int uc, bool accum
   const int64_t npix = (int64_t)c->cam.xreso * c->cam.yreso;
   const uint64_t ecap = c->pass_eye_cap;
   const bool cull = uc && cull_on(c);
+  seg_begin(c);
   k_pass_begin<<<1, 32, 0, sa>>>(c->ps, c->bt);
   KCHECK(c);
   CK(c, cudaEventRecord(c->ev[E::EV_FORK], sa));
@@ -783,6 +816,7 @@ int enq_pass(ppm_ctx* c, const LightSplit& ls, int64_t total, int uc, bool accum
   RC(enq_stamp(c, sa, ST_TRACE_END));
   RC(enq_build(c, sa, true, (uint64_t)total, c->rec_cap));
   RC(enq_stamp(c, sa, ST_BUILD_END));
+  seg_end(c);
   // eye branch
   k_eye_expand<<<nblk(npix, 128), 128, 0, sb>>>(c->scene, c->cam, nullptr, npix, 0, c->ps, eyenodes(c), (uint32_t)ecap, c->e_head.as<uint32_t>(),
                                                c->e_emit.as<double>(), 0, ST_EXPAND_BEGIN);
@@ -801,6 +835,7 @@ int enq_pass(ppm_ctx* c, const LightSplit& ls, int64_t total, int uc, bool accum
   }
   CK(c, cudaEventRecord(c->ev[E::EV_DL], sb));
   // gather
+  seg_begin(c);
   CK(c, cudaStreamWaitEvent(sa, c->ev[E::EV_NODES], 0));
   if (!c->opt_graph) CK(c, cudaEventRecord(c->ev[E::EV_G0], sa));
   RC(enq_gather(c, sa, c->e_pos.as<double>(), c->e_nrm.as<double>(), ecap, c->cam.pfilter, 0, nullptr, c->e_photon.as<double>(), nullptr, false,
@@ -812,6 +847,7 @@ int enq_pass(ppm_ctx* c, const LightSplit& ls, int64_t total, int uc, bool accum
   RC(enq_combine(c, npix, 0, uc != 0, false, c->pass_img.as<double>(), accumulate ? c->accum.as<double>() : nullptr, ST_COMBINE_BEGIN));
   k_pass_end<<<1, 32, 0, sa>>>(c->ps, c->out, accumulate ? c->accum.as<double>() + (size_t)npix * 3 : nullptr);
   KCHECK(c);
+  seg_end(c);
   return PPM_OK;
 }
 
@@ -825,12 +861,30 @@ int build_graph(ppm_ctx* c, const LightSplit& ls, int64_t total, int uc) {
   CK(c, cudaStreamSynchronize(c->stream2));
   const uint64_t l0 = c->launches;
   CK(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+  c->capturing = true; c->hi_nodes.clear();
   int rc = enq_pass(c, ls, total, uc, true, nullptr);
+  c->capturing = false;
   cudaGraph_t g = nullptr;
   cudaError_t e = cudaStreamEndCapture(c->stream, &g);
   if (rc) { if (g) cudaGraphDestroy(g); cudaGetLastError(); return rc; }
   if (e != cudaSuccess) { c->err = std::string("graph capture: ") + cudaGetErrorString(e); cudaGetLastError(); return PPM_ERR_CUDA; }
-  e = cudaGraphInstantiate(&c->gexec, g, 0);
+  {
+    // node priorities: main-stream nodes high, everything else low
+    size_t n = 0;
+    std::vector<cudaGraphNode_t> all;
+    if (cudaGraphGetNodes(g, nullptr, &n) == cudaSuccess && n) { all.resize(n); cudaGraphGetNodes(g, all.data(), &n); all.resize(n); }
+    std::sort(c->hi_nodes.begin(), c->hi_nodes.end());
+    for (cudaGraphNode_t nd : all) {
+      cudaGraphNodeType ty;
+      if (cudaGraphNodeGetType(nd, &ty) != cudaSuccess || ty != cudaGraphNodeTypeKernel) continue;
+      cudaLaunchAttributeValue v;
+      std::memset(&v, 0, sizeof v);
+      v.priority = std::binary_search(c->hi_nodes.begin(), c->hi_nodes.end(), nd) ? c->prio_hi : c->prio_lo;
+      cudaGraphKernelNodeSetAttribute(nd, cudaLaunchAttributePriority, &v);
+    }
+    cudaGetLastError();
+  }
+  e = cudaGraphInstantiateWithFlags(&c->gexec, g, cudaGraphInstantiateFlagUseNodePriority);   // else the launch stream's priority applies to every node
   cudaGraphDestroy(g);
   if (e != cudaSuccess) { c->gexec = nullptr; c->err = std::string("graph instantiate: ") + cudaGetErrorString(e); return PPM_ERR_CUDA; }
   c->graph_kernels = c->launches - l0;
@@ -1031,6 +1085,11 @@ int render_batch(ppm_ctx* c, uint64_t seed, uint32_t first_pass, uint32_t stride
   }
   st.ct[5] += stream_launches;                            // (graph mode: the graph's kernel nodes were counted per pass above)
   st.ct[7] = retried;
+  {
+    const PassOut& o = outs[(size_t)npass - 1];
+    for (int k = 0; k < PPM_NSTAMP; ++k)
+      c->timeline[k] = (o.stamp[k] && o.stamp[k] >= o.stamp[ST_BEGIN]) ? (double)(o.stamp[k] - o.stamp[ST_BEGIN]) * 1e-6 : 0.0;
+  }
   std::memcpy(c->ms, st.ms, sizeof st.ms);
   std::memcpy(c->counters, st.ct, sizeof st.ct);
   // the photon set and the map of this lane's last pass stay current for the probe entry points
@@ -1107,6 +1166,7 @@ int ppm_create(int device, ppm_ctx** out) {
   // remaining blocks of the long eye-branch kernels on stream2.
   int prio_lo = 0, prio_hi = 0;
   cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+  c->prio_hi = prio_hi; c->prio_lo = prio_lo;
   bool ok = cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_hi) == cudaSuccess;
   ok = ok && cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, prio_lo) == cudaSuccess;
   for (int i = 0; ok && i < ppm_ctx::EV_COUNT; ++i)
@@ -1203,21 +1263,27 @@ int ppm_scene_set(ppm_ctx* c, const ppm_prim* prims, int32_t nprims, const ppm_m
   }
   for (int i = 0; i < nlights; ++i)
     if (lights[i].type < PPM_LIGHT_POINT || lights[i].type > PPM_LIGHT_SUN) return fail(c, PPM_ERR_ARG, "bad light type");
-  CK(c, cudaSetDevice(c->device));
-  CK(c, cudaStreamSynchronize(c->stream));
-  std::memset(&c->scene, 0, sizeof c->scene);
-  c->scene.nprims = nprims; c->scene.nmats = nmats; c->scene.nlights = nlights;
-  std::memcpy(c->scene.prims, prims, sizeof(ppm_prim) * nprims);
-  std::memcpy(c->scene.mats, mats, sizeof(ppm_material) * nmats);
-  if (nlights) std::memcpy(c->scene.lights, lights, sizeof(ppm_light) * nlights);
-  c->scene.types.nwords = nprims > 32 ? 2 : 1;
+  DevScene* ns = new DevScene;
+  std::memset(ns, 0, sizeof *ns);
+  ns->nprims = nprims; ns->nmats = nmats; ns->nlights = nlights;
+  std::memcpy(ns->prims, prims, sizeof(ppm_prim) * nprims);
+  std::memcpy(ns->mats, mats, sizeof(ppm_material) * nmats);
+  if (nlights) std::memcpy(ns->lights, lights, sizeof(ppm_light) * nlights);
+  ns->types.nwords = nprims > 32 ? 2 : 1;
   for (int o = 0; o < nprims; ++o) {
     const unsigned long long bit = 1ull << o;
-    if (prims[o].type == PPM_SHAPE_PLAIN) c->scene.types.plain |= bit;
-    else if (prims[o].type == PPM_SHAPE_SPHERE) c->scene.types.sphere |= bit;
-    else if (prims[o].type == PPM_SHAPE_POLYGON) c->scene.types.poly |= bit;
-    else if (prims[o].type == PPM_SHAPE_PARALLELOGRAM) c->scene.types.para |= bit;
+    if (prims[o].type == PPM_SHAPE_PLAIN) ns->types.plain |= bit;
+    else if (prims[o].type == PPM_SHAPE_SPHERE) ns->types.sphere |= bit;
+    else if (prims[o].type == PPM_SHAPE_POLYGON) ns->types.poly |= bit;
+    else if (prims[o].type == PPM_SHAPE_PARALLELOGRAM) ns->types.para |= bit;
   }
+  // the same scene again (a host loop that hands the scene over every pass): keep the calibration and the pass graph
+  const bool same = c->have_scene && std::memcmp(ns, &c->scene, sizeof *ns) == 0;
+  if (same) { delete ns; return PPM_OK; }
+  CK(c, cudaSetDevice(c->device));
+  CK(c, cudaStreamSynchronize(c->stream));
+  c->scene = *ns;
+  delete ns;
   RC(upload_cull(c));
   c->have_scene = true;
   c->scene_ver++;
@@ -1228,6 +1294,7 @@ int ppm_camera_set(ppm_ctx* c, const ppm_camera* cam) {
   if (!c || !cam) return PPM_ERR_ARG;
   if (cam->xreso <= 0 || cam->yreso <= 0) return fail(c, PPM_ERR_ARG, "bad resolution");
   if (cam->pfilter < PPM_FILTER_NONE || cam->pfilter > PPM_FILTER_GAUSS) return fail(c, PPM_ERR_ARG, "bad photon filter");
+  if (c->have_camera && std::memcmp(&c->cam, cam, sizeof *cam) == 0) return PPM_OK;   // unchanged: keep calibration and graph
   c->cam = *cam;
   c->have_camera = true;
   c->cam_ver++;
@@ -1508,6 +1575,13 @@ int ppm_last_pass_stats(ppm_ctx* c, double ms[8], uint64_t counters[8]) {
   if (!c) return PPM_ERR_ARG;
   if (ms) std::memcpy(ms, c->ms, sizeof c->ms);
   if (counters) std::memcpy(counters, c->counters, sizeof c->counters);
+  return PPM_OK;
+}
+
+int ppm_last_pass_timeline(ppm_ctx* c, double ms_since_begin[16]) {
+  if (!c || !ms_since_begin) return PPM_ERR_ARG;
+  static_assert(PPM_NSTAMP == 16, "timeline slots");
+  std::memcpy(ms_since_begin, c->timeline, sizeof c->timeline);
   return PPM_OK;
 }
 

@@ -352,6 +352,14 @@ class Engine:
         self._ck(lib.ppm_image_mean(self._h, _ptr(out)))
         return out
 
+    def last_pass_timeline(self):
+        """Phase boundaries of the last pass, ms since its begin (include/ppm.h)."""
+        t = (C.c_double * 16)()
+        self._ck(lib.ppm_last_pass_timeline(self._h, t))
+        names = ["begin", "trace_end", "build_end", "expand_begin", "expand_end", "classify_end", "qsort_end", "dl_begin", "dl_end",
+                 "gather_begin", "gather_end", "combine_begin", "end"]
+        return {k: t[i] for i, k in enumerate(names)}
+
     def last_pass_stats(self):
         ms = (C.c_double * 8)(); ct = (C.c_uint64 * 8)()
         self._ck(lib.ppm_last_pass_stats(self._h, ms, ct))

@@ -78,6 +78,8 @@ def load():
                                       u32, i64, dbl, C.c_int, C.c_int, C.c_int, vp, vp, vp]),
         "orc_render_passes_parallel": (C.c_int, [P(K.Prim), C.c_int, P(K.Material), C.c_int, P(K.Light), C.c_int,
                                                  P(K.Camera), u64, u32, C.c_int, i64, vp, C.c_int, C.c_int, C.c_int, vp, vp]),
+        "orc_render_passes_bands": (C.c_int, [P(K.Prim), C.c_int, P(K.Material), C.c_int, P(K.Light), C.c_int,
+                                              P(K.Camera), u64, vp, C.c_int, i64, vp, C.c_int, vp, vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -178,6 +180,18 @@ class Oracle:
         self.L.orc_render_passes_parallel(scene.prims, scene.nprims, scene.mats, scene.nmats, scene.lights, scene.nlights,
                                           C.byref(cam), seed, pass0, nthreads, nphoton, _p(r2), 1 if uc else 0, row0, row1,
                                           _p(times), _p(stats))
+        return times, stats
+
+
+    def render_passes_bands(self, scene, cam, seed, pass_ids, nphoton, radius2_per_pass, uc, row0s, row1s):
+        """One single-threaded pass per entry, all concurrently; pass t traces image rows row0s[t]..row1s[t]."""
+        n = len(pass_ids)
+        ids = np.ascontiguousarray(pass_ids, np.uint32); r2 = np.ascontiguousarray(radius2_per_pass, np.float64)
+        a = np.ascontiguousarray(row0s, np.int32); b = np.ascontiguousarray(row1s, np.int32)
+        times = np.zeros((n, 3)); stats = np.zeros((n, 4), np.uint64)
+        self.L.orc_render_passes_bands(scene.prims, scene.nprims, scene.mats, scene.nmats, scene.lights, scene.nlights,
+                                       C.byref(cam), seed, _p(ids), n, nphoton, _p(r2), 1 if uc else 0, _p(a), _p(b),
+                                       _p(times), _p(stats))
         return times, stats
 
 

@@ -25,9 +25,10 @@ def test_reference_arm_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["unit"] == "pixels/s" and d["higher_is_better"] is True
     assert d["value"] > 0 and d["steps"] == 1 and d["n_gpus"] == 1 and d["dtype"] == "f64" and d["vs_baseline"] is None
-    assert d["config"]["workload"].startswith("configs[1]")
+    assert d["config"]["workload"].startswith("configs[4]")         # the north-star job is the default workload
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] == (os.cpu_count() or 1) and cb["value"] == d["value"] and "4 of 1024" in cb["sample"]
+    assert cb["kind"] == "port" and cb["cores"] == (os.cpu_count() or 1) and cb["value"] == d["value"] and "4 of 1080" in cb["sample"]
+    assert cb["extrapolated"] is True and "EXTRAPOLATED" in cb["sample"] and "stratified" in cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "pixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["gpu_launches"] == 0
 

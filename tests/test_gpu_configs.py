@@ -1,0 +1,193 @@
+"""GPU parity at the BASELINE configurations' OWN sizes and modes, with bounded (not merely counted) outliers,
+and the multi-context / multi-GPU frame equality.
+
+Why a pixel may deviate from the oracle at all: both sides draw the same Philox numbers, but libdevice and glibc
+sin/cos/pow differ in the last bits, so a hit point can move by ~1e-15 and ONE photon can fall on the other side of a
+query's d2 <= r2 test (or one photon path can take another roulette branch).  That changes a pixel by at most one
+photon's contribution  W (.) wt * power * cos / (pi r^2) <= QUANTUM = wt_max * power / (pi r^2)  per flipped photon.
+Every deviating pixel is therefore asserted to be within a small multiple of QUANTUM -- a bug that moved a pixel by
+more (wrong cell walk, lost heavy part, wrong culling certificate) fails however few pixels it touches.
+"""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import ppmpa_b200 as P
+from ppmpa_b200 import _capi as K
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EX = os.path.join(ROOT, "examples")
+SEED = 0x5EED0001
+WT_MAX = {K.FILTER_NONE: 1.0, K.FILTER_CONE: 1.0 / (1.0 - 2.0 / (3.0 * 1.1)), K.FILTER_GAUSS: 0.918 + 0.5}   # tracer.rs:198-216
+FLIPS = 4            # photons that may flip in one pixel (its nodes' neighbour sets together)
+
+
+def load_scene(name):
+    return P.read_scene(None if name is None else os.path.join(EX, name + ".scene"))
+
+
+def quantum(sc, nphoton, r2, pfilter):
+    power, _ = sc.photon_budget(nphoton)
+    return WT_MAX[pfilter] * power / (np.pi * r2)
+
+
+def assert_image_bounded(g, o, q, max_frac=5e-3, rtol=1e-6, what=""):
+    """g, o: [n][3] images.  Pixels beyond rtol are few AND each is within FLIPS photon contributions."""
+    err = np.abs(g - o)
+    rel = err / np.maximum(np.maximum(np.abs(o), np.abs(g)), 1e-300)
+    bad = np.any(rel > rtol, axis=1)
+    assert bad.mean() <= max_frac, f"{what}: {bad.mean():.4%} of the pixels differ by more than {rtol}"
+    worst = err.max() / q
+    assert worst <= FLIPS, f"{what}: a pixel is off by {worst:.2f} photon contributions (quantum {q:.3e}, max abs err {err.max():.3e})"
+    assert np.median(rel) < 1e-12, f"{what}: median relative error {np.median(rel):.2e}"
+    return bad.mean(), worst
+
+
+# ---------------------------------------------------------------------------
+# config 1: what the reference binary renders whatever files it is given (scene.rs:20-448, camera.rs:109-128,
+# ppmpa.rs:17-18: 256x256, 100 000 photons, r = 0.1), with and without -nc, WHOLE image
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("uc", [True, False])
+def test_config1_builtin_whole_image(engine, oracle, uc):
+    sc = load_scene(None)
+    cam = P.read_camera(None)
+    assert (cam.xreso, cam.yreso) == (256, 256)
+    engine.set_scene(sc); engine.set_camera(cam)
+    engine.accum_reset()
+    r2 = 0.1 * 0.1
+    engine.iteration(SEED, 0, 100000, r2, uc=uc)
+    g = engine.pass_image()
+    ms, ct = engine.last_pass_stats()
+    o, _, ostats = oracle.render_pass(sc, cam, SEED, 0, 100000, r2, uc)
+    assert ct["stored"] == int(ostats[0]) and ct["gather_nodes"] > 256 * 256 // 2
+    frac, worst = assert_image_bounded(g, o, quantum(sc, 100000, r2, cam.pfilter), what=f"config 1 uc={uc}")
+    print(f"config 1 uc={uc}: {frac:.4%} pixels beyond 1e-6, worst {worst:.2f} photon contributions")
+
+
+# ---------------------------------------------------------------------------
+# config 3: ex-sunwindow -nc at 1024^2 with 1 M photons: rows through the sunlit patch (heavy gather groups)
+# ---------------------------------------------------------------------------
+def test_config3_sunwindow_rows_through_the_patch(engine, oracle):
+    sc = load_scene("ex-sunwindow")
+    cam = P.read_camera(os.path.join(EX, "camera0.scr"), xreso=1024, yreso=1024, pfilter=K.FILTER_NONE, progressive=1)
+    engine.set_scene(sc); engine.set_camera(cam)
+    engine.accum_reset()
+    r2 = 0.1 * 0.1
+    engine.iteration(SEED, 0, 1_000_000, r2, uc=False)
+    img = engine.pass_image().reshape(1024, 1024, 3)
+    ms, ct = engine.last_pass_stats()
+    k_mean = ct["sum_k"] / max(ct["gather_nodes"], 1)
+    row = int(np.argmax(img.sum(axis=(1, 2))))                     # the brightest row crosses the sunlit patch
+    rows = (max(row - 1, 0), min(row + 1, 1024))
+    o, _, ostats = oracle.render_pass(sc, cam, SEED, 0, 1_000_000, r2, False, rows[0], rows[1])
+    assert ct["stored"] == int(ostats[0])
+    g = img[rows[0]:rows[1]].reshape(-1, 3)
+    # the patch really is heavy: the brightest pixels gather well over a thousand photons (radiance / quantum), mean K ~ 1000
+    q = quantum(sc, 1_000_000, r2, K.FILTER_NONE)
+    assert g.max() / q > 1000 and k_mean > 500, (g.max() / q, k_mean)
+    frac, worst = assert_image_bounded(g, o, q, what="config 3 rows")
+    print(f"config 3: rows {rows}, mean K {k_mean:.0f}, brightest pixel ~{g.max() / q:.0f} photons, {frac:.4%} beyond 1e-6, worst {worst:.2f}")
+    assert np.isfinite(img).all() and img.min() >= 0.0
+
+
+# ---------------------------------------------------------------------------
+# config 4: mirror-ball / coral-ball, fixed radius x filter sweep against the oracle on an identical map
+# (estimate_radiance + filters, tracer.rs:179-216), queries = the scene's own eye-path hit points
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["mirror-ball", "coral-ball"])
+def test_config4_fixed_radius_filter_sweep(engine, oracle, name):
+    sc = load_scene(name)
+    cam = P.read_camera(os.path.join(EX, "camera0.scr"), xreso=96, yreso=96, blur=0, antialias=0, progressive=1)
+    engine.set_scene(sc); engine.set_camera(cam)
+    power, ns = sc.photon_budget(300000)
+    engine.trace_photons(SEED, 0, False, ns, power)
+    ph, pw = engine.export_photons()
+    rays = engine.generate_rays(SEED, 0)
+    hit, t, pos, nrm, io = engine.calc_intersection(rays)
+    pos, nrm = np.ascontiguousarray(pos[hit >= 0]), np.ascontiguousarray(nrm[hit >= 0])
+    assert len(pos) > 5000
+    for r in (0.05, 0.1, 0.2, 0.3):
+        engine.build_photonmap(r * r)
+        m = oracle.map_build(ph, pw, r * r)
+        for pfilter in (K.FILTER_NONE, K.FILTER_CONE, K.FILTER_GAUSS):
+            g, gc = engine.estimate_radiance(pos, nrm, pfilter)
+            o, oc = m.gather(pos, nrm, pfilter, nthreads=8)
+            assert np.array_equal(gc, oc), (name, r, pfilter)              # neighbour-set sizes bit-exact
+            assert gc.max() > 20
+            err = np.abs(g - o)
+            tol = 1e-9 * np.maximum(np.abs(g), np.abs(o))
+            assert not (err > tol).any(), (name, r, pfilter, float(err.max()))
+
+
+# ---------------------------------------------------------------------------
+# one frame over several contexts == the same passes on one context (util/averager2.rb:49-62,86: a plain sum)
+# ---------------------------------------------------------------------------
+def test_sharded_frame_equals_single_context(engine):
+    """Passes {0..5} rendered on ONE context, against the same pass ids sharded round-robin over TWO other contexts
+    (rank r renders passes r, r+2, ...: exactly what bench.py / the CLI do per GPU) and summed.  Every pass image is a
+    pure function of (scene, camera, seed, pass id, photons, radius) -- the grid region comes from a calibration that
+    does not depend on which passes a context renders -- so the per-pass images are bit-identical and the frame sums
+    agree to the rounding of the different summation order."""
+    sc = load_scene("ex-glassbox")
+    cam = P.read_camera(os.path.join(EX, "camera0.scr"), xreso=96, yreso=64, pfilter=K.FILTER_NONE, progressive=1)
+    NP, NPH = 6, 50000
+    radii = P.radius_schedule(0.15, NP)
+    engine.set_scene(sc); engine.set_camera(cam)
+    singles = []
+    for p in range(NP):
+        engine.accum_reset()
+        engine.iteration(SEED, p, NPH, radii[p] ** 2, uc=True)
+        singles.append(engine.pass_image())
+    engine.accum_reset()
+    engine.iterate(SEED, 0, NP, NPH, radii ** 2, uc=True)
+    whole, n = engine.accum_read()
+    assert n == NP
+    ranks = [P.Engine(0), P.Engine(0)]
+    try:
+        parts = []
+        for r, e in enumerate(ranks):
+            e.set_scene(sc); e.set_camera(cam)
+            mine = P.passes_for_rank(NP, 2, r)
+            e.iterate(SEED, mine[0], len(mine), NPH, [radii[p] ** 2 for p in mine], uc=True, pass_stride=2)
+            acc, k = e.accum_read()
+            assert k == len(mine)
+            # a rank's accumulator is the lane-ordered sum of exactly its passes, bit for bit
+            lanes = e.get_option("lanes")
+            want = np.zeros_like(acc)
+            lane_sums = []
+            for j in range(min(lanes, len(mine))):
+                s = np.zeros_like(acc)
+                for p in mine[j::lanes]:
+                    s = s + singles[p]
+                lane_sums.append(s)
+            want = lane_sums[0]
+            for s in lane_sums[1:]:
+                want = want + s
+            assert np.array_equal(acc, want), f"rank {r}: accumulator is not the sum of its passes' images"
+            parts.append(acc)
+        total = parts[0] + parts[1]
+        ref = np.sum(singles, axis=0)
+        assert np.allclose(total, whole, rtol=1e-13, atol=0.0) and np.allclose(total, ref, rtol=1e-13, atol=0.0)
+    finally:
+        for e in ranks:
+            e.close()
+
+
+def test_two_gpu_frame_nccl_reduce(tmp_path):
+    """The frame reduced over 2 GPUs by ppm_accum_reduce (NCCL inside the C ABI, no torch.distributed) equals the sum
+    of the same pass ids rendered on one GPU.  Skipped below 2 GPUs."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    out = tmp_path / "frame.npz"
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "two_rank_frame.py"), str(out)], capture_output=True, timeout=300)
+    assert r.returncode == 0, r.stderr.decode()[-2000:]
+    z = np.load(out)
+    assert int(z["n_reduced"]) == int(z["n_single"]) == 6
+    assert np.allclose(z["reduced"], z["single"], rtol=1e-13, atol=0.0)
+    assert z["reduced"].max() > 0
