@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <vector>
 
 // Per-scene table for the conservative shadow-ray culling of k_direct_light (kernels_eye.cuh).
 // Everything here is a bound with a 1e-6 safety margin, never a quantity that enters a result.

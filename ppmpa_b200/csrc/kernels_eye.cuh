@@ -128,14 +128,10 @@ k_eye_expand(const __grid_constant__ DevScene sc, const __grid_constant__ ppm_ca
   }
   head[i] = last;
   st3(emit3 + i * 3, emit);
-  if (n_visited) {
+  {
     const unsigned conv = __activemask();
-    unsigned long long v = visited;
-    for (int o = 16; o > 0; o >>= 1) {
-      unsigned long long t = __shfl_down_sync(conv, v, o);
-      if (lane + o < 32 && ((conv >> (lane + o)) & 1u)) v += t;
-    }
-    if (lane == (unsigned)(__ffs(conv) - 1)) atomicAdd(n_visited, v);
+    const unsigned v = __reduce_add_sync(conv, visited);
+    if (lane == (unsigned)(__ffs(conv) - 1) && v) atomicAdd(n_visited, (unsigned long long)v);
   }
 }
 
@@ -236,8 +232,9 @@ __device__ __forceinline__ unsigned long long cull_classify(const DevScene& sc, 
         const double vcone = vv - cp.r * cp.r;
         if (vcone > 0.0 && vv < 1e12) {             // the node is outside the primitive's bounding sphere
           // angle(u, v) > asin(rl/|u|) + asin(r/|v|)  <=>  u.v < sqrt((uu - rl^2)(vv - r^2)) - rl r
-          const double rhs = (sqrt(ucone * vcone) - rl * cp.r) - 1e-7 * (uu + vv);
-          keep = !(dot(u, v) < rhs);
+          // (without the square root: x < sqrt(a), a > 0  <=>  x < 0 or x^2 < a; the 1e-7 margin dwarfs the rounding)
+          const double x = (dot(u, v) + rl * cp.r) + 1e-7 * (uu + vv);
+          keep = !(x < 0.0 || x * x < ucone * vcone);
         }
       }
       if (keep && cp.nvtx == 4 && off_light_plane) {

