@@ -91,3 +91,43 @@ def test_rtc_matches_library(engine):
     assert rgb.shape == (256 * 256, 3) and np.array_equal(rgb, want)
     r = subprocess.run([os.path.join(BIN, "rtc")], capture_output=True)
     assert r.returncode == 0 and b"Usage: rtc" in r.stdout
+
+
+def _read_p3(path):
+    tok = open(path).read().split("\n")
+    body = [l for l in tok if l and not l.startswith("#")]
+    assert body[0] == "P3"
+    w, h = [int(x) for x in body[1].split()]
+    vals = np.array(" ".join(body[3:]).split(), dtype=np.int64)
+    return vals.reshape(h * w, 3)
+
+
+def test_ppmpa_frame_matches_library(engine, tmp_path):
+    """ppmpa_frame = util/iterator.rb:90-117 + util/averager2.rb:49-110 in one process over the C ABI: the frame it
+    writes is the mean of the same pass ids rendered through the library.  With 2 GPUs present the same job sharded
+    over both (NCCL reduce inside libppm_b200.so, no Python) must give the same picture."""
+    import ctypes as C
+    import torch
+    scene, cam_file = os.path.join(EX, "mirror-ball.scene"), os.path.join(EX, "screen1.scr")
+    out1 = tmp_path / "frame1.ppm"
+    r = subprocess.run([os.path.join(BIN, "ppmpa_frame"), "5", "20000", "0.2", cam_file, scene, str(out1)], capture_output=True, env=ENV)
+    assert r.returncode == 0, r.stderr.decode()
+    assert b"5 passes x 20000 photons at 256x256 on 1 GPU(s)" in r.stderr
+    cam = P.read_camera(cam_file)
+    engine.set_scene(P.read_scene(scene)); engine.set_camera(cam)
+    engine.accum_reset()
+    radii = P.radius_schedule(0.2, 5)
+    engine.iterate(12345, 0, 5, 20000, radii ** 2, uc=True)
+    acc, n = engine.accum_read()
+    want = tmp_path / "want.ppm"
+    assert K.lib.ppm_write_mean_ppm(str(want).encode(), C.byref(cam), acc.ctypes.data, n) == 0
+    a, b = _read_p3(out1), _read_p3(want)
+    assert a.shape == (256 * 256, 3) and np.array_equal(a, b)
+    assert a.max() > 50
+    if torch.cuda.device_count() >= 2:
+        out2 = tmp_path / "frame2.ppm"
+        r = subprocess.run([os.path.join(BIN, "ppmpa_frame"), "-g", "2", "5", "20000", "0.2", cam_file, scene, str(out2)], capture_output=True, env=ENV)
+        assert r.returncode == 0, r.stderr.decode()
+        c = _read_p3(out2)
+        # same pass images, another summation order: 8-bit values may differ by one level on a rounding boundary
+        assert np.abs(c - a).max() <= 1 and np.mean(c != a) < 1e-3
