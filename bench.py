@@ -259,7 +259,10 @@ def run_gpu(args):
         eng.comm_init(world, rank, bytes(uid.cpu().numpy().tobytes()))
 
     def gp(step):
-        return min(global_pass(step, rank, world, K), JOB_PASSES - 1)
+        return global_pass(step, rank, world, K)
+
+    def r2_of(g):                                        # beyond the 1000-pass job (K x N > 1000) the radius stays at its last value
+        return float(radii[min(g, JOB_PASSES - 1)]) ** 2
 
     def sync_all():
         torch.cuda.synchronize()
@@ -275,7 +278,7 @@ def run_gpu(args):
         ids = [gp(s_) for s_ in steps]
         stride = (ids[1] - ids[0]) if len(ids) > 1 else 1
         assert all(ids[i + 1] - ids[i] == stride for i in range(len(ids) - 1))
-        eng.iterate(SEED, ids[0], len(ids), NPHOTON, [float(radii[g]) ** 2 for g in ids], UC, pass_stride=max(stride, 1))
+        eng.iterate(SEED, ids[0], len(ids), NPHOTON, [r2_of(g) for g in ids], UC, pass_stride=max(stride, 1))
 
     # warm-up: W untimed steps taken from the middle and both ends of the schedule (allocations, calibration, graphs, lanes)
     warm = [0, K - 1, K // 2] + list(range(1, max(W - 2, 1)))
@@ -339,7 +342,7 @@ def run_gpu(args):
             e.set_scene(sc)
             e.set_camera(cam)
             g = gp(s_)
-            e.iteration(SEED, g, NPHOTON, float(radii[g]) ** 2, UC)
+            e.iteration(SEED, g, NPHOTON, r2_of(g), UC)
             e.pass_image(bufs[lane])
 
     for lane in range(E2E_LANES):                        # warm the extra contexts (untimed)

@@ -606,6 +606,7 @@ int probe_sort_queries(ppm_ctx* c, const double* dpos, int64_t n) {
   RC(ensure_query(c, (uint64_t)n));
   c->hps.n_nodes = (unsigned long long)n; c->hps.n_query = 0u; c->hps.n_occ_q = 0u;
   c->hps.sum_k = 0ull; c->hps.cand = 0ull; c->hps.status = 0u;
+  std::memset(c->hps.sum_k_s, 0, sizeof c->hps.sum_k_s); std::memset(c->hps.cand_s, 0, sizeof c->hps.cand_s);
   c->hps.heavy[0] = c->hps.heavy[1] = c->hps.heavy[2] = c->hps.heavy[3] = 0u;
   RC(push_ps(c));
   return enq_query_sort(c, c->stream, dpos, (uint64_t)n);

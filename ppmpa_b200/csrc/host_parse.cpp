@@ -167,6 +167,11 @@ void parse_scene_text(std::istream& in, ppm_scene* sc) {
       ppm_material m;
       ppm_material_simple(&m, em, tr, ior, refl, spec, diff, metal, smooth);
       std::string name = need(it, "name", "material", ln);
+      // All 253 materials of the reference's example files say 0.0 and the reference never reads a scene file
+      // (scene.rs:20), so a non-zero value has no defined meaning: it is passed on as new_simple's roughness, loudly.
+      if (smooth != 0.0)
+        std::fprintf(stderr, "ppm scene: material '%s' (line %d): smoothness %g is passed as Surface::new_simple's roughness; "
+                             "the reference defines no mapping for a non-zero value\n", name.c_str(), ln, smooth);
       mat_index[name] = (int32_t)sc->mats.size();
       sc->mats.push_back(m);
       sc->mat_names.push_back(name);

@@ -59,13 +59,14 @@ struct HeavyList {
 
 // lanes 0..8 look up the nine runs of the group's neighbourhood; returns the length of the candidate stream and
 // leaves, per run, its cumulative end (sEnd) and start minus exclusive prefix (sOff) in the warp's shared arrays
-__device__ __forceinline__ uint32_t gather_group_runs(const Grid& g, const CellIndex& ix, uint32_t ck, uint32_t klast,
+// (cx, cy, cz) = cell coordinates of the group's leader, xlast = x coordinate of its last cell: the callers keep the
+// coordinates of their own query's cell in registers (three integer divisions per QUERY instead of five per GROUP: at
+// small radius a warp forms several groups and the divisions were 11 % of the kernel's instructions)
+__device__ __forceinline__ uint32_t gather_group_runs(const Grid& g, const CellIndex& ix, int cx, int cy, int cz, int xlast,
                                                       int lane, uint32_t* sEnd, uint32_t* sOff) {
   constexpr int REACH = 1, W = 2 * REACH + 1, ROWS = W * W;
   const unsigned FULL = 0xffffffffu;
-  const uint32_t nxp = (uint32_t)g.nx, nyp = (uint32_t)g.ny;
-  const int cx = (int)(ck % nxp), cy = (int)((ck / nxp) % nyp), cz = (int)(ck / (nxp * nyp));
-  const int x0 = max(cx - REACH, 0), x1 = min((int)(klast % nxp) + REACH, g.nx - 1);
+  const int x0 = max(cx - REACH, 0), x1 = min(xlast + REACH, g.nx - 1);
   uint32_t rbeg = 0, rlen = 0;
   if (lane < ROWS && x0 <= x1) {
     const int z = cz + lane / W - REACH, y = cy + lane % W - REACH;
@@ -170,19 +171,24 @@ k_gather(PassDev* ps, CellIndex ix, MapSoA m, const uint32_t* __restrict__ qkey,
   uint32_t cnt = 0;
   bool deferred = false;                               // this lane's query was handed to k_gather_heavy
   unsigned long long tests = 0;                        // (candidates staged) x (lanes of the group): distance tests done
-  const uint32_t nxp = (uint32_t)g.nx;
+  const uint32_t nxp = (uint32_t)g.nx, nyp = (uint32_t)g.ny;
+  const uint32_t qrow = key / nxp;                       // this query's cell: row id and coordinates, computed once
+  const int qcx = (int)(key - qrow * nxp), qcy = (int)(qrow % nyp), qcz = (int)(qrow / nyp);
   unsigned pending = __ballot_sync(FULL, valid);
   while (pending) {
     const int leader = __ffs(pending) - 1;
     const uint32_t ck = __shfl_sync(FULL, key, leader);
+    const uint32_t row_l = __shfl_sync(FULL, qrow, leader);
+    const int cx = __shfl_sync(FULL, qcx, leader), cy = __shfl_sync(FULL, qcy, leader), cz = __shfl_sync(FULL, qcz, leader);
     // Group = the pending lanes whose cell lies in the leader's row (same cy, cz) at most
     // GATHER_SPAN cells to the right of the leader's cell (keys are sorted, x fastest).  They
     // share ONE candidate stream covering [cx_leader - R, cx_last + R]: a superset of every
     // lane's own neighbourhood, so the extra candidates simply fail the distance test.
-    bool act = valid && key >= ck && key - ck <= (uint32_t)GATHER_SPAN && key / nxp == ck / nxp;
+    bool act = valid && key >= ck && key - ck <= (uint32_t)GATHER_SPAN && qrow == row_l;
     unsigned grp = __ballot_sync(FULL, act);
-    uint32_t klast = __shfl_sync(FULL, key, 31 - __clz((int)grp));
-    uint32_t total = gather_group_runs(g, ix, ck, klast, lane, sEnd[warp], sOff[warp]);
+    const int last = 31 - __clz((int)grp);
+    uint32_t klast = __shfl_sync(FULL, key, last);
+    uint32_t total = gather_group_runs(g, ix, cx, cy, cz, __shfl_sync(FULL, qcx, last), lane, sEnd[warp], sOff[warp]);
     if (hl.ctr && total > GATHER_HEAVY_MIN && klast != ck) {
       // A heavy stream is split into parts by its length, and the parts fix the order in which a query's photons are
       // summed.  Narrow the group to the leader's cell alone: the stream, its split and therefore every sum then
@@ -191,7 +197,7 @@ k_gather(PassDev* ps, CellIndex ix, MapSoA m, const uint32_t* __restrict__ qkey,
       act = valid && key == ck;
       grp = __ballot_sync(FULL, act);
       klast = ck;
-      total = gather_group_runs(g, ix, ck, klast, lane, sEnd[warp], sOff[warp]);
+      total = gather_group_runs(g, ix, cx, cy, cz, cx, lane, sEnd[warp], sOff[warp]);
     }
     pending &= ~grp;
     if (hl.ctr && total > GATHER_HEAVY_MIN) {
@@ -231,8 +237,8 @@ k_gather(PassDev* ps, CellIndex ix, MapSoA m, const uint32_t* __restrict__ qkey,
   }
   {
     const unsigned c = __reduce_add_sync(FULL, cnt);
-    if (lane == 0 && c) atomicAdd(&ps->sum_k, (unsigned long long)c);
-    if (lane == 0 && tests) atomicAdd(&ps->cand, tests);
+    if (lane == 0 && c) atomicAdd(&ps->sum_k_s[blockIdx.x & (PPM_NSLOT - 1)], (unsigned long long)c);
+    if (lane == 0 && tests) atomicAdd(&ps->cand_s[blockIdx.x & (PPM_NSLOT - 1)], tests);
   }
 }
 
@@ -273,12 +279,14 @@ k_gather_heavy(PassDev* ps, CellIndex ix, MapSoA m, const uint32_t* __restrict__
       if (MODE != 2) hnv = ld3(qnrm3 + (uint64_t)hqi * 3);
       if (MODE != 0) hr2 = r2q[hqi];
     }
-    const uint32_t total = gather_group_runs(g, ix, h_ck, h_klast, lane, sEnd[warp], sOff[warp]);
+    const uint32_t hnx = (uint32_t)g.nx, hny = (uint32_t)g.ny;
+    const uint32_t total = gather_group_runs(g, ix, (int)(h_ck % hnx), (int)((h_ck / hnx) % hny), (int)(h_ck / (hnx * hny)), (int)(h_klast % hnx),
+                                             lane, sEnd[warp], sOff[warp]);
     double ar = 0.0, ag = 0.0, ab = 0.0;
     uint32_t ac = 0;
     const uint32_t staged = gather_chunks<FILTER, MODE>(m, total, (t - h_p0) * 32u, h_np * 32u, lane, hact, sEnd[warp], sOff[warp], sP[warp],
                                                         sD[warp], hx, hy, hz, hnv, hr2, power, ar, ag, ab, ac);
-    if (lane == 0 && staged) atomicAdd(&ps->cand, (unsigned long long)staged * (unsigned)__popc(h_grp));
+    if (lane == 0 && staged) atomicAdd(&ps->cand_s[blockIdx.x & (PPM_NSLOT - 1)], (unsigned long long)staged * (unsigned)__popc(h_grp));
     HeavyPartial* hp = hl.partials + t;
     __stcg(&hp->rgb[0][lane], ar); __stcg(&hp->rgb[1][lane], ag); __stcg(&hp->rgb[2][lane], ab); __stcg(&hp->cnt[lane], ac);
     __threadfence();
@@ -303,7 +311,7 @@ k_gather_heavy(PassDev* ps, CellIndex ix, MapSoA m, const uint32_t* __restrict__
     }
     {
       const unsigned c = __reduce_add_sync(FULL, hact ? tc : 0u);
-      if (lane == 0 && c) atomicAdd(&ps->sum_k, (unsigned long long)c);
+      if (lane == 0 && c) atomicAdd(&ps->sum_k_s[blockIdx.x & (PPM_NSLOT - 1)], (unsigned long long)c);
     }
   }
 }

@@ -52,6 +52,7 @@ __host__ __device__ inline Grid make_grid(const Bounds& b, int have_bounds, doub
 #define PPM_ST_REC_OVERFLOW 1u           // more photon records than the record buffers hold
 #define PPM_ST_NODE_OVERFLOW 2u          // more gather nodes than the node pool holds
 #define PPM_NSTAMP 16
+#define PPM_NSLOT 64
 struct PassDev {
   Grid grid;
   Bounds bounds;
@@ -63,8 +64,10 @@ struct PassDev {
   unsigned long long ticket;             // photon ticket of k_trace_photons
   unsigned long long n_nodes;            // gather nodes made by k_eye_expand (may exceed the capacity)
   unsigned long long n_visited;          // eye-path nodes visited
-  unsigned long long sum_k;              // sum over the queries of the photons within r
-  unsigned long long cand;               // candidates tested (32 x chunks x lanes active), diagnostics
+  unsigned long long sum_k;              // sum over the queries of the photons within r   (totals of the slots below,
+  unsigned long long cand;               // candidate distance tests of k_gather            made by k_pass_end / the probes)
+  unsigned long long sum_k_s[PPM_NSLOT]; // per-CTA-group slots: 170 k warps adding to ONE address serialise in L2
+  unsigned long long cand_s[PPM_NSLOT];
   uint32_t n_map;                        // photons in the map of this pass
   uint32_t n_query;                      // gather queries of this pass (= min(n_nodes, capacity))
   uint32_t n_occ_p, n_occ_q;             // occupied cells: photons, queries
@@ -106,6 +109,7 @@ __global__ void k_pass_begin(PassDev* ps, const BatchDev* __restrict__ bt) {
   ps->seed = bt->seed; ps->power = bt->power; ps->pass = bt->pass[i]; ps->r2 = bt->r2[i];
   ps->grid = make_grid(ps->bounds, ps->have_bounds, bt->r2[i]);
   ps->n_rec = 0ull; ps->ticket = 0ull; ps->n_nodes = 0ull; ps->n_visited = 0ull; ps->sum_k = 0ull; ps->cand = 0ull;
+  for (int k = 0; k < PPM_NSLOT; ++k) { ps->sum_k_s[k] = 0ull; ps->cand_s[k] = 0ull; }
   ps->n_map = 0u; ps->n_query = 0u; ps->n_occ_p = 0u; ps->n_occ_q = 0u;
   ps->heavy[0] = ps->heavy[1] = ps->heavy[2] = ps->heavy[3] = 0u;
   ps->status = 0u;
@@ -116,6 +120,7 @@ __global__ void k_pass_begin(PassDev* ps, const BatchDev* __restrict__ bt) {
 __global__ void k_pass_end(PassDev* ps, PassOut* __restrict__ out, double* __restrict__ npass_acc) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   ps->stamp[ST_END] = globaltimer_ns();
+  for (int k = 0; k < PPM_NSLOT; ++k) { ps->sum_k += ps->sum_k_s[k]; ps->cand += ps->cand_s[k]; }
   PassOut& o = out[ps->cursor % PPM_BATCH_MAX];
   o.n_rec = ps->n_rec; o.n_nodes = ps->n_nodes; o.n_visited = ps->n_visited; o.sum_k = ps->sum_k; o.cand = ps->cand;
   o.status = ps->status; o.n_occ_p = ps->n_occ_p; o.n_occ_q = ps->n_occ_q; o.heavy_parts = ps->heavy[3];
