@@ -392,7 +392,7 @@ int enq_build(ppm_ctx* c, cudaStream_t st, bool traced, uint64_t nphoton, uint64
 int enq_query_sort(ppm_ctx* c, cudaStream_t st, const double* qpos, uint64_t cap) {
   PassDev* ps = c->ps;
   IdxWord* words = c->words_q.as<IdxWord>();
-  const unsigned wide = (unsigned)c->sm_count * 8;
+  const unsigned wide = (unsigned)c->sm_count * 8;     // (one trip per thread, 5 k CTAs: k_query_mark 97 -> 153 us, more lanes on the same hot index words)
   k_index_clear<<<(unsigned)c->sm_count * 4, 256, 0, st>>>(ps, words);
   KCHECK(c);
   k_query_mark<<<wide, 256, 0, st>>>(ps, qpos, (uint32_t)cap, c->qcell.as<uint32_t>(), words, -1);

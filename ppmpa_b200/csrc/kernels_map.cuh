@@ -398,6 +398,7 @@ __global__ void k_map_scatter(PassDev* ps, RecBuf rec, const uint32_t* __restric
 }
 
 // ---- query side: counting sort by cell ---------------------------------------------------------------------------
+#define MAP_UNROLL 4
 __global__ void k_query_mark(PassDev* ps, const double* __restrict__ qpos3, uint32_t cap, uint32_t* __restrict__ qcell,
                              IdxWord* __restrict__ words, int stamp_slot) {
   stamp(ps, stamp_slot);
@@ -408,18 +409,44 @@ __global__ void k_query_mark(PassDev* ps, const double* __restrict__ qpos3, uint
     if (made > (unsigned long long)cap) atomicOr(&ps->status, PPM_ST_NODE_OVERFLOW);
   }
   const Grid g = ps->grid;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const uint32_t c = cell_of(g, qpos3[(uint64_t)i * 3], qpos3[(uint64_t)i * 3 + 1], qpos3[(uint64_t)i * 3 + 2]);
-    qcell[i] = c;
-    mark_cell(words, c);
+  // the kernel is a chain of memory round trips with a handful of instructions in between: four queries per thread
+  // and trip, all loads issued before the first use
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += MAP_UNROLL * stride) {
+    double x[MAP_UNROLL], y[MAP_UNROLL], z[MAP_UNROLL];
+#pragma unroll
+    for (int k = 0; k < MAP_UNROLL; ++k) {
+      const uint32_t i = i0 + (uint32_t)k * stride;
+      if (i < n) { x[k] = qpos3[(uint64_t)i * 3]; y[k] = qpos3[(uint64_t)i * 3 + 1]; z[k] = qpos3[(uint64_t)i * 3 + 2]; }
+    }
+#pragma unroll
+    for (int k = 0; k < MAP_UNROLL; ++k) {
+      const uint32_t i = i0 + (uint32_t)k * stride;
+      if (i < n) {
+        const uint32_t c = cell_of(g, x[k], y[k], z[k]);
+        qcell[i] = c;
+        mark_cell(words, c);
+      }
+    }
   }
 }
 // one atomic per query: its position inside its cell (any order: a query's sum runs in map order wherever it sits)
 __global__ void k_query_count(const PassDev* __restrict__ ps, const uint32_t* __restrict__ qcell, const IdxWord* __restrict__ words,
                               uint32_t* __restrict__ cnt, uint32_t* __restrict__ qrank, uint32_t* __restrict__ qpos_in_cell) {
   const uint32_t n = ps->n_query;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const uint32_t r = cell_rank(words, qcell[i]);
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += MAP_UNROLL * stride) {
+   uint32_t rk[MAP_UNROLL];
+#pragma unroll
+   for (int k = 0; k < MAP_UNROLL; ++k) {               // the look-ups of the trip's queries first (independent round trips)
+     const uint32_t i = i0 + (uint32_t)k * stride;
+     rk[k] = i < n ? cell_rank(words, qcell[i]) : 0u;
+   }
+#pragma unroll
+   for (int k = 0; k < MAP_UNROLL; ++k) {
+    const uint32_t i = i0 + (uint32_t)k * stride;
+    if (i >= n) continue;
+    const uint32_t r = rk[k];
     qrank[i] = r;
     // neighbouring nodes come from neighbouring pixels and mostly share a cell: one atomic per distinct cell of the warp
     const unsigned act = __activemask();
@@ -429,16 +456,31 @@ __global__ void k_query_count(const PassDev* __restrict__ ps, const uint32_t* __
     if ((int)(threadIdx.x & 31u) == leader) base = atomicAdd(&cnt[r], (uint32_t)__popc(peers));
     base = __shfl_sync(peers, base, leader);
     qpos_in_cell[i] = base + (uint32_t)__popc(peers & ((1u << (threadIdx.x & 31u)) - 1u));
+   }
   }
 }
 __global__ void k_query_scatter(const PassDev* __restrict__ ps, const uint32_t* __restrict__ qcell, const uint32_t* __restrict__ qrank,
                                 const uint32_t* __restrict__ qpos_in_cell, const uint32_t* __restrict__ start,
                                 uint32_t* __restrict__ skey, uint32_t* __restrict__ sidx) {
   const uint32_t n = ps->n_query;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const uint32_t s = start[qrank[i]] + qpos_in_cell[i];
-    skey[s] = qcell[i];
-    sidx[s] = i;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += MAP_UNROLL * stride) {
+    uint32_t r[MAP_UNROLL], pic[MAP_UNROLL], cell[MAP_UNROLL], st[MAP_UNROLL];
+#pragma unroll
+    for (int k = 0; k < MAP_UNROLL; ++k) {
+      const uint32_t i = i0 + (uint32_t)k * stride;
+      if (i < n) { r[k] = qrank[i]; pic[k] = qpos_in_cell[i]; cell[k] = qcell[i]; }
+    }
+#pragma unroll
+    for (int k = 0; k < MAP_UNROLL; ++k) {
+      const uint32_t i = i0 + (uint32_t)k * stride;
+      if (i < n) st[k] = __ldg(start + r[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < MAP_UNROLL; ++k) {
+      const uint32_t i = i0 + (uint32_t)k * stride;
+      if (i < n) { const uint32_t s = st[k] + pic[k]; skey[s] = cell[k]; sidx[s] = i; }
+    }
   }
 }
 
