@@ -376,7 +376,8 @@ def run_gpu(args):
         achieved = alg_bytes / gather_s / 1e9
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "gather_traffic.json"))).get("dram_bytes_per_launch")
+            if XRES == 1920:                             # the ncu capture is of this workload (profiles/gather_traffic.json says which launch)
+                traffic = json.load(open(os.path.join(ROOT, "profiles", "gather_traffic.json"))).get("dram_bytes_per_launch")
         except (OSError, ValueError):
             pass
         # what actually limits k_gather: FP64 issue.  Lane-ops counted: 8 per candidate distance test (3 sub, 3 mul, 2 add)

@@ -139,8 +139,15 @@ __device__ __forceinline__ uint32_t gather_chunks(const MapSoA& m, uint32_t tota
 // membership, filter rmax and normaliser all use the query's own radius).  MODE 2: count only,
 // members are d2 <= r2q[] (the bisection steps of the k-NN radius search).
 // The number of queries, the grid, the radius and the photon power come from the pass state.
+// 56 registers without a min-blocks hint (9 CTAs per SM).  Measured: 48 registers / 10 CTAs: k_gather 0.594 -> 0.639 ms
+// at r = 0.019 and 2.05 -> 2.33 ms at r = 0.1; 40 / 12: 0.670 and 2.66 ms; a hint of 1 makes ptxas take 80 registers
+// (0.635 ms) -- gpurun_out/r2r_gather_minb.txt
 template <int FILTER, int MODE>
+#ifdef GATHER_MINB
+__global__ void __launch_bounds__(GATHER_WARPS * 32, GATHER_MINB)
+#else
 __global__ void __launch_bounds__(GATHER_WARPS * 32)
+#endif
 k_gather(PassDev* ps, CellIndex ix, MapSoA m, const uint32_t* __restrict__ qkey,
          const uint32_t* __restrict__ qidx, const double* __restrict__ qpos3, const double* __restrict__ qnrm3,
          const double* __restrict__ r2q, double* __restrict__ rgb3, uint32_t* __restrict__ counts, HeavyList hl, int stamp_slot) {
