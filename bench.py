@@ -218,6 +218,29 @@ class ClockSampler:
         return out
 
 
+def pin_to_gpu_numa_node(index):
+    """Run this rank's host threads (and first-touch its pinned buffers) on the CPUs next to its GPU: with 8 ranks the
+    per-step image read-back (50 MB) otherwise crosses the socket interconnect for half of the GPUs.  Best effort."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(index)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        cpus = set()
+        for part in open(f"/sys/bus/pci/devices/{bdf}/local_cpulist").read().strip().split(","):
+            if not part:
+                continue
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if cpus and cpus != allowed:
+            os.sched_setaffinity(0, cpus)
+            return sorted(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def run_gpu(args):
     # libraries (NCCL's version banner ...) may write to fd 1: keep stdout for the ONE JSON line
     sys.stdout.flush()
@@ -237,6 +260,7 @@ def run_gpu(args):
         raise SystemExit("bench.py needs a CUDA device (the engine has no CPU path)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    host_cpus = pin_to_gpu_numa_node(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     eng = P.Engine(local)
@@ -420,7 +444,8 @@ def run_gpu(args):
                 "ms_per_step": t_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": base_config(world), "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "checksum": checksum, "host_threads_per_gpu": E2E_LANES},
+                        "checksum": checksum, "host_threads_per_gpu": E2E_LANES,
+                        "host_cpus_per_rank": len(host_cpus) if host_cpus else None},
                 "gpu_launches": counts["launches"], "roofline": roofline, "cpu_baseline": cpu,
                 "passes_accumulated_on_rank0_after_reduce": n_acc,
                 "passes_retried_after_overflow": counts["retried"],

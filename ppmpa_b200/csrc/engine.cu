@@ -201,6 +201,10 @@ int finish_out(ppm_ctx* c, void* user, size_t bytes, void* dev) {
 }
 inline unsigned nblk(int64_t n, int b) { return (unsigned)std::max<int64_t>(1, (n + b - 1) / b); }
 
+// (Sleeping on a blocking-sync event instead of cudaStreamSynchronize was measured for the end-of-batch and read-back
+// waits: e2e -2 % on one GPU, no gain with 8 ranks x 4 host threads on 32 cores -- profiles/r2b_bench_n8.json.)
+cudaError_t wait_stream(ppm_ctx*, cudaStream_t st) { return cudaStreamSynchronize(st); }
+
 // host mirror <-> device pass state (probe entry points; a rendered pass never does this)
 int push_ps(ppm_ctx* c) {
   CK(c, cudaMemcpyAsync(c->ps, &c->hps, sizeof(PassDev), cudaMemcpyHostToDevice, c->stream));
@@ -208,7 +212,7 @@ int push_ps(ppm_ctx* c) {
 }
 int pull_ps(ppm_ctx* c) {
   CK(c, cudaMemcpyAsync(&c->hps, c->ps, sizeof(PassDev), cudaMemcpyDeviceToHost, c->stream));
-  CK(c, cudaStreamSynchronize(c->stream));
+  CK(c, wait_stream(c, c->stream));
   return PPM_OK;
 }
 
@@ -981,7 +985,7 @@ int run_passes(ppm_ctx* c, std::vector<ppm_ctx*>& lane, const std::vector<int32_
     }
     for (int j = 0; j < lanes; ++j) {
       if (!cnt[j]) continue;
-      cudaError_t e = cudaStreamSynchronize(lane[j]->stream);
+      cudaError_t e = wait_stream(lane[j], lane[j]->stream);
       if (e != cudaSuccess) return fail(c, PPM_ERR_CUDA, std::string("pass batch: ") + cudaGetErrorString(e));
     }
     std::vector<int> pos(lanes, 0);
@@ -1588,7 +1592,7 @@ int ppm_last_pass_timeline(ppm_ctx* c, double ms_since_begin[16]) {
 
 static int copy_out(ppm_ctx* c, void* user, const void* dev, size_t bytes) {
   CK(c, cudaMemcpyAsync(user, dev, bytes, is_device_ptr(user) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->stream));
-  CK(c, cudaStreamSynchronize(c->stream));
+  CK(c, wait_stream(c, c->stream));
   return PPM_OK;
 }
 
