@@ -32,8 +32,9 @@ __device__ __forceinline__ double filter_gauss(double d, double rmax) {
 #define GATHER_WARPS 4
 #endif
 #ifndef GATHER_SPAN
-#define GATHER_SPAN 3        // a group may span cells cx .. cx+3 of one row
+#define GATHER_SPAN 4        // a group may span cells cx .. cx+4 of one row (3: logical 0.586 -> 0.596 over the north-star schedule, 5: 0.596)
 #endif
+
 // A group whose candidate stream is longer than GATHER_HEAVY_MIN is not processed by its warp alone: the warp
 // publishes it as S = ceil(total / GATHER_HEAVY_MIN) (<= 64) independent PARTS in a device-side list; part k takes the
 // 32-candidate chunks k, k + S, k + 2S, ... of the stream.  k_gather_heavy (launched only when the list is not empty)
