@@ -594,6 +594,7 @@ int do_map_build(ppm_ctx* c, double radius2, bool fresh_bounds) {
   }
   c->hps.r2 = radius2; c->hps.power = c->power;
   c->hps.grid = make_grid(c->hps.bounds, c->hps.have_bounds, radius2);
+  c->hps.inv_pi_r2 = (1.0 / PPM_PI) / radius2;
   c->hps.n_rec = n; c->hps.n_map = c->rec_traced ? 0u : (uint32_t)n;
   c->hps.n_occ_p = 0u; c->hps.status = 0u;
   RC(ensure_build(c, n, c->rec_traced ? c->rec_nphoton : 0));

@@ -180,8 +180,9 @@ k_gather(PassDev* ps, CellIndex ix, MapSoA m, const uint32_t* __restrict__ qkey,
   bool deferred = false;                               // this lane's query was handed to k_gather_heavy
   unsigned long long tests = 0;                        // (candidates staged) x (lanes of the group): distance tests done
   const uint32_t nxp = (uint32_t)g.nx, nyp = (uint32_t)g.ny;
-  const uint32_t qrow = key / nxp;                       // this query's cell: row id and coordinates, computed once
-  const int qcx = (int)(key - qrow * nxp), qcy = (int)(qrow % nyp), qcz = (int)(qrow / nyp);
+  const uint32_t qrow = grid_div(key, g.mx, g.sx1, g.sx2);   // this query's cell: row id and coordinates, computed once
+  const uint32_t qzc = grid_div(qrow, g.my, g.sy1, g.sy2);
+  const int qcx = (int)(key - qrow * nxp), qcy = (int)(qrow - qzc * nyp), qcz = (int)qzc;
   unsigned pending = __ballot_sync(FULL, valid);
   while (pending) {
     const int leader = __ffs(pending) - 1;
@@ -238,7 +239,7 @@ k_gather(PassDev* ps, CellIndex ix, MapSoA m, const uint32_t* __restrict__ qkey,
   }
   if (valid && !deferred) {
     if (MODE != 2) {
-      const double sc = (1.0 / PPM_PI) / r2;          // rad * (ONE_PI / radius), tracer.rs:193
+      const double sc = MODE == 0 ? ps->inv_pi_r2 : (1.0 / PPM_PI) / r2;   // rad * (ONE_PI / radius), tracer.rs:193
       rgb3[(uint64_t)qi * 3] = rr * sc; rgb3[(uint64_t)qi * 3 + 1] = rg * sc; rgb3[(uint64_t)qi * 3 + 2] = rb * sc;
     }
     if (counts) counts[qi] = cnt;

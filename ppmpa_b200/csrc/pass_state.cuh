@@ -13,7 +13,22 @@ struct Grid {
   double inv_cell;
   int32_t nx, ny, nz;
   uint32_t ncells;
+  uint32_t mx, sx1, sx2, my, sy1, sy2;   // exact division of a cell id by nx / ny without a divide (grid_div)
 };
+// Division of a 32-bit value by an invariant divisor (Granlund-Montgomery, branch free): q = (t + ((n - t) >> s1)) >> s2
+// with t = mulhi(m, n).  k_gather splits every query's cell id into coordinates; two of these replace three hardware
+// integer divisions (~60 instructions) per query.
+__host__ __device__ inline void grid_div_init(uint32_t d, uint32_t& m, uint32_t& s1, uint32_t& s2) {
+  uint32_t l = 0;
+  while ((1ull << l) < (unsigned long long)d) ++l;
+  m = (uint32_t)((((1ull << l) - (unsigned long long)d) << 32) / (unsigned long long)d + 1ull);
+  s1 = l < 1u ? l : 1u;
+  s2 = l > 0u ? l - 1u : 0u;
+}
+__device__ __forceinline__ uint32_t grid_div(uint32_t n, uint32_t m, uint32_t s1, uint32_t s2) {
+  const uint32_t t = __umulhi(m, n);
+  return (t + ((n - t) >> s1)) >> s2;
+}
 struct Bounds { double lo[3], hi[3]; };
 #define PPM_CELL_CAP 67108864.0          // 2^26 cells: 2^20 index words = 16 MB
 #define PPM_CELL_CAP_WORDS ((1u << 20) + 2u)
@@ -29,6 +44,7 @@ __host__ __device__ inline Grid make_grid(const Bounds& b, int have_bounds, doub
   double cell = sqrt(radius2) * (1.0 + 1.0 / 1024.0);
   g.org[0] = g.org[1] = g.org[2] = 0.0;
   g.nx = g.ny = g.nz = 1; g.inv_cell = 1.0 / cell; g.ncells = 1;
+  grid_div_init(1u, g.mx, g.sx1, g.sx2); grid_div_init(1u, g.my, g.sy1, g.sy2);
   if (!have_bounds) return g;
   for (int it = 0; it < 64; ++it) {
     double dims[3];
@@ -43,6 +59,7 @@ __host__ __device__ inline Grid make_grid(const Bounds& b, int have_bounds, doub
   for (int k = 0; k < 3; ++k) g.org[k] = b.lo[k] - 0.5 * cell;
   g.inv_cell = 1.0 / cell;
   g.ncells = (uint32_t)g.nx * (uint32_t)g.ny * (uint32_t)g.nz;
+  grid_div_init((uint32_t)g.nx, g.mx, g.sx1, g.sx2); grid_div_init((uint32_t)g.ny, g.my, g.sy1, g.sy2);
   return g;
 }
 
@@ -60,6 +77,7 @@ struct PassDev {
   uint32_t pass;                         // Philox pass id of this pass
   uint64_t seed;
   double r2, power;
+  double inv_pi_r2;                      // (1 / pi) / r2: the normaliser of the fixed-radius estimate (tracer.rs:193), once per pass
   unsigned long long n_rec;              // photon records appended by the tracer (may exceed the capacity)
   unsigned long long ticket;             // photon ticket of k_trace_photons
   unsigned long long n_nodes;            // gather nodes made by k_eye_expand (may exceed the capacity)
@@ -108,6 +126,7 @@ __global__ void k_pass_begin(PassDev* ps, const BatchDev* __restrict__ bt) {
   const uint32_t i = ps->cursor % PPM_BATCH_MAX;
   ps->seed = bt->seed; ps->power = bt->power; ps->pass = bt->pass[i]; ps->r2 = bt->r2[i];
   ps->grid = make_grid(ps->bounds, ps->have_bounds, bt->r2[i]);
+  ps->inv_pi_r2 = (1.0 / PPM_PI) / bt->r2[i];
   ps->n_rec = 0ull; ps->ticket = 0ull; ps->n_nodes = 0ull; ps->n_visited = 0ull; ps->sum_k = 0ull; ps->cand = 0ull;
   for (int k = 0; k < PPM_NSLOT; ++k) { ps->sum_k_s[k] = 0ull; ps->cand_s[k] = 0ull; }
   ps->n_map = 0u; ps->n_query = 0u; ps->n_occ_p = 0u; ps->n_occ_q = 0u;
