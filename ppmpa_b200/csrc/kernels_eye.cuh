@@ -9,7 +9,11 @@
 // ---- camera ---------------------------------------------------------------------
 __device__ __forceinline__ void camera_ray(const ppm_camera& cam, int64_t pix, uint64_t seed, uint32_t pass, D3& pos, D3& dir) {
   Philox rng(seed, pass, PPM_DOMAIN_EYE, (uint64_t)pix, 0);
-  double y = (double)(pix / cam.xreso), x = (double)(pix % cam.xreso);
+  // (32-bit division when the pixel index allows it: the 64-bit one is a ~100-instruction subroutine per pixel)
+  int64_t py, px;
+  if (pix >= 0 && pix < (int64_t)0x7fffffff) { const uint32_t q = (uint32_t)pix / (uint32_t)cam.xreso; py = q; px = (int64_t)((uint32_t)pix - q * (uint32_t)cam.xreso); }
+  else { py = pix / cam.xreso; px = pix % cam.xreso; }
+  double y = (double)py, x = (double)px;
   D3 blur = mk3(0.0, 0.0, 0.0);
   if (cam.blur) {
     double r1 = rng.range(-0.5, 0.5);
