@@ -352,6 +352,9 @@ __device__ __forceinline__ double ts5(unsigned i) {   // the literals 0.1, 0.3, 
 #ifndef PPM_DL_MINB
 #define PPM_DL_MINB 8
 #endif
+#ifndef PPM_DL_STRAIGHT
+#define PPM_DL_STRAIGHT 1
+#endif
 __global__ void __launch_bounds__(128, PPM_DL_MINB)
 k_direct_light(const __grid_constant__ DevScene sc, PassDev* ps, uint32_t cap, const unsigned long long* __restrict__ masks,
                const uint32_t* __restrict__ order, const double* __restrict__ pos3, const double* __restrict__ nrm3,
@@ -421,6 +424,33 @@ k_direct_light(const __grid_constant__ DevScene sc, PassDev* ps, uint32_t cap, c
       const double C = (2.0 * l.flux * 0.2 * 0.2) / (PPM_PI * 4.0);   // 2 * flux * PARA_DIV^2 / (4 pi), light.rs:142
       double acc = 0.0, inv_prev = 0.0;
       bool have_prev = false;
+#if PPM_DL_STRAIGHT
+      if (!need_ld) {
+        // No node of the warp has a primitive to test (two thirds of the warps in cell-sorted order): the same samples,
+        // decisions and operations as the loop below, but as straight-line selects, so that the reciprocal chains of
+        // consecutive samples overlap instead of waiting behind the `continue` branches.
+#pragma unroll 5
+        for (unsigned s = 0; s < 25; ++s) {
+          const D3 d = mk3(s_gp[s][0], s_gp[s][1], s_gp[s][2]) - p;
+          const double dd = dot(d, d);
+          const double b = dot(nv, d);
+          bool ok = cert && dd != 0.0 && (side != 0 || dot(lnv, d) < 0.0);
+          const double inv = 1.0 / dd;
+          double cc = (b * b) * inv;
+          if (b * b > nn_thr * dd) {
+            ok = ok && !(b < 0.0);
+          } else if (ok) {                                    // grazing: the reference's own cos0 (rare)
+            D3 ld = d;
+            normalize(d, ld);
+            const double cos0 = dot(nv, ld);
+            ok = !(cos0 < 0.0);
+            cc = cos0 * cos0;
+          }
+          if (ok && have_prev) acc = acc + inv_prev * cc;
+          if (ok) { have_prev = true; inv_prev = inv; }
+        }
+      } else
+#endif
       for (unsigned s = 0; s < 25; ++s) {
         const D3 gp = mk3(s_gp[s][0], s_gp[s][1], s_gp[s][2]);
         const D3 d = gp - p;
