@@ -202,14 +202,25 @@ void* ppm_stream(ppm_ctx* ctx);
  *   "gather_heavy"  1 = split very long candidate streams over many warps (changes only the summation order)
  *   "dl_stats"      1 = print culling statistics to stderr
  *   "graph"         1 = whole passes run as CUDA graphs without host round trips (default), 0 = stream mode
+ *   "bvh"           1 = the NEXT ppm_scene_set indexes the bounded primitives with a bounding-volume hierarchy even
+ *                   for a scene of <= 64 primitives (bit-identical hits; larger scenes always use it)
  * Unknown names return PPM_ERR_ARG. */
 int  ppm_option_set(ppm_ctx* ctx, const char* name, int64_t value);
 int  ppm_option_get(ppm_ctx* ctx, const char* name, int64_t* value);
 
-/* replaces the (lgts, objs) pair read_scene returns, scene.rs:443-447 */
+/* replaces the (lgts, objs) pair read_scene returns, scene.rs:443-447.
+ * Up to 64 primitives every ray tests every object, as calc_intersection does (tracer.rs:306-350).  Larger scenes
+ * (at most 64 infinite planes, 2^26 bounded primitives, 48 materials, 8 lights) are indexed by a bounding-volume
+ * hierarchy built here, on the host, once per scene; the traversal culls with padded boxes and tests the remaining
+ * candidates with the same arithmetic and tie rule, so hit indices and distances are the brute-force scan's. */
 int  ppm_scene_set(ppm_ctx* ctx, const ppm_prim* prims, int32_t nprims,
                    const ppm_material* mats, int32_t nmats,
                    const ppm_light* lights, int32_t nlights);
+/* Host-only inspection of the hierarchy ppm_scene_set builds for a scene in BVH mode: node and leaf-primitive counts,
+ * depth, SAH cost relative to the root box, and a self-check (PPM_ERR_STATE unless every bounded primitive sits in
+ * exactly one leaf, strictly inside every box on its path, and the depth fits the traversal stack). */
+int  ppm_bvh_inspect(const ppm_prim* prims, int32_t nprims, int64_t* n_nodes, int64_t* n_leaf_prims,
+                     int32_t* depth, double* sah_cost);
 /* replaces the Camera read_camera returns, camera.rs:176-204 */
 int  ppm_camera_set(ppm_ctx* ctx, const ppm_camera* cam);
 

@@ -102,6 +102,7 @@ SIGNATURES = {
     "ppm_option_set": (C.c_int, [vp, C.c_char_p, i64]),
     "ppm_option_get": (C.c_int, [vp, C.c_char_p, P(i64)]),
     "ppm_scene_set": (C.c_int, [vp, P(Prim), i32, P(Material), i32, P(Light), i32]),
+    "ppm_bvh_inspect": (C.c_int, [P(Prim), i32, P(C.c_int64), P(C.c_int64), P(i32), P(dbl)]),
     "ppm_camera_set": (C.c_int, [vp, P(Camera)]),
     "ppm_intersect": (C.c_int, [vp, vp, i64, vp, vp, vp, vp, vp]),
     "ppm_trace_photons": (C.c_int, [vp, u64, u32, C.c_int, P(i64), dbl, P(u64)]),

@@ -10,6 +10,7 @@
 #define PPM_DEV_CORE_CUH_
 
 #include "../../include/ppm.h"
+#include "bvh_types.h"
 
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -25,12 +26,21 @@
 // primitive loops are warp-uniform, so every read is a constant-cache broadcast.
 // primitives by shape (bit o = primitive o); nwords = 1 if the scene has <= 32 primitives
 struct PrimMasks { unsigned long long plain, sphere, poly, para; int nwords, _pad; };
+//
+// BVH mode (bvh_on; scenes beyond PPM_MAX_PRIMS primitives, or the "bvh" option): `prims` holds only the scene's
+// infinite planes (nprims of them, unb_obj[] = their object indices), the bounded primitives are reached through the
+// hierarchy in device memory (bvh.cuh) and `gprims` is the whole primitive array in object order.
 struct DevScene {
-  int32_t nprims, nmats, nlights, _pad;
+  int32_t nprims, nmats, nlights, bvh_on;
   ppm_prim prims[PPM_MAX_PRIMS];
   ppm_material mats[PPM_MAX_MATS];
   ppm_light lights[PPM_MAX_LIGHTS];
   PrimMasks types;                 // filled by ppm_scene_set
+  const BvhNode* bvh;              // node 0 = root; nullptr when the scene has no bounded primitive
+  const BvhPrim* bprims;           // leaf order
+  const ppm_prim* gprims;          // [nprims_total], object order
+  int32_t nprims_total, _pad;
+  int32_t unb_obj[PPM_MAX_PRIMS];
 };
 static_assert(sizeof(DevScene) < 32000, "scene must fit the kernel parameter space");
 
@@ -192,6 +202,18 @@ __device__ __forceinline__ void consider_polygon(double l, D3 p0, D3 d1, D3 d2, 
   consider_ratio(c, det, o, best_t, best_o);
 }
 
+// geometry.rs:179-193
+__device__ __forceinline__ void consider_sphere(D3 center, double rad, D3 pos, D3 dir, int o, double& best_t, int& best_o) {
+  D3 oc = center - pos;
+  double t0 = dot(oc, dir);
+  double t1 = rad * rad - (dot(oc, oc) - (t0 * t0));
+  if (t1 > 0.0) {
+    double t2 = sqrt(t1);
+    if (t2 == 0.0) consider(t0, o, best_t, best_o);
+    else { consider(t0 - t2, o, best_t, best_o); consider(t0 + t2, o, best_t, best_o); }
+  }
+}
+
 #define PPM_FOR_EACH_BIT(mask64, o)                                                        \
   if (mask64) _Pragma("unroll 1") for (int w__ = 0; w__ < pm.nwords; ++w__)                \
     for (unsigned m__ = (unsigned)((mask64) >> (32 * w__)), o = 0; m__ && ((o = __ffs(m__) - 1 + 32 * w__), true); m__ &= m__ - 1)
@@ -215,26 +237,27 @@ __device__ __forceinline__ void scan_prims(const DevScene& sc, const PrimMasks& 
   PPM_FOR_EACH_BIT(pm.sphere, o) {
     // geometry.rs:179-193
     const ppm_prim& s = sc.prims[o];
-    D3 oc = ld3(s.position) - pos;
-    double t0 = dot(oc, dir);
-    double rad = s.scalar;
-    double t1 = rad * rad - (dot(oc, oc) - (t0 * t0));
-    if (t1 > 0.0) {
-      double t2 = sqrt(t1);
-      if (t2 == 0.0) consider(t0, (int)o, best_t, best_o);
-      else { consider(t0 - t2, (int)o, best_t, best_o); consider(t0 + t2, (int)o, best_t, best_o); }
-    }
+    consider_sphere(ld3(s.position), s.scalar, pos, dir, (int)o, best_t, best_o);
   }
 }
 
+#include "bvh.cuh"
+
 // Nearest hit: calc_intersection, tracer.rs:306-350.  Every object is tested; roots with t >= NEARLY0
 // are kept and the reference stable-sorts by t and takes the first.
+// BVH = true (a scene in BVH mode): the planes from the constant list, then the hierarchy; same candidates' arithmetic,
+// same tie rule on the object index, so the result is the brute-force scan's.
+template <bool BVH = false>
 __device__ __forceinline__ bool nearest_hit(const DevScene& sc, D3 pos, D3 dir, Isect& is) {
   double best_t = 0.0;
   int best_o = -1;
   scan_prims(sc, sc.types, pos, dir, best_t, best_o);
+  if (BVH) {
+    if (best_o >= 0) best_o = sc.unb_obj[best_o];          // plane order = object order, so ties among planes were right
+    bvh_traverse(sc, pos, dir, best_t, best_o);
+  }
   if (best_o < 0) return false;
-  const ppm_prim& s = sc.prims[best_o];
+  const ppm_prim& s = BVH ? sc.gprims[best_o] : sc.prims[best_o];
   D3 p = pos + dir * best_t;            // Ray::target, geometry.rs:56-58
   D3 n;
   if (s.type == PPM_SHAPE_SPHERE) {
@@ -246,6 +269,23 @@ __device__ __forceinline__ bool nearest_hit(const DevScene& sc, D3 pos, D3 dir, 
   if (dot(n, dir) > 0.0) { is.nvec = -n; is.io = 1; }
   else { is.nvec = n; is.io = 0; }
   return true;
+}
+// Shadow ray of a scene in BVH mode: what `illuminated` (tracer.rs:272-290) consumes of calc_intersection.
+// Returns 0 = nothing hit, 1 = hit (hit_pos set), 2 = calc_intersection is None because get_normal failed.
+__device__ __forceinline__ int nearest_hit_pos_bvh(const DevScene& sc, D3 pos, D3 dir, D3& hit_pos) {
+  double best_t = 0.0;
+  int best_o = -1;
+  scan_prims(sc, sc.types, pos, dir, best_t, best_o);
+  if (best_o >= 0) best_o = sc.unb_obj[best_o];
+  bvh_traverse(sc, pos, dir, best_t, best_o);
+  if (best_o < 0) return 0;
+  hit_pos = pos + dir * best_t;
+  const ppm_prim& s = sc.gprims[best_o];
+  if (s.type == PPM_SHAPE_SPHERE) {
+    D3 n;
+    if (!normalize(hit_pos - ld3(s.position), n)) return 2;
+  }
+  return 1;
 }
 
 // Shadow-ray variant for k_direct_light: only the primitives in `pm` (the conservative per-node

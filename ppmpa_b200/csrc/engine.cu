@@ -33,8 +33,13 @@
 #include <cstdlib>
 #include <cstdio>
 #include <cstring>
+#include <memory>
 #include <string>
 #include <vector>
+
+namespace ppmhost {   // host_bvh.cpp
+bool bvh_build(const ppm_prim* prims, int64_t n, std::vector<BvhNode>& out_nodes, std::vector<BvhPrim>& out_prims, int* depth, std::string& err);
+}
 
 // ===========================================================================
 // context
@@ -87,7 +92,14 @@ struct ppm_ctx {
   DevScene scene;
   ppm_camera cam;
   // switches (ppm_option_set; initial values from the environment, read once at ppm_create)
-  int opt_lanes = PPM_DEFAULT_LANES, opt_dl_cull = 1, opt_gather_heavy = 1, opt_dl_stats = 0, opt_graph = 1;
+  int opt_lanes = PPM_DEFAULT_LANES, opt_dl_cull = 1, opt_gather_heavy = 1, opt_dl_stats = 0, opt_graph = 1, opt_bvh = 0;
+  // the scene as handed in (BVH mode keeps it to recognise "the same scene again") and its hierarchy (bvh_types.h)
+  std::vector<ppm_prim> h_prims;
+  std::vector<ppm_material> h_mats;
+  std::vector<ppm_light> h_lights;
+  DBuf bvh_nodes, bvh_prims, g_prims;
+  uint64_t bvh_nnodes = 0, bvh_nprims = 0;
+  int bvh_depth = 0;
   // pass state: device copy, host mirror (probe entry points), batch table and per-pass reports
   PassDev* ps = nullptr;
   PassDev hps;
@@ -323,7 +335,7 @@ int upload_cull(ppm_ctx* c) {
   return PPM_OK;
 }
 // culling is possible when switched on ("dl_cull") and bit 63 of the masks is free for the certificate
-bool cull_on(const ppm_ctx* c) { return c->opt_dl_cull && c->scene.nprims <= 63 && c->scene.nlights > 0; }
+bool cull_on(const ppm_ctx* c) { return c->opt_dl_cull && !c->scene.bvh_on && c->scene.nprims <= 63 && c->scene.nlights > 0; }
 
 // ---- enqueue helpers: launches only, sizes come from PassDev, nothing waits for the host ------------------------
 template <class Op>
@@ -348,7 +360,8 @@ int enq_trace(ppm_ctx* c, cudaStream_t st, const LightSplit& ls, int64_t total, 
   if (total <= 0) return PPM_OK;
   // persistent grid: enough CTAs to fill every SM (resident CTAs are limited by registers), never more threads than photons
   const unsigned blocks = (unsigned)std::min<int64_t>((total + 127) / 128, (int64_t)c->sm_count * 8);
-  k_trace_photons<<<blocks, 128, 0, st>>>(c->scene, ls, c->ps, uc, total, recbuf(c), (unsigned long long)cap, c->pmask.as<uint32_t>());
+  if (c->scene.bvh_on) k_trace_photons<true><<<blocks, 128, 0, st>>>(c->scene, ls, c->ps, uc, total, recbuf(c), (unsigned long long)cap, c->pmask.as<uint32_t>());
+  else k_trace_photons<false><<<blocks, 128, 0, st>>>(c->scene, ls, c->ps, uc, total, recbuf(c), (unsigned long long)cap, c->pmask.as<uint32_t>());
   KCHECK(c);
   return PPM_OK;
 }
@@ -471,7 +484,8 @@ int enq_dl_classify(ppm_ctx* c, cudaStream_t st, const double* dpos, const doubl
 }
 int enq_direct_light(ppm_ctx* c, cudaStream_t st, const double* dpos, const double* dnrm, uint64_t cap, double* dout,
                      const unsigned long long* masks, const uint32_t* order, unsigned long long* dbg, int stamp_slot) {
-  k_direct_light<<<nblk((int64_t)cap, 128), 128, 0, st>>>(c->scene, c->ps, (uint32_t)cap, masks, order, dpos, dnrm, dout, dbg, stamp_slot);
+  if (c->scene.bvh_on) k_direct_light<true><<<nblk((int64_t)cap, 128), 128, 0, st>>>(c->scene, c->ps, (uint32_t)cap, nullptr, order, dpos, dnrm, dout, dbg, stamp_slot);
+  else k_direct_light<false><<<nblk((int64_t)cap, 128), 128, 0, st>>>(c->scene, c->ps, (uint32_t)cap, masks, order, dpos, dnrm, dout, dbg, stamp_slot);
   KCHECK(c);
   return PPM_OK;
 }
@@ -668,8 +682,10 @@ int probe_eye_expand(ppm_ctx* c, const double* drays, int64_t n, int64_t first_p
     RC(ensure_eye(c, (uint64_t)n, c->eye_cap));
     c->hps.seed = seed; c->hps.pass = pass; c->hps.n_nodes = 0ull; c->hps.n_visited = 0ull; c->hps.status = 0u;
     RC(push_ps(c));
-    k_eye_expand<<<nblk(n, 128), 128, 0, c->stream>>>(c->scene, c->cam, drays, n, first_pixel, c->ps, eyenodes(c), (uint32_t)c->eye_cap,
-                                                     c->e_head.as<uint32_t>(), c->e_emit.as<double>(), classic, -1);
+    if (c->scene.bvh_on) k_eye_expand<true><<<nblk(n, 128), 128, 0, c->stream>>>(c->scene, c->cam, drays, n, first_pixel, c->ps, eyenodes(c), (uint32_t)c->eye_cap,
+                                                                                c->e_head.as<uint32_t>(), c->e_emit.as<double>(), classic, -1);
+    else k_eye_expand<false><<<nblk(n, 128), 128, 0, c->stream>>>(c->scene, c->cam, drays, n, first_pixel, c->ps, eyenodes(c), (uint32_t)c->eye_cap,
+                                                                  c->e_head.as<uint32_t>(), c->e_emit.as<double>(), classic, -1);
     KCHECK(c);
     RC(pull_ps(c));
     if (c->hps.n_nodes <= c->eye_cap) break;
@@ -824,8 +840,10 @@ int enq_pass(ppm_ctx* c, const LightSplit& ls, int64_t total, int uc, bool accum
   RC(enq_stamp(c, sa, ST_BUILD_END));
   seg_end(c);
   // eye branch
-  k_eye_expand<<<nblk(npix, 128), 128, 0, sb>>>(c->scene, c->cam, nullptr, npix, 0, c->ps, eyenodes(c), (uint32_t)ecap, c->e_head.as<uint32_t>(),
-                                               c->e_emit.as<double>(), 0, ST_EXPAND_BEGIN);
+  if (c->scene.bvh_on) k_eye_expand<true><<<nblk(npix, 128), 128, 0, sb>>>(c->scene, c->cam, nullptr, npix, 0, c->ps, eyenodes(c), (uint32_t)ecap, c->e_head.as<uint32_t>(),
+                                                                          c->e_emit.as<double>(), 0, ST_EXPAND_BEGIN);
+  else k_eye_expand<false><<<nblk(npix, 128), 128, 0, sb>>>(c->scene, c->cam, nullptr, npix, 0, c->ps, eyenodes(c), (uint32_t)ecap, c->e_head.as<uint32_t>(),
+                                                            c->e_emit.as<double>(), 0, ST_EXPAND_BEGIN);
   KCHECK(c);
   RC(enq_stamp(c, sb, ST_EXPAND_END));
   if (cull) RC(enq_dl_classify(c, sb, c->e_pos.as<double>(), c->e_nrm.as<double>(), ecap, c->dl_masks.as<unsigned long long>()));
@@ -1194,6 +1212,7 @@ int ppm_create(int device, ppm_ctx** out) {
   c->opt_gather_heavy = opt_from_env("PPM_GATHER_HEAVY", 1) != 0;
   c->opt_dl_stats = opt_from_env("PPM_DL_STATS", 0) != 0;
   c->opt_graph = opt_from_env("PPM_GRAPH", 1) != 0;
+  c->opt_bvh = opt_from_env("PPM_BVH", 0) != 0;
   *out = c;
   return PPM_OK;
 }
@@ -1212,7 +1231,7 @@ void ppm_destroy(ppm_ctx* c) {
                  &c->qcnt, &c->qstart, &c->qrank, &c->qpic, &c->skey, &c->sidx, &c->tsum_q, &c->heavy, &c->knn_lo, &c->knn_hi, &c->knn_thr,
                  &c->knn_cnt, &c->knn_act, &c->st_in0, &c->st_in1, &c->st_out0, &c->st_out1, &c->st_out2, &c->st_out3, &c->st_out4, &c->e_head,
                  &c->e_prev, &c->e_pos, &c->e_nrm, &c->e_w, &c->e_emit, &c->e_direct, &c->e_photon, &c->dl_dbg, &c->dl_masks, &c->cull,
-                 &c->pass_img, &c->accum};
+                 &c->pass_img, &c->accum, &c->bvh_nodes, &c->bvh_prims, &c->g_prims};
   for (DBuf* b : all) b->release();
   if (c->ps) cudaFree(c->ps);
   if (c->bt) cudaFree(c->bt);
@@ -1235,6 +1254,7 @@ static int* opt_slot(ppm_ctx* c, const char* name) {
   if (!std::strcmp(name, "gather_heavy")) return &c->opt_gather_heavy;
   if (!std::strcmp(name, "dl_stats")) return &c->opt_dl_stats;
   if (!std::strcmp(name, "graph")) return &c->opt_graph;
+  if (!std::strcmp(name, "bvh")) return &c->opt_bvh;
   return nullptr;
 }
 int ppm_option_set(ppm_ctx* c, const char* name, int64_t value) {
@@ -1261,35 +1281,77 @@ int ppm_scene_set(ppm_ctx* c, const ppm_prim* prims, int32_t nprims, const ppm_m
                   const ppm_light* lights, int32_t nlights) {
   if (!c) return PPM_ERR_ARG;
   if (!prims || !mats || nprims <= 0 || nmats <= 0 || nlights < 0 || (nlights > 0 && !lights)) return fail(c, PPM_ERR_ARG, "null/empty scene arrays");
-  if (nprims > PPM_MAX_PRIMS || nmats > PPM_MAX_MATS || nlights > PPM_MAX_LIGHTS)
-    return fail(c, PPM_ERR_CAPACITY, "scene exceeds 64 primitives / 48 materials / 8 lights (the hit test walks every primitive; no BVH)");
+  if (nmats > PPM_MAX_MATS || nlights > PPM_MAX_LIGHTS) return fail(c, PPM_ERR_CAPACITY, "scene exceeds 48 materials / 8 lights");
   for (int i = 0; i < nprims; ++i) {
     if (prims[i].material < 0 || prims[i].material >= nmats) return fail(c, PPM_ERR_ARG, "primitive material index out of range");
     if (prims[i].type < PPM_SHAPE_POINT || prims[i].type > PPM_SHAPE_PARALLELOGRAM) return fail(c, PPM_ERR_ARG, "bad shape type");
   }
   for (int i = 0; i < nlights; ++i)
     if (lights[i].type < PPM_LIGHT_POINT || lights[i].type > PPM_LIGHT_SUN) return fail(c, PPM_ERR_ARG, "bad light type");
+  // Up to PPM_MAX_PRIMS primitives travel in the kernel parameters and every ray tests all of them, as the reference
+  // does.  Larger scenes (or any scene with the "bvh" option set) go through the hierarchy of bvh_types.h.
+  const bool bvh = nprims > PPM_MAX_PRIMS || c->opt_bvh != 0;
+  // the same scene again (a host loop that hands the scene over every pass): keep the calibration and the pass graph
+  if (c->have_scene && (c->scene.bvh_on != 0) == bvh && (int32_t)c->h_prims.size() == nprims && (int32_t)c->h_mats.size() == nmats &&
+      (int32_t)c->h_lights.size() == nlights && std::memcmp(c->h_prims.data(), prims, sizeof(ppm_prim) * nprims) == 0 &&
+      std::memcmp(c->h_mats.data(), mats, sizeof(ppm_material) * nmats) == 0 &&
+      (nlights == 0 || std::memcmp(c->h_lights.data(), lights, sizeof(ppm_light) * nlights) == 0))
+    return PPM_OK;
   DevScene* ns = new DevScene;
+  std::unique_ptr<DevScene> ns_owner(ns);
   std::memset(ns, 0, sizeof *ns);
-  ns->nprims = nprims; ns->nmats = nmats; ns->nlights = nlights;
-  std::memcpy(ns->prims, prims, sizeof(ppm_prim) * nprims);
+  ns->nmats = nmats; ns->nlights = nlights; ns->nprims_total = nprims;
   std::memcpy(ns->mats, mats, sizeof(ppm_material) * nmats);
   if (nlights) std::memcpy(ns->lights, lights, sizeof(ppm_light) * nlights);
-  ns->types.nwords = nprims > 32 ? 2 : 1;
-  for (int o = 0; o < nprims; ++o) {
-    const unsigned long long bit = 1ull << o;
-    if (prims[o].type == PPM_SHAPE_PLAIN) ns->types.plain |= bit;
-    else if (prims[o].type == PPM_SHAPE_SPHERE) ns->types.sphere |= bit;
-    else if (prims[o].type == PPM_SHAPE_POLYGON) ns->types.poly |= bit;
-    else if (prims[o].type == PPM_SHAPE_PARALLELOGRAM) ns->types.para |= bit;
+  std::vector<BvhNode> nodes;
+  std::vector<BvhPrim> bprims;
+  int depth = 0;
+  if (!bvh) {
+    ns->nprims = nprims;
+    std::memcpy(ns->prims, prims, sizeof(ppm_prim) * nprims);
+  } else {
+    // the constant list keeps the infinite planes (in object order), the hierarchy takes the bounded primitives
+    int nu = 0;
+    for (int i = 0; i < nprims; ++i) {
+      if (prims[i].type != PPM_SHAPE_PLAIN) continue;
+      if (nu >= PPM_MAX_PRIMS) return fail(c, PPM_ERR_CAPACITY, "scene has more than 64 infinite planes");
+      ns->prims[nu] = prims[i]; ns->unb_obj[nu] = i; ++nu;
+    }
+    ns->nprims = nu; ns->bvh_on = 1;
+    std::string why;
+    if (!ppmhost::bvh_build(prims, nprims, nodes, bprims, &depth, why)) return fail(c, PPM_ERR_CAPACITY, "BVH: " + why);
   }
-  // the same scene again (a host loop that hands the scene over every pass): keep the calibration and the pass graph
-  const bool same = c->have_scene && std::memcmp(ns, &c->scene, sizeof *ns) == 0;
-  if (same) { delete ns; return PPM_OK; }
+  ns->types.nwords = ns->nprims > 32 ? 2 : 1;
+  for (int o = 0; o < ns->nprims; ++o) {
+    const unsigned long long bit = 1ull << o;
+    if (ns->prims[o].type == PPM_SHAPE_PLAIN) ns->types.plain |= bit;
+    else if (ns->prims[o].type == PPM_SHAPE_SPHERE) ns->types.sphere |= bit;
+    else if (ns->prims[o].type == PPM_SHAPE_POLYGON) ns->types.poly |= bit;
+    else if (ns->prims[o].type == PPM_SHAPE_PARALLELOGRAM) ns->types.para |= bit;
+  }
   CK(c, cudaSetDevice(c->device));
   CK(c, cudaStreamSynchronize(c->stream));
+  CK(c, cudaStreamSynchronize(c->stream2));
+  for (ppm_ctx* t : c->twins) { CK(c, cudaStreamSynchronize(t->stream)); CK(c, cudaStreamSynchronize(t->stream2)); }
+  c->have_scene = false;
+  if (bvh) {
+    RC(ens(c, c->g_prims, sizeof(ppm_prim) * (size_t)nprims));
+    CK(c, cudaMemcpy(c->g_prims.p, prims, sizeof(ppm_prim) * (size_t)nprims, cudaMemcpyHostToDevice));
+    ns->gprims = c->g_prims.as<ppm_prim>();
+    if (!nodes.empty()) {
+      RC(ens(c, c->bvh_nodes, sizeof(BvhNode) * nodes.size()));
+      RC(ens(c, c->bvh_prims, sizeof(BvhPrim) * bprims.size()));
+      CK(c, cudaMemcpy(c->bvh_nodes.p, nodes.data(), sizeof(BvhNode) * nodes.size(), cudaMemcpyHostToDevice));
+      CK(c, cudaMemcpy(c->bvh_prims.p, bprims.data(), sizeof(BvhPrim) * bprims.size(), cudaMemcpyHostToDevice));
+      ns->bvh = c->bvh_nodes.as<BvhNode>();
+      ns->bprims = c->bvh_prims.as<BvhPrim>();
+    }
+  }
+  c->bvh_nnodes = nodes.size(); c->bvh_nprims = bprims.size(); c->bvh_depth = depth;
   c->scene = *ns;
-  delete ns;
+  c->h_prims.assign(prims, prims + nprims);
+  c->h_mats.assign(mats, mats + nmats);
+  c->h_lights.assign(lights, lights + nlights);
   RC(upload_cull(c));
   c->have_scene = true;
   c->scene_ver++;
@@ -1320,8 +1382,10 @@ int ppm_intersect(ppm_ctx* c, const double* rays6, int64_t n, int32_t* hit_idx, 
   RC(stage_out(c, pos3, (size_t)n * 24, c->st_out2, &dp));
   RC(stage_out(c, nrm3, (size_t)n * 24, c->st_out3, &dn));
   RC(stage_out(c, io, (size_t)n * 4, c->st_out4, &di));
-  k_intersect<<<nblk(n, 128), 128, 0, c->stream>>>(c->scene, (const double*)drays, n, (int32_t*)dh, (double*)dt, (double*)dp,
-                                                  (double*)dn, (int32_t*)di);
+  if (c->scene.bvh_on) k_intersect<true><<<nblk(n, 128), 128, 0, c->stream>>>(c->scene, (const double*)drays, n, (int32_t*)dh, (double*)dt, (double*)dp,
+                                                                             (double*)dn, (int32_t*)di);
+  else k_intersect<false><<<nblk(n, 128), 128, 0, c->stream>>>(c->scene, (const double*)drays, n, (int32_t*)dh, (double*)dt, (double*)dp,
+                                                               (double*)dn, (int32_t*)di);
   KCHECK(c);
   RC(finish_out(c, hit_idx, (size_t)n * 4, dh));
   RC(finish_out(c, t, (size_t)n * 8, dt));

@@ -59,6 +59,7 @@ struct EyeStack {
 #ifndef PPM_EYE_MINB
 #define PPM_EYE_MINB 6
 #endif
+template <bool BVH>
 __global__ void __launch_bounds__(128, PPM_EYE_MINB)
 k_eye_expand(const __grid_constant__ DevScene sc, const __grid_constant__ ppm_camera cam, const double* __restrict__ rays6,
              int64_t n, int64_t first_pixel, PassDev* ps, EyeNodes nodes, uint32_t cap,
@@ -86,7 +87,7 @@ k_eye_expand(const __grid_constant__ DevScene sc, const __grid_constant__ ppm_ca
     EyeStack e = st[--sp];
     if (e.depth >= PPM_MAX_TRACE) continue;
     Isect is;
-    if (!nearest_hit(sc, e.pos, e.dir, is)) continue;
+    if (!nearest_hit<BVH>(sc, e.pos, e.dir, is)) continue;
     ++visited;
     Philox rng(seed, pass, PPM_DOMAIN_EYE, (uint64_t)pix, e.node);
     EyeNode nd;
@@ -355,6 +356,7 @@ __device__ __forceinline__ double ts5(unsigned i) {   // the literals 0.1, 0.3, 
 #ifndef PPM_DL_STRAIGHT
 #define PPM_DL_STRAIGHT 1
 #endif
+template <bool BVH>
 __global__ void __launch_bounds__(128, PPM_DL_MINB)
 k_direct_light(const __grid_constant__ DevScene sc, PassDev* ps, uint32_t cap, const unsigned long long* __restrict__ masks,
                const uint32_t* __restrict__ order, const double* __restrict__ pos3, const double* __restrict__ nrm3,
@@ -420,7 +422,7 @@ k_direct_light(const __grid_constant__ DevScene sc, PassDev* ps, uint32_t cap, c
       PrimMasks pm;
       pm.plain = mask & tmask.plain; pm.sphere = mask & tmask.sphere; pm.poly = mask & tmask.poly; pm.para = mask & tmask.para;
       pm.nwords = tmask.nwords; pm._pad = 0;
-      const bool need_ld = mask != 0ull;                      // warp-uniform (masks are OR-ed across the warp)
+      const bool need_ld = BVH || mask != 0ull;               // warp-uniform (masks are OR-ed across the warp)
       const double C = (2.0 * l.flux * 0.2 * 0.2) / (PPM_PI * 4.0);   // 2 * flux * PARA_DIV^2 / (4 pi), light.rs:142
       double acc = 0.0, inv_prev = 0.0;
       bool have_prev = false;
@@ -476,7 +478,7 @@ k_direct_light(const __grid_constant__ DevScene sc, PassDev* ps, uint32_t cap, c
         }
         if (need_ld) {
           D3 hp;
-          const int hit = nearest_hit_masked(sc, p, ld, pm, hp);
+          const int hit = BVH ? nearest_hit_pos_bvh(sc, p, ld, hp) : nearest_hit_masked(sc, p, ld, pm, hp);
           if (hit == 1) {
             const D3 po = hp - p;
             if (dd - dot(po, po) > 0.002) continue;

@@ -7,6 +7,7 @@
 #include "pass_state.cuh"
 
 
+template <bool BVH>
 __global__ void k_intersect(const __grid_constant__ DevScene sc, const double* __restrict__ rays6, int64_t n,
                             int32_t* __restrict__ hit, double* __restrict__ t, double* __restrict__ pos3,
                             double* __restrict__ nrm3, int32_t* __restrict__ io) {
@@ -14,7 +15,7 @@ __global__ void k_intersect(const __grid_constant__ DevScene sc, const double* _
   if (i >= n) return;
   D3 p = ld3(rays6 + i * 6), d = ld3(rays6 + i * 6 + 3);
   Isect is;
-  bool ok = nearest_hit(sc, p, d, is);
+  bool ok = nearest_hit<BVH>(sc, p, d, is);
   hit[i] = ok ? is.obj : -1;
   if (t) t[i] = ok ? is.t : 0.0;
   if (pos3) st3(pos3 + i * 3, ok ? is.pos : mk3(0, 0, 0));
@@ -62,6 +63,7 @@ struct RecBuf {
 #ifndef PPM_TRACE_MINB
 #define PPM_TRACE_MINB 6
 #endif
+template <bool BVH>
 __global__ void __launch_bounds__(128, PPM_TRACE_MINB)
 k_trace_photons(const __grid_constant__ DevScene sc, const __grid_constant__ LightSplit ls, PassDev* ps,
                 int uc, int64_t n, RecBuf rec, unsigned long long cap, uint32_t* __restrict__ pmask) {
@@ -109,7 +111,7 @@ k_trace_photons(const __grid_constant__ DevScene sc, const __grid_constant__ Lig
     const D3 in_dir = dir;
     const int l = depth;
     if (alive) {
-      if (!nearest_hit(sc, pos, dir, is)) {
+      if (!nearest_hit<BVH>(sc, pos, dir, is)) {
         alive = false;
       } else {
         store = (uc == 0 || l > 0) && surf_store_photon(sc.mats[is.mat]);
