@@ -105,3 +105,14 @@ def mesh_scene(base, triangles, material, spheres=()):
     s = ArrayScene(prims, mats, lights)
     s.nlights = base.nlights
     return s
+
+
+def mesh_scene_text(base_text, triangles, material_name):
+    """The text of a .scene file: `base_text` (whose LAST section must be `object:`) plus
+    one `polygon` object per triangle with inline vertices, written with repr() so that the doubles round-trip."""
+    lines = [base_text.rstrip("\n")]
+    for k, t in enumerate(np.asarray(triangles, np.float64)):
+        lines.append(f"  - type: polygon\n    name: tri{k}\n    material: {material_name}")
+        for i in range(3):
+            lines.append(f"    pos{i + 1}: [ {float(t[i][0])!r}, {float(t[i][1])!r}, {float(t[i][2])!r} ]")
+    return "\n".join(lines) + "\n"

@@ -56,3 +56,19 @@ def test_degenerate_inputs():
     sc.prims[sc.nprims - 1].position[0] = float("inf")
     assert inspect(sc)[0] == -4                   # PPM_ERR_CAPACITY
     assert K.lib.ppm_bvh_inspect(None, 0, None, None, None, None) != 0
+
+
+def test_mesh_scene_file_parses_to_the_same_primitives(tmp_path):
+    """A 973-object scene FILE (the drop-in format) gives the same primitive array as building it through the ABI."""
+    path = os.path.join(EX, "ex-glassbox.scene")
+    base = P.read_scene(path)
+    tris = synth.uv_sphere_triangles((0.3, 2.6, 1.0), 0.7, 16, 32)
+    f = tmp_path / "mesh.scene"
+    f.write_text(synth.mesh_scene_text(open(path).read(), tris, "glass"))
+    parsed = P.read_scene(str(f))
+    built = synth.mesh_scene(base, tris, 4)
+    assert parsed.nprims == built.nprims == 973
+    a = np.frombuffer(bytes(parsed.prims), np.uint8).reshape(parsed.nprims, -1)
+    b = np.frombuffer(bytes(built.prims), np.uint8).reshape(built.nprims, -1)
+    assert np.array_equal(a, b)
+    assert inspect(parsed)[0] == 0

@@ -208,3 +208,22 @@ def test_bvh_large_mesh_properties(engine):
     assert (np.einsum("ij,ij->i", nrm[mesh], d[mesh]) <= 0.0).all()                  # the normal faces the ray
     assert (~mesh[disc < -(0.05 * r) ** 2]).all()          # clearly outside the silhouette: never the mesh
     engine.set_scene(base)
+
+
+def test_ppmpa_cli_on_a_mesh_scene_file(engine, tmp_path):
+    """The drop-in CLI (`ppmpa <#photon> <radius> <camera> <scene>`, ppmpa.rs:15) on a 973-object scene FILE: the
+    parser, the BVH build and the pass give the image the library gives for the same scene built through the ABI."""
+    import subprocess
+    from test_gpu_cli import BIN, ENV, parse_ppmf
+    path = os.path.join(EX, "ex-glassbox.scene")
+    tris = synth.uv_sphere_triangles((0.3, 2.6, 1.0), 0.7, 16, 32)
+    f = tmp_path / "mesh.scene"
+    f.write_text(synth.mesh_scene_text(open(path).read(), tris, "glass"))
+    cam_file = os.path.join(EX, "screen1.scr")
+    r = subprocess.run([os.path.join(BIN, "ppmpa"), "20000", "0.15", cam_file, str(f)], capture_output=True, env=ENV, check=True)
+    hdr, img = parse_ppmf(r.stdout.decode())
+    sc, _ = mesh_scene()
+    engine.set_scene(sc); engine.set_camera(P.read_camera(cam_file))
+    engine.iteration(12345, 3, 20000, 0.15 ** 2, uc=True)
+    assert hdr[3] == "256 256" and np.array_equal(img, engine.pass_image())
+    engine.set_scene(load_scene("ex-glassbox"))
