@@ -33,7 +33,7 @@ __device__ __forceinline__ void bvh_leaf(const DevScene& sc, uint32_t ref, D3 po
     const double2* q = reinterpret_cast<const double2*>(sc.bprims + first + k);
     const double2 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2), d = __ldg(q + 3), e = __ldg(q + 4);
     const long long meta = __double_as_longlong(e.y);
-    const int obj = (int)(meta & 0xffffffffll), type = (int)(meta >> 32);
+    const int obj = (int)(meta & 0xffffffffll), type = (int)(meta >> 32) & 0xff;
     const D3 p0 = mk3(a.x, a.y, b.x);
     if (type == PPM_SHAPE_SPHERE) consider_sphere(p0, b.y, pos, dir, obj, best_t, best_o);
     else consider_polygon(type == PPM_SHAPE_PARALLELOGRAM ? 2.0 : 1.0, p0, mk3(b.y, c.x, c.y), mk3(d.x, d.y, e.x), pos, dir, obj, best_t, best_o);

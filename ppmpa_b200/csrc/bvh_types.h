@@ -32,8 +32,8 @@ struct BvhPrim {
   double d1[3];            // edge 1 | (radius, 0, 0)
   double d2[3];            // edge 2
   int32_t obj;             // object index in the scene (order of ppm_scene_set)
-  int32_t type;            // PPM_SHAPE_*
-};
+  int32_t type;            // PPM_SHAPE_* in bits 0..7; bit 8 + l: the primitive lies in the plane of area light l
+};                         // (the emitter's own geometry: class (b) of the shadow-ray culling, kernels_eye.cuh)
 #ifdef __cplusplus
 static_assert(sizeof(BvhNode) == 128, "BvhNode layout");
 static_assert(sizeof(BvhPrim) == 80, "BvhPrim layout");

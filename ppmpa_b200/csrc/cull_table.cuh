@@ -10,6 +10,21 @@
 #include <cstring>
 #include <vector>
 
+// a polygon / parallelogram lying in the plane of light l (unit normal nl): every vertex within 1e-12 (relative to the
+// scene scale) of the plane through the quad -- the emitter's own geometry
+static inline bool cull_in_light_plane(const ppm_light& l, const double nl[3], const ppm_prim& s) {
+  if (s.type != PPM_SHAPE_POLYGON && s.type != PPM_SHAPE_PARALLELOGRAM) return false;
+  auto len3 = [](const double* a) { return std::sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]); };
+  const double scale = 1.0 + len3(l.pos) + len3(s.position) + len3(s.dir1) + len3(s.dir2);
+  for (int j = 0; j < 4; ++j) {
+    double h = 0.0;
+    for (int k = 0; k < 3; ++k)
+      h += nl[k] * ((s.position[k] + ((j & 1) ? s.dir1[k] : 0.0) + ((j & 2) ? s.dir2[k] : 0.0)) - l.pos[k]);
+    if (!(std::fabs(h) <= 1e-12 * scale)) return false;
+  }
+  return true;
+}
+
 // Per-scene table for the conservative shadow-ray culling of k_direct_light (kernels_eye.cuh).
 // Everything here is a bound with a 1e-6 safety margin, never a quantity that enters a result.
 static inline void build_cull(const DevScene& sc, DevCull& cu) {
@@ -78,16 +93,7 @@ static inline void build_cull(const DevScene& sc, DevCull& cu) {
         for (int k = 0; k < 3; ++k) cl.nl[k] = cx[k] / cn;
         for (int o = 0; o < sc.nprims; ++o) {
           const ppm_prim& s = sc.prims[o];
-          if (s.type != PPM_SHAPE_POLYGON && s.type != PPM_SHAPE_PARALLELOGRAM) continue;
-          bool in_plane = true;
-          double scale = 1.0 + len3(l.pos) + len3(s.position) + len3(s.dir1) + len3(s.dir2);
-          for (int j = 0; j < 4 && in_plane; ++j) {
-            double h = 0.0;
-            for (int k = 0; k < 3; ++k)
-              h += cl.nl[k] * ((s.position[k] + ((j & 1) ? s.dir1[k] : 0.0) + ((j & 2) ? s.dir2[k] : 0.0)) - l.pos[k]);
-            if (!(std::fabs(h) <= 1e-12 * scale)) in_plane = false;
-          }
-          if (in_plane) cl.coplanar |= 1ull << o;
+          if (cull_in_light_plane(l, cl.nl, s)) cl.coplanar |= 1ull << o;
         }
       }
     }

@@ -270,14 +270,15 @@ __device__ __forceinline__ bool nearest_hit(const DevScene& sc, D3 pos, D3 dir, 
   else { is.nvec = n; is.io = 0; }
   return true;
 }
-// Shadow ray of a scene in BVH mode: what `illuminated` (tracer.rs:272-290) consumes of calc_intersection.
-// Returns 0 = nothing hit, 1 = hit (hit_pos set), 2 = calc_intersection is None because get_normal failed.
-__device__ __forceinline__ int nearest_hit_pos_bvh(const DevScene& sc, D3 pos, D3 dir, D3& hit_pos) {
+// Shadow ray of a scene in BVH mode: what `illuminated` (tracer.rs:272-290) consumes of calc_intersection, over the planes
+// in `pm` (indices into the constant list) and, when `walk`, the hierarchy.
+// Returns 0 = no candidate, 1 = hit (hit_pos set), 2 = calc_intersection is None because get_normal failed.
+__device__ __forceinline__ int nearest_hit_masked_bvh(const DevScene& sc, D3 pos, D3 dir, const PrimMasks& pm, bool walk, D3& hit_pos) {
   double best_t = 0.0;
   int best_o = -1;
-  scan_prims(sc, sc.types, pos, dir, best_t, best_o);
+  scan_prims(sc, pm, pos, dir, best_t, best_o);
   if (best_o >= 0) best_o = sc.unb_obj[best_o];
-  bvh_traverse(sc, pos, dir, best_t, best_o);
+  if (walk) bvh_traverse(sc, pos, dir, best_t, best_o);
   if (best_o < 0) return 0;
   hit_pos = pos + dir * best_t;
   const ppm_prim& s = sc.gprims[best_o];

@@ -335,7 +335,8 @@ int upload_cull(ppm_ctx* c) {
   return PPM_OK;
 }
 // culling is possible when switched on ("dl_cull") and bit 63 of the masks is free for the certificate
-bool cull_on(const ppm_ctx* c) { return c->opt_dl_cull && !c->scene.bvh_on && c->scene.nprims <= 63 && c->scene.nlights > 0; }
+// (BVH mode: bit 62 says "walk the hierarchy"; the constant list then holds only the scene's planes)
+bool cull_on(const ppm_ctx* c) { return c->opt_dl_cull && c->scene.nprims <= (c->scene.bvh_on ? 62 : 63) && c->scene.nlights > 0; }
 
 // ---- enqueue helpers: launches only, sizes come from PassDev, nothing waits for the host ------------------------
 template <class Op>
@@ -478,13 +479,14 @@ int enq_gather(ppm_ctx* c, cudaStream_t st, const double* dpos, const double* dn
   return PPM_OK;
 }
 int enq_dl_classify(ppm_ctx* c, cudaStream_t st, const double* dpos, const double* dnrm, uint64_t cap, unsigned long long* masks) {
-  k_dl_classify<<<nblk((int64_t)cap, 128), 128, 0, st>>>(c->scene, c->cull.as<DevCull>(), c->ps, (uint32_t)cap, dpos, dnrm, masks, -1);
+  if (c->scene.bvh_on) k_dl_classify<true><<<nblk((int64_t)cap, 128), 128, 0, st>>>(c->scene, c->cull.as<DevCull>(), c->ps, (uint32_t)cap, dpos, dnrm, masks, -1);
+  else k_dl_classify<false><<<nblk((int64_t)cap, 128), 128, 0, st>>>(c->scene, c->cull.as<DevCull>(), c->ps, (uint32_t)cap, dpos, dnrm, masks, -1);
   KCHECK(c);
   return PPM_OK;
 }
 int enq_direct_light(ppm_ctx* c, cudaStream_t st, const double* dpos, const double* dnrm, uint64_t cap, double* dout,
                      const unsigned long long* masks, const uint32_t* order, unsigned long long* dbg, int stamp_slot) {
-  if (c->scene.bvh_on) k_direct_light<true><<<nblk((int64_t)cap, 128), 128, 0, st>>>(c->scene, c->ps, (uint32_t)cap, nullptr, order, dpos, dnrm, dout, dbg, stamp_slot);
+  if (c->scene.bvh_on) k_direct_light<true><<<nblk((int64_t)cap, 128), 128, 0, st>>>(c->scene, c->ps, (uint32_t)cap, masks, order, dpos, dnrm, dout, dbg, stamp_slot);
   else k_direct_light<false><<<nblk((int64_t)cap, 128), 128, 0, st>>>(c->scene, c->ps, (uint32_t)cap, masks, order, dpos, dnrm, dout, dbg, stamp_slot);
   KCHECK(c);
   return PPM_OK;
@@ -1320,6 +1322,18 @@ int ppm_scene_set(ppm_ctx* c, const ppm_prim* prims, int32_t nprims, const ppm_m
     ns->nprims = nu; ns->bvh_on = 1;
     std::string why;
     if (!ppmhost::bvh_build(prims, nprims, nodes, bprims, &depth, why)) return fail(c, PPM_ERR_CAPACITY, "BVH: " + why);
+    // class (b) of the shadow-ray culling: primitives lying in the plane of an area light (its own emitter geometry)
+    for (int li = 0; li < nlights; ++li) {
+      const ppm_light& l = lights[li];
+      if (l.type != PPM_LIGHT_PARALLELOGRAM) continue;
+      const double cx[3] = {l.dir1[1] * l.dir2[2] - l.dir2[1] * l.dir1[2], l.dir1[2] * l.dir2[0] - l.dir2[2] * l.dir1[0],
+                            l.dir1[0] * l.dir2[1] - l.dir2[0] * l.dir1[1]};
+      const double cn = std::sqrt(cx[0] * cx[0] + cx[1] * cx[1] + cx[2] * cx[2]);
+      if (!(cn > 0.0 && cn < 1e150)) continue;
+      const double nl[3] = {cx[0] / cn, cx[1] / cn, cx[2] / cn};
+      for (BvhPrim& q : bprims)
+        if (cull_in_light_plane(l, nl, prims[q.obj])) q.type |= 1 << (8 + li);
+    }
   }
   ns->types.nwords = ns->nprims > 32 ? 2 : 1;
   for (int o = 0; o < ns->nprims; ++o) {

@@ -218,7 +218,7 @@ extern "C" int ppm_bvh_inspect(const ppm_prim* prims, int32_t nprims, int64_t* n
         if (q.obj < 0 || q.obj >= nprims || seen[(size_t)q.obj]) return PPM_ERR_STATE;
         seen[(size_t)q.obj] = 1;
         const ppm_prim& s = prims[q.obj];
-        if (q.type != s.type) return PPM_ERR_STATE;
+        if ((q.type & 0xff) != s.type) return PPM_ERR_STATE;
         double c[4][3]; int nc = 0;
         if (s.type == PPM_SHAPE_SPHERE) {
           for (int a = 0; a < 3; ++a) { c[0][a] = s.position[a] - std::fabs(s.scalar); c[1][a] = s.position[a] + std::fabs(s.scalar); }

@@ -291,7 +291,129 @@ __device__ __forceinline__ unsigned long long cull_classify(const DevScene& sc, 
   return mask;
 }
 
+// ---- BVH mode: the bounded primitives against the SHAFT of a node -------------------------------------------------
+// All 25 shadow rays of a node run from the node p to points of the light's quad, i.e. inside the pyramid with apex p
+// over the quad.  Whatever lies outside one of its four side planes (by the same > 1e-6 rad margin as the pyramid test
+// of cull_classify) cannot be met by any of them.  One walk of the hierarchy with the pyramid instead of 25 walks with
+// rays: a subtree is dropped when its (padded) box is outside a side plane; at a leaf the primitives' own corners
+// (polygon: the parallelogram's four, a superset of the triangle) or box (sphere) are tested the same way.
+// Returns 2 = some primitive may be met (test the hierarchy for this node), 1 = only primitives lying in the light's
+// plane (class (b): harmless given a certificate), 0 = none.
+__device__ __forceinline__ bool shaft_outside(const D3 pn[4], const double pnn[4], D3 lo, D3 hi) {   // lo, hi relative to p
+  const double ww = (fmax(lo.x * lo.x, hi.x * hi.x) + fmax(lo.y * lo.y, hi.y * hi.y)) + fmax(lo.z * lo.z, hi.z * hi.z);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    // the largest n . w over the box's corners; all corners are outside when even that one is
+    const double d = (fmax(pn[j].x * lo.x, pn[j].x * hi.x) + fmax(pn[j].y * lo.y, pn[j].y * hi.y)) + fmax(pn[j].z * lo.z, pn[j].z * hi.z);
+    if (d < 0.0 && d * d > 1e-12 * (pnn[j] * ww)) return true;
+  }
+  return false;
+}
+// The walk visits at most PPM_SHAFT_BUDGET nodes and leaves: a shaft that grazes a finely tessellated surface would
+// otherwise visit hundreds of boxes to prove what 25 ray walks find directly.  Measured on a 1 M-triangle glass sphere
+// at 1080p (profiles/r2bvh_budget.txt): pass 32.5 ms without the classification, 38.2 ms with an unbounded walk (it costs
+// 10 ms and saves 5), 35.2 / 33.6 / 30.6 / 28.8 ms with budgets 200 / 64 / 24 / 8.  Running out of budget answers
+// "test", which is always safe.
+#ifndef PPM_SHAFT_BUDGET
+#define PPM_SHAFT_BUDGET 8
+#endif
+// squared distance from the origin to the box [lo, hi] (0 inside)
+__device__ __forceinline__ double box_dist2(D3 lo, D3 hi) {
+  const double x = fmax(fmax(lo.x, -hi.x), 0.0), y = fmax(fmax(lo.y, -hi.y), 0.0), z = fmax(fmax(lo.z, -hi.z), 0.0);
+  return (x * x + y * y) + z * z;
+}
+__device__ __forceinline__ int bvh_shaft_classify(const DevScene& sc, const CullLight& cl, int li, D3 p) {
+  if (!sc.bvh) return 0;
+  const D3 u = ld3(cl.c) - p;
+  const double uu = dot(u, u);
+  if (!(uu < 1e6)) return 2;
+  const double L = sqrt(uu) + cl.r;
+  if (!(fabs(dot(ld3(cl.nl), u)) > 1e-6 * (1.0 + L))) return 2;      // the node lies (nearly) in the light's plane
+  D3 pn[4];
+  double pnn[4];
+  {
+    D3 a[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) a[j] = ld3(cl.corner[j]) - p;
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {                          // as in cull_classify
+      const D3 n = cross(a[j], a[(j + 1) & 3]);
+      const double nn = dot(n, n);
+      const double s = dot(n, a[(j + 2) & 3]);
+      ok = ok && nn > 1e-12 * (dot(a[j], a[j]) * dot(a[(j + 1) & 3], a[(j + 1) & 3])) &&
+           s * s > 1e-12 * (nn * dot(a[(j + 2) & 3], a[(j + 2) & 3]));
+      pn[j] = s < 0.0 ? -n : n;
+      pnn[j] = nn;
+    }
+    if (!ok) return 2;
+  }
+  int res = 0;
+  uint32_t stack[PPM_BVH_STACK];
+  int sp = 0, budget = PPM_SHAFT_BUDGET;
+  uint32_t cur = 0u;
+  for (;;) {
+    if (--budget < 0) return 2;                            // not settled within the budget: let the rays decide
+    if (cur & PPM_BVH_LEAF) {
+      const uint32_t first = cur & 0x0FFFFFFFu, cnt = ((cur >> 28) & 7u) + 1u;
+      for (uint32_t k = 0; k < cnt; ++k) {
+        const double2* q = reinterpret_cast<const double2*>(sc.bprims + first + k);
+        const double2 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2), d = __ldg(q + 3), e = __ldg(q + 4);
+        const int type = (int)(__double_as_longlong(e.y) >> 32);
+        const D3 p0 = mk3(a.x, a.y, b.x) - p;
+        bool out;
+        if ((type & 0xff) == PPM_SHAPE_SPHERE) {
+          const double r = fabs(b.y) * (1.0 + 1e-6) + 1e-6 * (1.0 + (fabs(a.x) + fabs(a.y) + fabs(b.x)));
+          out = shaft_outside(pn, pnn, p0 - mk3(r, r, r), p0 + mk3(r, r, r));
+        } else {
+          const D3 d1 = mk3(b.y, c.x, c.y), d2 = mk3(d.x, d.y, e.x);
+          D3 w[4];
+          w[0] = p0; w[1] = p0 + d1; w[2] = (p0 + d1) + d2; w[3] = p0 + d2;
+          out = false;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            bool all_out = true;
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+              const double dd = dot(pn[j], w[v]);
+              all_out = all_out && dd < 0.0 && dd * dd > 1e-12 * (pnn[j] * dot(w[v], w[v]));
+            }
+            out = out || all_out;
+          }
+        }
+        if (out) continue;
+        if ((type >> (8 + li)) & 1) res = 1;               // lies in the light's plane
+        else return 2;
+      }
+    } else {
+      const double2* q = reinterpret_cast<const double2*>(sc.bvh + cur);
+      double box[12];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) { const double2 v = __ldg(q + k); box[2 * k] = v.x; box[2 * k + 1] = v.y; }
+      const uint2 ch = __ldg(reinterpret_cast<const uint2*>(q + 6));
+      const D3 lo0 = mk3(box[0], box[1], box[2]) - p, hi0 = mk3(box[3], box[4], box[5]) - p;
+      const D3 lo1 = mk3(box[6], box[7], box[8]) - p, hi1 = mk3(box[9], box[10], box[11]) - p;
+      const bool h0 = !shaft_outside(pn, pnn, lo0, hi0);
+      const bool h1 = ch.y != PPM_BVH_NONE && !shaft_outside(pn, pnn, lo1, hi1);
+      if (h0 && h1) {
+        // the child nearer to the apex first: a node ON the indexed surface finds its own neighbourhood at once, and the
+        // walk ends with the first primitive that has to be tested
+        const double e0 = box_dist2(lo0, hi0), e1 = box_dist2(lo1, hi1);
+        const bool first0 = e0 <= e1;
+        stack[sp++] = first0 ? ch.y : ch.x;
+        cur = first0 ? ch.x : ch.y;
+        continue;
+      }
+      if (h0) { cur = ch.x; continue; }
+      if (h1) { cur = ch.y; continue; }
+    }
+    if (sp == 0) return res;
+    cur = stack[--sp];
+  }
+}
+
 #define PPM_CULL_CERT (1ull << 63)
+#define PPM_CULL_BVH (1ull << 62)      // BVH mode: the node's shadow rays must walk the hierarchy
 // Conservative "no sample of this light can ever reach the hit test" for a node: every sample fails
 // `dot(lnv, d) < 0` (light.rs:112) or every sample has cos0 < 0 (tracer.rs:277-278).  The bands are > 1000 x the
 // rounding of the reference's own tests, so this only fires when each of the 25 reference decisions is certain.
@@ -309,6 +431,7 @@ __device__ __forceinline__ bool light_never_tested(const ppm_light& l, const Cul
 // primitives the node's shadow rays towards light li must test, bit 63 = the node has a certificate.  A separate
 // kernel so that it has its own register budget (k_direct_light is compiled for 64 registers) and can run right after
 // the eye-path expansion, concurrently with the photon branch.  The node count comes from the pass state.
+template <bool BVH>
 #ifdef PPM_CLS_MINB                                   // tuning builds (tools/build_variants.sh): 5 / 6 / 8 CTAs per SM are all slower
 __global__ void __launch_bounds__(128, PPM_CLS_MINB)
 #else
@@ -323,12 +446,16 @@ k_dl_classify(const __grid_constant__ DevScene sc, const DevCull* __restrict__ c
   if (node >= n) return;
   const D3 p = ld3(pos3 + node * 3);
   const D3 nv = ld3(nrm3 + node * 3);
-  const unsigned long long all = (1ull << sc.nprims) - 1ull;       // nprims <= 63 here (bit 63 is the certificate)
+  const unsigned long long all = (1ull << sc.nprims) - 1ull;       // nprims <= 62 here (bits 62 / 63: hierarchy / certificate)
   for (int li = 0; li < sc.nlights; ++li) {
     unsigned long long m = 0;
     if (sc.lights[li].type == PPM_LIGHT_PARALLELOGRAM && !light_never_tested(sc.lights[li], cull->light[li], p, nv)) {
       bool cert;
-      m = cull_classify(sc, cull, li, p, all, cert);
+      m = cull_classify(sc, cull, li, p, all, cert);      // BVH mode: the scene's planes
+      if (BVH) {
+        const int sh = bvh_shaft_classify(sc, cull->light[li], li, p);
+        if (sh == 2 || (sh == 1 && !cert)) m |= PPM_CULL_BVH;
+      }
       if (cert) m |= PPM_CULL_CERT;
     }
     masks[(int64_t)li * cap + node] = m;
@@ -396,13 +523,14 @@ k_direct_light(const __grid_constant__ DevScene sc, PassDev* ps, uint32_t cap, c
       s_lc[2] = fabs(lnv.x) + fabs(lnv.y) + fabs(lnv.z);
     }
     __syncthreads();
-    bool cert = false, own_none = false;
+    bool cert = false, own_none = false, walk = BVH;         // walk (BVH mode, warp-uniform): shadow rays go through the hierarchy
     unsigned long long mask = all;
     if (masks) {
       const unsigned long long own = masks[(int64_t)li * cap + node];   // k_dl_classify
       cert = (own & PPM_CULL_CERT) != 0ull;
-      mask = own & ~PPM_CULL_CERT;
-      own_none = mask == 0ull;                                // a property of the node alone (the OR below is not)
+      mask = own & ~(PPM_CULL_CERT | PPM_CULL_BVH);
+      own_none = (own & ~PPM_CULL_CERT) == 0ull;              // a property of the node alone (the OR below is not)
+      if (BVH) walk = __any_sync(0xffffffffu, (own & PPM_CULL_BVH) != 0ull);
       const unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)mask);
       const unsigned hi = __reduce_or_sync(0xffffffffu, (unsigned)(mask >> 32));
       mask = ((unsigned long long)hi << 32) | lo;
@@ -422,7 +550,7 @@ k_direct_light(const __grid_constant__ DevScene sc, PassDev* ps, uint32_t cap, c
       PrimMasks pm;
       pm.plain = mask & tmask.plain; pm.sphere = mask & tmask.sphere; pm.poly = mask & tmask.poly; pm.para = mask & tmask.para;
       pm.nwords = tmask.nwords; pm._pad = 0;
-      const bool need_ld = BVH || mask != 0ull;               // warp-uniform (masks are OR-ed across the warp)
+      const bool need_ld = walk || mask != 0ull;              // warp-uniform (masks are OR-ed across the warp)
       const double C = (2.0 * l.flux * 0.2 * 0.2) / (PPM_PI * 4.0);   // 2 * flux * PARA_DIV^2 / (4 pi), light.rs:142
       double acc = 0.0, inv_prev = 0.0;
       bool have_prev = false;
@@ -478,7 +606,7 @@ k_direct_light(const __grid_constant__ DevScene sc, PassDev* ps, uint32_t cap, c
         }
         if (need_ld) {
           D3 hp;
-          const int hit = BVH ? nearest_hit_pos_bvh(sc, p, ld, hp) : nearest_hit_masked(sc, p, ld, pm, hp);
+          const int hit = BVH ? nearest_hit_masked_bvh(sc, p, ld, pm, walk, hp) : nearest_hit_masked(sc, p, ld, pm, hp);
           if (hit == 1) {
             const D3 po = hp - p;
             if (dd - dot(po, po) > 0.002) continue;

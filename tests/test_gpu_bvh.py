@@ -227,3 +227,48 @@ def test_ppmpa_cli_on_a_mesh_scene_file(engine, tmp_path):
     engine.iteration(12345, 3, 20000, 0.15 ** 2, uc=True)
     assert hdr[3] == "256 256" and np.array_equal(img, engine.pass_image())
     engine.set_scene(load_scene("ex-glassbox"))
+
+
+@pytest.mark.parametrize("coherent", [False, True])
+@pytest.mark.parametrize("name", ["mesh-opaque", "mesh-glass", None, "ex-glassbox", "sample1", "adversarial"])
+def test_bvh_direct_light_cull_is_exact(engine, oracle, name, coherent, tmp_path):
+    """BVH mode's shadow-ray culling (planes classified per node as in brute-force mode, the hierarchy against the
+    node -> light-quad shaft, kernels_eye.cuh: bvh_shaft_classify) must not change a decision: culled == unculled,
+    and both == the oracle's get_radiance_from_light.  Mesh scenes, and example scenes with the hierarchy forced
+    (ex-glassbox and sample1 have an emitter polygon lying in the light's plane: class (b))."""
+    from test_gpu_parity import ADVERSARIAL_SCENE, _cull_probe_nodes
+    forced = contextlib.nullcontext()
+    if name == "mesh-opaque":
+        sc, _ = mesh_scene(material=WALL, spheres=[((-1.0, 0.6, 0.5), 0.6)])
+    elif name == "mesh-glass":
+        sc, _ = mesh_scene(material=GLASS)
+    else:
+        if name == "adversarial":
+            f = tmp_path / "adversarial.scene"
+            f.write_text(ADVERSARIAL_SCENE)
+            sc = P.read_scene(str(f))
+        else:
+            sc = load_scene(name)
+        forced = bvh_forced(engine)
+    with forced:
+        engine.set_scene(sc)
+        pos, nrm = _cull_probe_nodes(engine, 78)
+        if coherent:
+            cell = np.floor(pos / 0.05).astype(np.int64)
+            order = np.lexsort((cell[:, 0], cell[:, 1], cell[:, 2]))
+            pos, nrm = np.ascontiguousarray(pos[order]), np.ascontiguousarray(nrm[order])
+        engine.set_option("dl_cull", 1)
+        a = engine.direct_light(pos, nrm)
+        engine.set_option("dl_cull", 0)
+        try:
+            b = engine.direct_light(pos, nrm)
+        finally:
+            engine.set_option("dl_cull", 1)
+    assert np.array_equal(a > 0, b > 0), f"{np.sum(np.any((a > 0) != (b > 0), axis=1))} of {len(a)} nodes lit differently with culling"
+    assert_rel(a, b, 1e-12, atol=1e-15)
+    sub = np.random.default_rng(5).choice(len(pos), 6000, replace=False)
+    o = oracle.direct_light(sc, pos[sub], nrm[sub])
+    assert o.max() > 0 and np.count_nonzero(np.any(o > 0, axis=1)) > 300
+    assert np.array_equal(a[sub] > 0, o > 0)
+    assert_rel(a[sub], o, 1e-12)
+    engine.set_scene(load_scene("ex-glassbox"))

@@ -13,7 +13,7 @@ for spec in "$@"; do
   (
     $NVCC -O3 -std=c++17 -lineinfo -fmad=false $ARCH -Xcompiler -fPIC -Xcompiler -ffp-contract=off -Xcompiler -pthread $defs \
       -Xptxas -v -c engine.cu -o build/engine_$name.o 2> build/engine_$name.ptxas.log
-    $NVCC $ARCH -shared -cudart static -Xcompiler -pthread -o ../variants/libppm_b200_$name.so build/engine_$name.o build/host_model.o build/host_parse.o build/host_io.o -ldl
+    $NVCC $ARCH -shared -cudart static -Xcompiler -pthread -o ../variants/libppm_b200_$name.so build/engine_$name.o build/host_model.o build/host_parse.o build/host_io.o build/host_bvh.o -ldl
     echo "built $name ($defs)"
   ) &
   while [ $(jobs -r | wc -l) -ge 6 ]; do sleep 0.5; done
