@@ -272,3 +272,34 @@ def test_bvh_direct_light_cull_is_exact(engine, oracle, name, coherent, tmp_path
     assert np.array_equal(a[sub] > 0, o > 0)
     assert_rel(a[sub], o, 1e-12)
     engine.set_scene(load_scene("ex-glassbox"))
+
+
+def test_bvh_two_lanes_equal_sequential_and_scene_switch(engine):
+    """ppm_render_passes on two lanes (the second lane reads the first one's hierarchy) == the same passes one by one,
+    on a mesh scene; then switching back to a small scene (brute-force mode) and to the mesh again re-renders the
+    same images (graphs and lanes follow the scene version)."""
+    sc, _ = mesh_scene()
+    small = load_scene("ex-glassbox")
+    cam = P.read_camera(os.path.join(EX, "camera0.scr"), xreso=64, yreso=64, pfilter=K.FILTER_NONE, progressive=1)
+    engine.set_scene(sc); engine.set_camera(cam)
+    radii = P.radius_schedule(0.2, 4)
+    engine.accum_reset()
+    imgs = []
+    for p in range(4):
+        engine.iteration(SEED, 20 + p, 20000, radii[p] ** 2, uc=True)
+        imgs.append(engine.pass_image())
+    engine.accum_reset()
+    engine.iterate(SEED, 20, 4, 20000, radii ** 2, uc=True)
+    acc, n = engine.accum_read()
+    assert n == 4 and np.array_equal(engine.pass_image(), imgs[3])
+    assert np.array_equal(acc, (imgs[0] + imgs[2]) + (imgs[1] + imgs[3]))
+    engine.set_scene(small)
+    engine.accum_reset()
+    engine.iterate(SEED, 20, 2, 20000, radii[:2] ** 2, uc=True)
+    small_img = engine.pass_image()
+    assert not np.array_equal(small_img, imgs[1])
+    engine.set_scene(sc)
+    engine.accum_reset()
+    engine.iterate(SEED, 20, 2, 20000, radii[:2] ** 2, uc=True)
+    assert np.array_equal(engine.pass_image(), imgs[1])
+    engine.set_scene(small)
