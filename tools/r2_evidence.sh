@@ -22,4 +22,9 @@ for tool in memcheck racecheck initcheck; do
   timeout 900 compute-sanitizer --tool $tool python tools/sanitize_small.py 2>&1 | tail -6 >> $O/r2_sanitize.txt
 done
 timeout 600 python tools/soak.py > $O/r2_soak.txt 2>&1
+# BVH path: traversal throughput / pass times up to 1 M triangles, launch list and ncu --set full of a mesh-scene pass
+timeout 600 python tools/bvh_bench.py --sizes 16x32,64x128,256x512,512x1024 > $O/r2_bvh_bench.txt 2>&1
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/r2_bvh_launches.csv python tools/ncu_pass_bvh.py > /dev/null 2>&1
+python tools/launch_summary.py $O/r2_bvh_launches.csv > $O/r2_bvh_launch_summary.txt
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_direct_light|k_eye_expand|k_dl_classify|k_trace_photons' --launch-skip 8 --launch-count 4 -o $O/r2_bvh_full python tools/ncu_pass_bvh.py > $O/r2_bvh_ncu.log 2>&1
 ls -la $O/r2_*
