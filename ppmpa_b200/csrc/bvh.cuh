@@ -41,8 +41,11 @@ __device__ __forceinline__ void bvh_leaf(const DevScene& sc, uint32_t ref, D3 po
 }
 
 // Tests the bounded primitives the ray can reach and folds them into (best_t, best_o) -- best_o < 0: no candidate yet.
-__device__ __forceinline__ void bvh_traverse(const DevScene& sc, D3 pos, D3 dir, double& best_t, int& best_o) {
+// any_t2 >= 0 (shadow rays): the walk may stop at the first candidate with t^2 < any_t2 -- the caller only asks whether
+// the nearest hit is nearer than that, and the nearest hit is at most as far as any candidate.
+__device__ __forceinline__ void bvh_traverse(const DevScene& sc, D3 pos, D3 dir, double& best_t, int& best_o, double any_t2 = -1.0) {
   if (!sc.bvh) return;
+  if (best_o >= 0 && best_t * best_t < any_t2) return;
   // 1/d, with |1/d| capped at 1e300 so that a ray parallel to an axis keeps a finite o * (1/d): its slab then
   // evaluates to -+huge on the two sides of the origin, as it should, instead of inf - inf
   const D3 inv = mk3(bvh_inv(dir.x), bvh_inv(dir.y), bvh_inv(dir.z));
@@ -54,6 +57,7 @@ __device__ __forceinline__ void bvh_traverse(const DevScene& sc, D3 pos, D3 dir,
   for (;;) {
     if (cur & PPM_BVH_LEAF) {
       bvh_leaf(sc, cur, pos, dir, best_t, best_o);
+      if (best_o >= 0 && best_t * best_t < any_t2) return;
     } else {
       const double2* q = reinterpret_cast<const double2*>(sc.bvh + cur);
       double box[12];

@@ -273,12 +273,17 @@ __device__ __forceinline__ bool nearest_hit(const DevScene& sc, D3 pos, D3 dir, 
 // Shadow ray of a scene in BVH mode: what `illuminated` (tracer.rs:272-290) consumes of calc_intersection, over the planes
 // in `pm` (indices into the constant list) and, when `walk`, the hierarchy.
 // Returns 0 = no candidate, 1 = hit (hit_pos set), 2 = calc_intersection is None because get_normal failed.
-__device__ __forceinline__ int nearest_hit_masked_bvh(const DevScene& sc, D3 pos, D3 dir, const PrimMasks& pm, bool walk, D3& hit_pos) {
+// occl_t2: `illuminated` only asks whether sq_ldist - |hit - p|^2 > 0.002 for the NEAREST hit (dir is a unit vector,
+// so |hit - p| = t).  A candidate with t^2 < occl_t2 = (sq_ldist - 0.002)(1 - 1e-6) already says yes, for itself and
+// for whatever is nearer (the 1e-6 margin is ten orders above the rounding of |hit - p|^2): the walk stops there and the
+// caller reaches the same verdict with this candidate's position as it would with the nearest one's.
+__device__ __forceinline__ int nearest_hit_masked_bvh(const DevScene& sc, D3 pos, D3 dir, const PrimMasks& pm, bool walk, double occl_t2,
+                                                      D3& hit_pos) {
   double best_t = 0.0;
   int best_o = -1;
   scan_prims(sc, pm, pos, dir, best_t, best_o);
   if (best_o >= 0) best_o = sc.unb_obj[best_o];
-  if (walk) bvh_traverse(sc, pos, dir, best_t, best_o);
+  if (walk) bvh_traverse(sc, pos, dir, best_t, best_o, occl_t2);
   if (best_o < 0) return 0;
   hit_pos = pos + dir * best_t;
   const ppm_prim& s = sc.gprims[best_o];

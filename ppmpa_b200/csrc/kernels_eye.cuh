@@ -606,7 +606,7 @@ k_direct_light(const __grid_constant__ DevScene sc, PassDev* ps, uint32_t cap, c
         }
         if (need_ld) {
           D3 hp;
-          const int hit = BVH ? nearest_hit_masked_bvh(sc, p, ld, pm, walk, hp) : nearest_hit_masked(sc, p, ld, pm, hp);
+          const int hit = BVH ? nearest_hit_masked_bvh(sc, p, ld, pm, walk, (dd - 0.002) * (1.0 - 1e-6), hp) : nearest_hit_masked(sc, p, ld, pm, hp);
           if (hit == 1) {
             const D3 po = hp - p;
             if (dd - dot(po, po) > 0.002) continue;

@@ -303,3 +303,17 @@ def test_bvh_two_lanes_equal_sequential_and_scene_switch(engine):
     engine.iterate(SEED, 20, 2, 20000, radii[:2] ** 2, uc=True)
     assert np.array_equal(engine.pass_image(), imgs[1])
     engine.set_scene(small)
+
+
+@pytest.mark.parametrize("material", [GLASS, WALL])
+def test_bvh_trace_rays_classic_parity(engine, oracle, material):
+    """trace_ray_classic (tracer.rs:221-259, the `rtc` renderer) through the hierarchy: deterministic given the rays."""
+    sc, _ = mesh_scene(material=material)
+    cam = P.read_camera(os.path.join(EX, "screen1.scr"), xreso=64, yreso=64)
+    engine.set_scene(sc); engine.set_camera(cam)
+    rays = oracle.generate_rays(cam, 3, 0)
+    g = engine.trace_rays_classic(rays, 3, 0)
+    o = oracle.trace_rays_classic(sc, list(cam.ambient), rays)
+    assert o.max() > 0
+    assert_rel(g, o, 1e-12)
+    engine.set_scene(load_scene("ex-glassbox"))
