@@ -318,6 +318,15 @@ int  ppm_pass_image_read(ppm_ctx* ctx, double* rgb3_h_or_d);
 /* accumulator: sum over passes + number of passes summed */
 int  ppm_accum_reset(ppm_ctx* ctx);
 int  ppm_accum_read(ppm_ctx* ctx, double* rgb3_h_or_d, uint32_t* n_pass);
+/* Checkpoint / resume of a frame in progress.  The reference's pass images are files, so a killed job keeps what it
+ * rendered and util/averager2.rb:49-62 sums whatever is there; here the sums live on the device:
+ *   ppm_accum_add   adds a sum image (as ppm_accum_read returns it) and its pass count to the accumulator
+ *   ppm_accum_save  writes ["PPMACC1\n", xreso, yreso, n_pass, 0 (u32 each), 3*W*H f64] atomically (temp file + rename)
+ *   ppm_accum_load  ADDS such a file to the accumulator (PPM_ERR_ARG if its resolution is not the camera's,
+ *                   PPM_ERR_PARSE if it is not a checkpoint); n_pass (may be NULL) = the passes it held */
+int  ppm_accum_add(ppm_ctx* ctx, const double* rgb3_h_or_d, uint32_t n_pass);
+int  ppm_accum_save(ppm_ctx* ctx, const char* path);
+int  ppm_accum_load(ppm_ctx* ctx, const char* path, uint32_t* n_pass);
 /* raw device pointers of the accumulator (3*W*H doubles) and pass counter
  * (1 double, so both reduce in one dtype).  The pointers stay valid until the
  * camera resolution changes or the ctx is destroyed. */

@@ -123,6 +123,9 @@ SIGNATURES = {
     "ppm_pass_image_read": (C.c_int, [vp, vp]),
     "ppm_accum_reset": (C.c_int, [vp]),
     "ppm_accum_read": (C.c_int, [vp, vp, P(u32)]),
+    "ppm_accum_add": (C.c_int, [vp, vp, u32]),
+    "ppm_accum_save": (C.c_int, [vp, C.c_char_p]),
+    "ppm_accum_load": (C.c_int, [vp, C.c_char_p, P(u32)]),
     "ppm_accum_device": (C.c_int, [vp, P(vp), P(vp), P(u64)]),
     "ppm_image_mean": (C.c_int, [vp, vp]),
     "ppm_comm_unique_id": (C.c_int, [vp]),

@@ -1693,6 +1693,68 @@ int ppm_accum_reset(ppm_ctx* c) {
   return PPM_OK;
 }
 
+// Checkpoint / resume.  The reference's pass images are files (util/iterator.rb:96-117), so a killed job keeps what it has
+// rendered and averager2.rb:49-62 sums whatever is there; here the sums live on the device, so they can be taken out
+// (ppm_accum_read / ppm_accum_save) and put back (ppm_accum_add / ppm_accum_load) -- also how pass sums rendered
+// elsewhere are merged into a frame.
+int ppm_accum_add(ppm_ctx* c, const double* rgb3, uint32_t n_pass) {
+  if (!c || !rgb3) return PPM_ERR_ARG;
+  if (!c->have_camera) return fail(c, PPM_ERR_STATE, "camera not set");
+  CK(c, cudaSetDevice(c->device));
+  RC(ensure_accum(c));
+  const void* dsrc;
+  RC(stage_in(c, rgb3, (size_t)c->accum_pixels * 24, c->st_in0, &dsrc));
+  const int64_t n = (int64_t)c->accum_pixels * 3;
+  k_accum_add<<<nblk(n, 256), 256, 0, c->stream>>>(c->accum.as<double>(), (const double*)dsrc, n, (double)n_pass);
+  KCHECK(c);
+  CK(c, cudaStreamSynchronize(c->stream));
+  return PPM_OK;
+}
+namespace {
+struct AccFileHeader { char magic[8]; uint32_t xreso, yreso, n_pass, _pad; };
+const char kAccMagic[8] = {'P', 'P', 'M', 'A', 'C', 'C', '1', '\n'};
+}
+int ppm_accum_save(ppm_ctx* c, const char* path) {
+  if (!c || !path) return PPM_ERR_ARG;
+  if (!c->accum.p || !c->accum_pixels) return fail(c, PPM_ERR_STATE, "no accumulator yet");
+  std::vector<double> sum((size_t)c->accum_pixels * 3);
+  uint32_t n = 0;
+  RC(ppm_accum_read(c, sum.data(), &n));
+  AccFileHeader h;
+  std::memcpy(h.magic, kAccMagic, 8);
+  h.xreso = (uint32_t)c->cam.xreso; h.yreso = (uint32_t)c->cam.yreso; h.n_pass = n; h._pad = 0;
+  // written beside the target and renamed: a job killed while saving leaves the previous checkpoint intact
+  const std::string tmp = std::string(path) + ".tmp";
+  FILE* f = std::fopen(tmp.c_str(), "wb");
+  if (!f) return fail(c, PPM_ERR_IO, std::string("cannot write ") + tmp);
+  bool ok = std::fwrite(&h, sizeof h, 1, f) == 1 && std::fwrite(sum.data(), 8, sum.size(), f) == sum.size();
+  ok = (std::fclose(f) == 0) && ok;
+  if (!ok || std::rename(tmp.c_str(), path) != 0) { std::remove(tmp.c_str()); return fail(c, PPM_ERR_IO, std::string("cannot write ") + path); }
+  return PPM_OK;
+}
+int ppm_accum_load(ppm_ctx* c, const char* path, uint32_t* n_pass) {
+  if (!c || !path) return PPM_ERR_ARG;
+  if (!c->have_camera) return fail(c, PPM_ERR_STATE, "camera not set");
+  FILE* f = std::fopen(path, "rb");
+  if (!f) return fail(c, PPM_ERR_IO, std::string("cannot read ") + path);
+  AccFileHeader h;
+  std::vector<double> sum;
+  bool ok = std::fread(&h, sizeof h, 1, f) == 1 && std::memcmp(h.magic, kAccMagic, 8) == 0;
+  if (ok && (h.xreso != (uint32_t)c->cam.xreso || h.yreso != (uint32_t)c->cam.yreso)) {
+    std::fclose(f);
+    return fail(c, PPM_ERR_ARG, "checkpoint resolution differs from the camera's");
+  }
+  if (ok) {
+    sum.resize((size_t)h.xreso * h.yreso * 3);
+    ok = std::fread(sum.data(), 8, sum.size(), f) == sum.size();
+  }
+  std::fclose(f);
+  if (!ok) return fail(c, PPM_ERR_PARSE, std::string("not an accumulator checkpoint: ") + path);
+  RC(ppm_accum_add(c, sum.data(), h.n_pass));
+  if (n_pass) *n_pass = h.n_pass;
+  return PPM_OK;
+}
+
 int ppm_accum_read(ppm_ctx* c, double* rgb3, uint32_t* n_pass) {
   if (!c) return PPM_ERR_ARG;
   if (!c->accum.p || !c->accum_pixels) return fail(c, PPM_ERR_STATE, "no accumulator yet");

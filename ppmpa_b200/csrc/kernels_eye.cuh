@@ -659,6 +659,12 @@ __global__ void k_accum_merge(double* __restrict__ acc, double* __restrict__ oth
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) { acc[i] += other[i]; other[i] = 0.0; }
 }
+// acc[0..n) += src; the pass counter acc[n] += npass   (ppm_accum_add: a saved sum image put back)
+__global__ void k_accum_add(double* __restrict__ acc, const double* __restrict__ src, int64_t n, double npass) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) acc[i] += src[i];
+  if (i == 0) acc[n] += npass;
+}
 __global__ void k_scale(const double* __restrict__ in, const double* __restrict__ npass, int64_t n, double* __restrict__ out) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = in[i] / npass[0];

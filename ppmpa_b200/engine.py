@@ -319,6 +319,18 @@ class Engine:
         self._ck(lib.ppm_accum_read(self._h, _ptr(out), C.byref(n)))
         return out, n.value
 
+    def accum_add(self, rgb3, n_pass):
+        """Adds a sum image (as accum_read returns it) and its pass count: resume / merge (averager2.rb:49-62)."""
+        self._ck(lib.ppm_accum_add(self._h, _ptr(_f64(rgb3, (3,))), int(n_pass)))
+
+    def accum_save(self, path):
+        self._ck(lib.ppm_accum_save(self._h, str(path).encode()))
+
+    def accum_load(self, path):
+        n = C.c_uint32()
+        self._ck(lib.ppm_accum_load(self._h, str(path).encode(), C.byref(n)))
+        return n.value
+
     def accum_device(self):
         """(device pointer, number of doubles) of [sum image | pass count]."""
         p = C.c_void_p(); q = C.c_void_p(); n = C.c_uint64()

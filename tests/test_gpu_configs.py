@@ -191,3 +191,63 @@ def test_two_gpu_frame_nccl_reduce(tmp_path):
     assert int(z["n_reduced"]) == int(z["n_single"]) == 6
     assert np.allclose(z["reduced"], z["single"], rtol=1e-13, atol=0.0)
     assert z["reduced"].max() > 0
+
+
+def test_accumulator_checkpoint_and_resume(engine, tmp_path):
+    """ppm_accum_add / ppm_accum_save / ppm_accum_load: a frame interrupted after two passes and resumed from the
+    checkpoint equals the frame rendered in one go (the reference keeps every pass as a file, util/iterator.rb:96-117,
+    and averager2.rb:49-62 sums whatever is there)."""
+    import ppmpa_b200 as P
+    from ppmpa_b200 import _capi as K
+    sc = P.read_scene(os.path.join(EX, "ex-glassbox.scene"))
+    cam = P.read_camera(os.path.join(EX, "camera0.scr"), xreso=48, yreso=40, pfilter=K.FILTER_NONE, progressive=1)
+    engine.set_scene(sc); engine.set_camera(cam)
+    radii = P.radius_schedule(0.2, 5)
+    engine.set_option("lanes", 1)
+    try:
+        engine.accum_reset()
+        engine.iterate(0x5EED0001, 0, 5, 20000, radii ** 2, uc=True)
+        whole, n = engine.accum_read()
+        assert n == 5
+        engine.accum_reset()
+        engine.iterate(0x5EED0001, 0, 2, 20000, radii[:2] ** 2, uc=True)
+        part, n2 = engine.accum_read()
+        ck = tmp_path / "frame.acc"
+        engine.accum_save(ck)
+        assert os.path.getsize(ck) == 24 + 48 * 40 * 3 * 8 and not os.path.exists(str(ck) + ".tmp")
+        engine.accum_reset()                                  # "the job was killed"
+        assert engine.accum_load(ck) == 2
+        engine.iterate(0x5EED0001, 2, 3, 20000, radii[2:] ** 2, uc=True)
+        resumed, n3 = engine.accum_read()
+        assert n3 == 5 and np.array_equal(resumed, whole)     # one lane: the same additions in the same order
+        # accum_add: merging sums rendered elsewhere
+        engine.accum_reset()
+        engine.accum_add(part, n2)
+        engine.accum_add(part, n2)
+        twice, n4 = engine.accum_read()
+        assert n4 == 4 and np.array_equal(twice, part + part)
+        # a checkpoint of another resolution is refused, a file that is not a checkpoint too
+        engine.set_camera(P.read_camera(os.path.join(EX, "camera0.scr"), xreso=32, yreso=32))
+        with pytest.raises(P.PPMError):
+            engine.accum_load(ck)
+        bad = tmp_path / "bad.acc"
+        bad.write_bytes(b"P3\n1 1\n255\n0 0 0\n" * 4)
+        with pytest.raises(P.PPMError):
+            engine.accum_load(bad)
+    finally:
+        engine.set_option("lanes", 2)
+
+
+def test_ppmpa_frame_resumes_from_a_checkpoint(tmp_path):
+    """ppmpa_frame -r: two instalments of three passes write the picture of one run of six."""
+    import subprocess
+    frame = os.path.join(ROOT, "ppmpa_b200", "bin", "ppmpa_frame")
+    env = dict(os.environ, PPM_SEED="7", PPM_LANES="1")
+    args = ["20000", "0.15", os.path.join(EX, "screen1.scr"), os.path.join(EX, "mirror-ball.scene")]
+    whole, part, ck = tmp_path / "whole.ppm", tmp_path / "part.ppm", tmp_path / "frame.acc"
+    subprocess.run([frame, "6"] + args + [str(whole)], check=True, env=env, capture_output=True)
+    r1 = subprocess.run([frame, "-r", str(ck), "3"] + args + [str(part)], check=True, env=env, capture_output=True)
+    assert b"resuming" not in r1.stderr and os.path.exists(ck)
+    r2 = subprocess.run([frame, "-r", str(ck), "3"] + args + [str(part)], check=True, env=env, capture_output=True)
+    assert b"resuming after 3 passes" in r2.stderr and b"6 passes" in r2.stderr
+    assert open(whole).read() == open(part).read()
