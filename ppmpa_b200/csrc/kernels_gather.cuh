@@ -31,6 +31,9 @@ __device__ __forceinline__ double filter_gauss(double d, double rmax) {
 #ifndef GATHER_WARPS
 #define GATHER_WARPS 4
 #endif
+#ifndef GATHER_YSPAN
+#define GATHER_YSPAN 2       // ... and rows cy .. cy+2 of one z layer
+#endif
 #ifndef GATHER_SPAN
 #define GATHER_SPAN 4        // a group may span cells cx .. cx+4 of one row (3: logical 0.586 -> 0.596 over the north-star schedule, 5: 0.596)
 #endif
@@ -63,9 +66,13 @@ struct HeavyList {
 // (cx, cy, cz) = cell coordinates of the group's leader, xlast = x coordinate of its last cell: the callers keep the
 // coordinates of their own query's cell in registers (three integer divisions per QUERY instead of five per GROUP: at
 // small radius a warp forms several groups and the divisions were 11 % of the kernel's instructions)
-__device__ __forceinline__ uint32_t gather_group_runs(const Grid& g, const CellIndex& ix, int cx, int cy, int cz, int xlast,
+// ylast = y coordinate of the group's last row (cy for a single-row group): the stream then covers the rows
+// cy - 1 .. ylast + 1 of the three z layers, z-major, y next, x fastest -- the order of the sorted map, so every query
+// still meets the photons of its own 27 cells in the same order whatever group it was served in.
+__device__ __forceinline__ uint32_t gather_group_runs(const Grid& g, const CellIndex& ix, int cx, int cy, int cz, int xlast, int ylast,
                                                       int lane, uint32_t* sEnd, uint32_t* sOff) {
-  constexpr int REACH = 1, W = 2 * REACH + 1, ROWS = W * W;
+  constexpr int REACH = 1;
+  const int W = ylast - cy + 2 * REACH + 1, ROWS = (2 * REACH + 1) * W;      // <= 32 (GATHER_YSPAN <= 7)
   const unsigned FULL = 0xffffffffu;
   const int x0 = max(cx - REACH, 0), x1 = min(xlast + REACH, g.nx - 1);
   uint32_t rbeg = 0, rlen = 0;
@@ -187,17 +194,20 @@ k_gather(PassDev* ps, CellIndex ix, MapSoA m, const uint32_t* __restrict__ qkey,
   while (pending) {
     const int leader = __ffs(pending) - 1;
     const uint32_t ck = __shfl_sync(FULL, key, leader);
-    const uint32_t row_l = __shfl_sync(FULL, qrow, leader);
     const int cx = __shfl_sync(FULL, qcx, leader), cy = __shfl_sync(FULL, qcy, leader), cz = __shfl_sync(FULL, qcz, leader);
     // Group = the pending lanes whose cell lies in the leader's row (same cy, cz) at most
     // GATHER_SPAN cells to the right of the leader's cell (keys are sorted, x fastest).  They
     // share ONE candidate stream covering [cx_leader - R, cx_last + R]: a superset of every
     // lane's own neighbourhood, so the extra candidates simply fail the distance test.
-    bool act = valid && key >= ck && key - ck <= (uint32_t)GATHER_SPAN && qrow == row_l;
+    // ... and, since a surface that is one cell thick in x (a wall facing x) leaves a single cell per row, the
+    // cells of up to GATHER_YSPAN further rows of the same z layer in the same x range.
+    // (groups are no longer contiguous key ranges: a lane served with an earlier leader must not be served again)
+    bool act = ((pending >> lane) & 1u) != 0u && qcz == cz && qcy >= cy && qcy - cy <= GATHER_YSPAN && qcx >= cx && qcx - cx <= GATHER_SPAN;
     unsigned grp = __ballot_sync(FULL, act);
     const int last = 31 - __clz((int)grp);
-    uint32_t klast = __shfl_sync(FULL, key, last);
-    uint32_t total = gather_group_runs(g, ix, cx, cy, cz, __shfl_sync(FULL, qcx, last), lane, sEnd[warp], sOff[warp]);
+    uint32_t klast = __shfl_sync(FULL, key, last);        // keys are sorted: != ck iff the group has more than one cell
+    const int xlast = __reduce_max_sync(FULL, act ? qcx : cx), ylast = __reduce_max_sync(FULL, act ? qcy : cy);
+    uint32_t total = gather_group_runs(g, ix, cx, cy, cz, xlast, ylast, lane, sEnd[warp], sOff[warp]);
     if (hl.ctr && total > GATHER_HEAVY_MIN && klast != ck) {
       // A heavy stream is split into parts by its length, and the parts fix the order in which a query's photons are
       // summed.  Narrow the group to the leader's cell alone: the stream, its split and therefore every sum then
@@ -206,7 +216,7 @@ k_gather(PassDev* ps, CellIndex ix, MapSoA m, const uint32_t* __restrict__ qkey,
       act = valid && key == ck;
       grp = __ballot_sync(FULL, act);
       klast = ck;
-      total = gather_group_runs(g, ix, cx, cy, cz, cx, lane, sEnd[warp], sOff[warp]);
+      total = gather_group_runs(g, ix, cx, cy, cz, cx, cy, lane, sEnd[warp], sOff[warp]);
     }
     pending &= ~grp;
     if (hl.ctr && total > GATHER_HEAVY_MIN) {
@@ -290,7 +300,7 @@ k_gather_heavy(PassDev* ps, CellIndex ix, MapSoA m, const uint32_t* __restrict__
     }
     const uint32_t hnx = (uint32_t)g.nx, hny = (uint32_t)g.ny;
     const uint32_t total = gather_group_runs(g, ix, (int)(h_ck % hnx), (int)((h_ck / hnx) % hny), (int)(h_ck / (hnx * hny)), (int)(h_klast % hnx),
-                                             lane, sEnd[warp], sOff[warp]);
+                                             (int)((h_klast / hnx) % hny), lane, sEnd[warp], sOff[warp]);
     double ar = 0.0, ag = 0.0, ab = 0.0;
     uint32_t ac = 0;
     const uint32_t staged = gather_chunks<FILTER, MODE>(m, total, (t - h_p0) * 32u, h_np * 32u, lane, hact, sEnd[warp], sOff[warp], sP[warp],
