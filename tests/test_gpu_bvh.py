@@ -319,10 +319,13 @@ def test_bvh_trace_rays_classic_parity(engine, oracle, material):
     engine.set_scene(load_scene("ex-glassbox"))
 
 
-@pytest.mark.parametrize("seed,scale", [(1, 1.0), (2, 1.0), (3, 1e-3), (4, 1e3), (5, 1.0), (6, 37.5)])
-def test_bvh_random_scenes_match_bruteforce_and_oracle(engine, oracle, seed, scale):
+@pytest.mark.parametrize("seed,scale,offset", [(1, 1.0, 0.0), (2, 1.0, 0.0), (3, 1e-3, 0.0), (4, 1e3, 0.0), (5, 1.0, 0.0),
+                                               (6, 37.5, 0.0), (7, 1.0, 1e5), (8, 0.01, -3e3)])
+def test_bvh_random_scenes_match_bruteforce_and_oracle(engine, oracle, seed, scale, offset):
     """Random soups of overlapping triangles, parallelograms (some needle-thin), spheres (some nested) and tilted
-    planes at scene scales from 1e-3 to 1e3: the hierarchy must return the scan's hit for every ray."""
+    planes at scene scales from 1e-3 to 1e3, also far from the origin (coordinates 1e5 x the scene's size: the hit
+    arithmetic loses 5 digits there, the padded boxes must still hold every accepted hit): the hierarchy must return
+    the scan's hit for every ray."""
     import ctypes as C
     rng = np.random.default_rng(seed)
     base = load_scene("ex-glassbox")
@@ -334,26 +337,26 @@ def test_bvh_random_scenes_match_bruteforce_and_oracle(engine, oracle, seed, sca
             prims.append(q)
 
     for _ in range(34):
-        c = rng.uniform(-2, 2, 3) * scale
+        c = rng.uniform(-2, 2, 3) * scale + offset
         e = rng.normal(size=(2, 3)) * scale * rng.choice([1.0, 0.3, 1e-3])          # 1e-3: needles
         poly(c, c + e[0], c + e[1], rng.random() < 0.3)
     for _ in range(8):
         q = K.Prim()
-        K.lib.ppm_prim_sphere(C.byref(q), K.D3(*(rng.uniform(-1, 1, 3) * scale)), float(rng.uniform(0.05, 1.5) * scale), 0)
+        K.lib.ppm_prim_sphere(C.byref(q), K.D3(*(rng.uniform(-1, 1, 3) * scale + offset)), float(rng.uniform(0.05, 1.5) * scale), 0)
         prims.append(q)
     for _ in range(4):
         q = K.Prim()
         n = rng.normal(size=3)
-        K.lib.ppm_prim_plain(C.byref(q), K.D3(*n), float(rng.uniform(1, 4) * scale), 0)
+        K.lib.ppm_prim_plain(C.byref(q), K.D3(*n), float(rng.uniform(1, 4) * scale - n.sum() * offset), 0)
         prims.append(q)
     order = rng.permutation(len(prims))                      # planes in between the bounded primitives
     arr = (K.Prim * len(prims))(*[prims[i] for i in order])
     sc = synth.ArrayScene(arr, base.mats, base.lights)
     sc.nmats, sc.nlights = base.nmats, base.nlights
     assert 40 <= sc.nprims <= 64
-    o = rng.uniform(-3, 3, size=(30000, 3)) * scale
+    o = rng.uniform(-3, 3, size=(30000, 3)) * scale + offset
     d = rng.normal(size=(30000, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
-    aimed = (rng.uniform(-2, 2, size=(15000, 3)) * scale) - o[:15000]                # towards the cluster
+    aimed = (rng.uniform(-2, 2, size=(15000, 3)) * scale + offset) - o[:15000]       # towards the cluster
     d[:15000] = aimed / np.linalg.norm(aimed, axis=1, keepdims=True)
     rays = np.concatenate([o, d], axis=1)
     engine.set_scene(sc)
