@@ -97,6 +97,21 @@ __device__ __forceinline__ uint32_t gather_group_runs(const Grid& g, const CellI
   __syncwarp();
   return total;
 }
+// one member photon's contribution: filter weight x photon_to_radiance (optics.rs:224-233), into its wavelength's channel
+template <int FILTER>
+__device__ __forceinline__ void gather_accept(double d2, double r2, double2 c, double2 d, int w, D3 nv, double power,
+                                              double& rr, double& rg, double& rb) {
+  const double wt = FILTER == PPM_FILTER_NONE ? 1.0 : (FILTER == PPM_FILTER_CONE ? filter_cone(d2, r2) : filter_gauss(d2, r2));
+  const double cos0 = (nv.x * c.x + nv.y * c.y) + nv.z * d.x;
+  const double pw2 = cos0 < 0.0 ? (wt * power) * -cos0 : 0.0;
+  if (w == 0) rr = rr + pw2; else if (w == 1) rg = rg + pw2; else rb = rb + pw2;
+}
+#ifndef GATHER_LAZYWL
+#define GATHER_LAZYWL 1      // the wavelength word of an accepted candidate is read again from shared memory instead of kept
+#endif
+#ifndef GATHER_UNROLL
+#define GATHER_UNROLL 6      // candidates per trip of the test loop (1: 0.560, 2: 0.550 ms at r = 0.0189; profiles/r2_gather_unroll.txt)
+#endif
 // chunks base = first, first + stride, ... of the candidate stream: stage 32 candidates, test them against the lane's query
 // returns the number of candidates staged (warp-uniform)
 template <int FILTER, int MODE>
@@ -121,7 +136,39 @@ __device__ __forceinline__ uint32_t gather_chunks(const MapSoA& m, uint32_t tota
     const int mcount = (int)min(32u, total - base);
     staged += (uint32_t)mcount;
     if (act) {
-      for (int t = 0; t < mcount; ++t) {
+      int t = 0;
+#if GATHER_UNROLL > 1
+      // GATHER_UNROLL candidates per trip: their distance chains are independent (the accept blocks still run in stream
+      // order, so every query adds its photons in the same order)
+      for (; t + GATHER_UNROLL <= mcount; t += GATHER_UNROLL) {
+        double d2u[GATHER_UNROLL];
+#if !GATHER_LAZYWL
+        double wlu[GATHER_UNROLL];
+#endif
+#pragma unroll
+        for (int u = 0; u < GATHER_UNROLL; ++u) {
+          const double2 a = sP[t + u][0], b = sP[t + u][1];
+          const double ax = qx - a.x, ay = qy - a.y, az = qz - b.x;
+          d2u[u] = (ax * ax + ay * ay) + az * az;
+#if !GATHER_LAZYWL
+          wlu[u] = b.y;
+#endif
+        }
+#pragma unroll
+        for (int u = 0; u < GATHER_UNROLL; ++u) {
+          if (d2u[u] <= r2) {
+            ++cnt;
+#if GATHER_LAZYWL
+            const double wl = sP[t + u][1].y;
+#else
+            const double wl = wlu[u];
+#endif
+            if (MODE != 2) gather_accept<FILTER>(d2u[u], r2, sD[t + u][0], sD[t + u][1], (int)__double_as_longlong(wl), nv, power, rr, rg, rb);
+          }
+        }
+      }
+#endif
+      for (; t < mcount; ++t) {
         const double2 a = sP[t][0], b = sP[t][1];
         // squared_euclidean: ((qx-px)^2 + (qy-py)^2) + (qz-pz)^2, member iff d2 <= r2
         const double ax = qx - a.x, ay = qy - a.y, az = qz - b.x;
@@ -129,13 +176,7 @@ __device__ __forceinline__ uint32_t gather_chunks(const MapSoA& m, uint32_t tota
         if (d2 <= r2) {
           ++cnt;
           if (MODE == 2) continue;
-          const double wt = FILTER == PPM_FILTER_NONE ? 1.0 : (FILTER == PPM_FILTER_CONE ? filter_cone(d2, r2) : filter_gauss(d2, r2));
-          const double2 c = sD[t][0], d = sD[t][1];
-          // photon_to_radiance, optics.rs:224-233
-          const double cos0 = (nv.x * c.x + nv.y * c.y) + nv.z * d.x;
-          const double pw2 = cos0 < 0.0 ? (wt * power) * -cos0 : 0.0;
-          const int w = (int)__double_as_longlong(b.y);
-          if (w == 0) rr = rr + pw2; else if (w == 1) rg = rg + pw2; else rb = rb + pw2;
+          gather_accept<FILTER>(d2, r2, sD[t][0], sD[t][1], (int)__double_as_longlong(b.y), nv, power, rr, rg, rb);
         }
       }
     }
