@@ -480,6 +480,11 @@ __device__ __forceinline__ double ts5(unsigned i) {   // the literals 0.1, 0.3, 
 #ifndef PPM_DL_MINB
 #define PPM_DL_MINB 8
 #endif
+#ifndef PPM_DL_UNROLL
+#define PPM_DL_UNROLL 5      // samples per trip of the straight-line loop: 1 / 3 / 5 / 25 -> 930 / 893 / 867 / 950 us (profiles/r2_dl_straight_unroll.txt)
+#endif
+#define PPM_PRAGMA_(x) _Pragma(#x)
+#define PPM_UNROLL(n) PPM_PRAGMA_(unroll n)
 #ifndef PPM_DL_STRAIGHT
 #define PPM_DL_STRAIGHT 1
 #endif
@@ -559,7 +564,7 @@ k_direct_light(const __grid_constant__ DevScene sc, PassDev* ps, uint32_t cap, c
         // No node of the warp has a primitive to test (two thirds of the warps in cell-sorted order): the same samples,
         // decisions and operations as the loop below, but as straight-line selects, so that the reciprocal chains of
         // consecutive samples overlap instead of waiting behind the `continue` branches.
-#pragma unroll 5
+PPM_UNROLL(PPM_DL_UNROLL)
         for (unsigned s = 0; s < 25; ++s) {
           const D3 d = mk3(s_gp[s][0], s_gp[s][1], s_gp[s][2]) - p;
           const double dd = dot(d, d);
