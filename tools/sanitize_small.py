@@ -40,5 +40,24 @@ hq = np.zeros((100, 3)); hq[:, 0] = rng.uniform(-0.1, 0.1, 100)
 g, cnt = eng.estimate_radiance(hq, nrm[:100], 2)
 assert cnt.max() > 4000
 eng.estimate_radiance_knn(hq, nrm[:100], 50, 0)
+# BVH mode: a 221-triangle mesh + spheres (hierarchy, shaft classification, any-hit shadow rays), then the forced mode
+# on a small scene, then back; checkpoint add
+from ppmpa_b200 import synth
+base = P.read_scene(os.path.join(EX, "ex-glassbox.scene"))
+mesh = synth.mesh_scene(base, synth.uv_sphere_triangles((0.3, 2.6, 1.0), 0.7, 8, 16), 4, spheres=[((-1.0, 0.5, 1.0), 0.4)])
+eng.set_scene(mesh)
+eng.accum_reset()
+eng.iteration(1, 0, 3000, 0.3 ** 2, True)
+eng.iterate(1, 1, 2, 3000, [0.09, 0.08], uc=False)
+eng.calc_intersection(rays)
+eng.trace_rays_classic(rays, 1, 0)
+eng.direct_light(q, nrm)
+eng.set_option("bvh", 1)
+eng.set_scene(base)
+eng.iteration(1, 5, 3000, 0.2 ** 2, True)
+eng.set_option("bvh", 0)
+eng.set_scene(base)
+acc, n = eng.accum_read()
+eng.accum_add(acc, n)
 print("sanitize run ok", float(img.sum()))
 eng.close()
