@@ -368,3 +368,39 @@ def test_bvh_random_scenes_match_bruteforce_and_oracle(engine, oracle, seed, sca
     assert_hits_equal(walked, oracle.intersect(sc, rays))
     assert (walked[0] >= 0).mean() > 0.5
     engine.set_scene(base)
+
+
+def test_bvh_edge_scenes(engine, oracle):
+    """Planes only with the hierarchy forced (nothing to index), a Point primitive among the triangles (never hit,
+    calc_distance has no root for it), and more than 64 infinite planes (refused with PPM_ERR_CAPACITY, not indexed)."""
+    import ctypes as C
+    base = load_scene("ex-glassbox")
+    # planes only, forced
+    planes = synth.ArrayScene((K.Prim * 6)(*[base.prims[i] for i in range(6)]), base.mats, base.lights)
+    planes.nmats, planes.nlights = base.nmats, base.nlights
+    rays = random_rays(4000, 51)
+    with bvh_forced(engine):
+        engine.set_scene(planes)
+        assert_hits_equal(engine.calc_intersection(rays), oracle.intersect(planes, rays))
+        pos = rays[:500, :3].copy()
+        nrm = np.tile([0.0, 1.0, 0.0], (500, 1))
+        assert_rel(engine.direct_light(pos, nrm), oracle.direct_light(planes, pos, nrm), 1e-12)
+    # a Point primitive in a mesh scene
+    tris = synth.uv_sphere_triangles((0.3, 2.6, 1.0), 0.7, 8, 16)
+    sc = synth.mesh_scene(base, tris, WALL)
+    sc.prims[base.nprims + 5].type = K.SHAPE_POINT
+    engine.set_scene(sc)
+    g = engine.calc_intersection(rays)
+    assert_hits_equal(g, oracle.intersect(sc, rays))
+    assert not (g[0] == base.nprims + 5).any()
+    # 70 planes + 1 triangle: too many unbounded primitives for the constant list
+    many = (K.Prim * 71)()
+    for i in range(70):
+        K.lib.ppm_prim_plain(C.byref(many[i]), K.D3(0.0, 1.0, 0.0), float(i), 0)
+    many[70] = sc.prims[base.nprims]
+    bad = synth.ArrayScene(many, base.mats, base.lights)
+    bad.nmats, bad.nlights = base.nmats, base.nlights
+    with pytest.raises(P.PPMError) as e:
+        engine.set_scene(bad)
+    assert e.value.code == -4
+    engine.set_scene(base)
