@@ -17,7 +17,9 @@
 
 #define PPM_BVH_LEAF 0x80000000u          // child reference: leaf flag | (count - 1) << 28 | first BvhPrim slot
 #define PPM_BVH_NONE 0xFFFFFFFFu          // child reference: no child (a root with one leaf)
-#define PPM_BVH_LEAF_MAX 4u               // primitives per leaf
+#ifndef PPM_BVH_LEAF_MAX
+#define PPM_BVH_LEAF_MAX 2u               // primitives per leaf (1 / 2 / 3 / 4 / 8 swept: profiles/r2_bvh_leaf_sweep.txt; the child reference has 3 bits for the count)
+#endif
 #define PPM_BVH_STACK 64                  // traversal stack; the builder bounds the depth (PPM_BVH_SAH_DEPTH + log2 N)
 #define PPM_BVH_SAH_DEPTH 30              // below this depth splits are by SAH, beyond it by object median
 #define PPM_BVH_MAX_PRIMS (1u << 26)
